@@ -1,0 +1,171 @@
+/*
+ * ld_sampler.h -- C ABI of the B200-native LocalDiffusion sampler (libld_sampler.so).
+ *
+ * The reference (edshkim98/LocalDiffusion-Hallucination) has no FFI: its boundary for this
+ * path is two Python nn.Module APIs, `Unet.forward` (ddpm.py:404) and
+ * `GaussianDiffusion.sample` (ddpm.py:1078).  This header is the C-ABI those two calls are
+ * re-hosted on; the Python shims in `localdiffusion_hallucination_b200/` bind it with ctypes
+ * (see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative ld_status; nothing throws across the
+ *     ABI; `ld_last_error()` returns a thread-local, NUL-terminated description.
+ *   - tensors are plain pointers + sizes.  Images are dense NCHW fp32 with C == 1 (which is
+ *     byte-identical to NHWC), exactly what the reference passes around (ddpm.py:1121-1125).
+ *   - device pointers are borrowed for the duration of the call; all device work is enqueued on
+ *     the caller's `stream` (a cudaStream_t passed as void*); host-pointer entry points
+ *     (`*_host`) copy in/out themselves and synchronise the stream before returning.
+ *   - one handle per device; a handle is not thread-safe.
+ *   - there is no CPU fallback: every compute entry point fails with LD_ERR_NO_DEVICE when no
+ *     sm_100 device is usable.
+ */
+#ifndef LD_SAMPLER_H_
+#define LD_SAMPLER_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define LD_API __attribute__((visibility("default")))
+#else
+#define LD_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ld_handle ld_handle;
+
+typedef enum ld_status {
+  LD_OK = 0,
+  LD_ERR_INVALID = -1,   /* bad argument / shape contract (ddpm.py:405, 515-516, 536, 561) */
+  LD_ERR_NO_DEVICE = -2, /* no usable sm_100 CUDA device */
+  LD_ERR_CUDA = -3,      /* a CUDA call failed; see ld_last_error() */
+  LD_ERR_STATE = -4,     /* call order violated (weights missing, schedule missing, ...) */
+  LD_ERR_KEY = -5,       /* unknown / duplicate / wrongly-shaped state_dict key */
+  LD_ERR_MASK = -6       /* "mask should be binary" (ddpm.py:698) or fusion sanity (ddpm.py:790) */
+} ld_status;
+
+enum { LD_MAX_LEVELS = 8 };
+
+/* Arithmetic used for the dense contractions.  Statistics, residual stream of the sampler
+ * (x_t, x0, posterior) and accumulators are fp32 in both modes. */
+typedef enum ld_precision {
+  LD_PREC_FP32 = 0, /* fp32 storage + fp32 CUDA-core FMA: the parity path (rel err <= 1e-3) */
+  LD_PREC_BF16 = 1  /* bf16 storage + tcgen05 (fp32 accumulate in TMEM): the fast path      */
+} ld_precision;
+
+/* Conditional-encoder depth, `ResUnet(data=mode)` (unet_model.py:91-137). */
+typedef enum ld_cond_mode {
+  LD_COND_MRI = 0,  /* 4 blocks, 3 max-pools, 256 output channels at S/8 ('mri','mvtec','mvtecGray') */
+  LD_COND_MNIST = 1 /* 3 blocks, 2 max-pools, 128 output channels at S/4 ('mnist','mvtecSR')         */
+} ld_cond_mode;
+
+/* Mirrors the constructor arguments of `Unet` that reach the sampling path (ddpm.py:287-307). */
+typedef struct ld_model_desc {
+  int32_t dim;                       /* ddpm.py:289 */
+  int32_t init_dim;                  /* ddpm.py:290 (resolved, never 0) */
+  int32_t n_levels;                  /* len(dim_mults) */
+  int32_t dim_mults[LD_MAX_LEVELS];  /* ddpm.py:292 */
+  int32_t full_attn[LD_MAX_LEVELS];  /* ddpm.py:304, 0/1 per level */
+  int32_t channels;                  /* ddpm.py:293; must be 1 on this path */
+  int32_t resnet_groups;             /* ddpm.py:296 */
+  int32_t attn_heads;                /* ddpm.py:303 */
+  int32_t attn_dim_head;             /* ddpm.py:302; must be 32 */
+  float sinusoidal_theta;            /* ddpm.py:301 */
+  int32_t cond_mode;                 /* ld_cond_mode */
+  int32_t precision;                 /* ld_precision */
+} ld_model_desc;
+
+/* Flags of one sampling call, i.e. the state of the reference's `config` dict *after* the
+ * per-call fix-ups of `GaussianDiffusion.sample` (ddpm.py:1093-1117), which stay on the host. */
+typedef struct ld_sample_desc {
+  int32_t batch;            /* B */
+  int32_t height, width;    /* image_size (square in the reference, ddpm.py:1121) */
+  int32_t num_timesteps;    /* loop length: T, or use_gt_timestep (ddpm.py:944) */
+  int32_t branch_out;       /* 1: two-trajectory mode (ddpm.py:671) */
+  int32_t start_intermediate; /* 1: fuse at t <= start_timestep (ddpm.py:779) */
+  int32_t start_timestep;   /* config['start_timestep'] */
+  int32_t mask_x;           /* 1: masked fill of the OOD x0 (ddpm.py:697-703) */
+  int32_t ood_uses_cond;    /* 1: non-MRI data, OOD x0 := cond_out (ddpm.py:704-708) */
+  float cond_in_floor;      /* 0.95, or 0.5 for data=='mnist' (ddpm.py:683-686) */
+  float min_val, max_val;   /* min_max_val[0], [1] (ddpm.py:775-776) */
+  int32_t return_pair;      /* 1: output is [2,B,1,H,W] (ddpm.py:965-970) */
+  int32_t record_x0;        /* 1: also write every step's x0 to `x0_trace` (return_all_outputs) */
+} ld_sample_desc;
+
+LD_API const char* ld_last_error(void);
+/* Build id, e.g. "ld_sampler 0.1 sm_100a". */
+LD_API const char* ld_version(void);
+/* Number of usable sm_100 devices (0 when there is none or no driver). */
+LD_API int ld_device_count(void);
+
+/* --- lifetime ----------------------------------------------------------------------------- */
+LD_API int ld_create(const ld_model_desc* desc, int device, ld_handle** out);
+LD_API int ld_destroy(ld_handle* h);
+
+/* --- weights: replaces `load_state_dict` on the reference `Unet` (ddpm.py:1513-1521) -------
+ * `key` is the reference state_dict key without the `model.` prefix,
+ * `data` is host fp32 in the reference's layout (conv: [Cout,Cin,kh,kw]).  Every key of the
+ * model must be loaded exactly once before `ld_finalize_weights`; the dead
+ * `conv_fusion.mlp.1.{weight,bias}` are accepted and ignored (ddpm.py:436). */
+LD_API int ld_num_weights(const ld_handle* h);
+LD_API int ld_weight_info(const ld_handle* h, int index, const char** key, int64_t shape[4], int* ndim);
+LD_API int ld_load_weight(ld_handle* h, const char* key, const float* data, const int64_t* shape, int ndim);
+LD_API int ld_finalize_weights(ld_handle* h);
+
+/* --- schedule: the three `[T]` buffers the DDPM update reads (ddpm.py:591-593, 659-666) -----
+ * `sigma` (optional) is exp(0.5*posterior_log_variance_clipped) as the host computed it
+ * (ddpm.py:853); when NULL it is derived from the log-variance with expf. */
+LD_API int ld_set_schedule(ld_handle* h, int T, const float* posterior_mean_coef1,
+                    const float* posterior_mean_coef2, const float* posterior_log_variance_clipped,
+                    const float* sigma);
+
+/* --- `Unet.forward(x, cond_img, time)` (ddpm.py:404-451) -------------------------------------
+ * x, cond, out: device fp32 [N,1,H,W]; t: device int64 [N]. */
+LD_API int ld_unet_forward(ld_handle* h, const float* x, const float* cond, const int64_t* t, float* out,
+                    int N, int H, int W, void* stream);
+/* `ResUnet.forward` (unet_model.py:122-137): cond [N,1,H,W] -> feat fp32 NCHW [N,Cf,H/f,W/f]. */
+LD_API int ld_cond_encode(ld_handle* h, const float* cond, float* feat, int N, int H, int W, void* stream);
+
+/* --- `GaussianDiffusion.p_sample_loop` (ddpm.py:930-977) --------------------------------------
+ * cond, mask: device fp32 [B,1,H,W] (mask is the *soft* map; >= 1.0 means OOD, ddpm.py:672).
+ * noise: device fp32 [num_timesteps, B,1,H,W]; noise[0] is x_T (already q_sample'd by the host
+ *        when use_gt), noise[1+i] is the draw of loop iteration i (t = T-1-i), none for t == 0.
+ * out:   device fp32 [B,1,H,W] (or [2,B,1,H,W] when return_pair).
+ * x0_trace: optional device fp32 [num_timesteps, 2, B,1,H,W] (slot 1 unused after fusion). */
+LD_API int ld_sample(ld_handle* h, const ld_sample_desc* sd, const float* cond, const float* mask,
+              const float* noise, float* out, float* x0_trace, void* stream);
+
+/* --- one DDPM update on caller-owned state (ddpm.py:841-860 + 768-838), for parity tests -----
+ * kind 0: branched step; kind 1: fusion step (composite, then single update); kind 2: single.
+ * x_out/x_in/x0_out/x0_in/z/mask: device fp32 [n]; raw UNet outputs come in through x0_*, the
+ * clamped (and, for kind 1, fused) x0 goes back out through them; x_* are updated in place. */
+LD_API int ld_posterior_step(ld_handle* h, int kind, int t, float* x_out, float* x_in, float* x0_out,
+                      float* x0_in, const float* cond, const float* mask, const float* z,
+                      const ld_sample_desc* sd, int64_t n, void* stream);
+
+/* --- introspection for bench.py -------------------------------------------------------------- */
+/* Kernel launches enqueued by this handle since creation (our own kernels only). */
+LD_API int64_t ld_launch_count(const ld_handle* h);
+/* Device workspace currently owned by the handle, bytes. */
+LD_API int64_t ld_workspace_bytes(const ld_handle* h);
+/* Tunables: "micro_batch" (images per UNet pass, 0 = all), "use_graph" (0/1). */
+LD_API int ld_set_option(ld_handle* h, const char* name, int64_t value);
+
+/* --- test hooks (used by tests/ only) ---------------------------------------------------------
+ * Named intermediate activations of the last `ld_unet_forward` (requires option "debug_keep"=1
+ * before the first forward): dims = {N, C, H, W}; fetch converts to NCHW fp32. */
+LD_API int ld_debug_num_taps(ld_handle* h);
+LD_API int ld_debug_tap_info(ld_handle* h, int index, const char** name, int32_t dims[4]);
+LD_API int ld_debug_tap_fetch(ld_handle* h, int index, float* out_nchw, void* stream);
+/* One convolution through one kernel: kernel 0 = CUDA-core fp32, 1 = CUDA-core with bf16 storage,
+ * 2 = tcgen05.  x0/x1/res/out: device fp32 NHWC; w_host: host fp32 [Cout, C0+C1, ks, ks]. */
+LD_API int ld_debug_conv(int kernel, const float* x0, int C0, const float* x1, int C1, int N, int Hin,
+                         int Win, int up, int H, int W, const float* w_host, const float* bias_host,
+                         int Cout, int ks, const float* res, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LD_SAMPLER_H_ */

@@ -1,0 +1,8 @@
+"""B200-native (sm_100a) drop-in for the LocalDiffusion conditional reverse-diffusion sampler.
+
+Public surface mirrors the reference's `ddpm.py`: `Unet`, `GaussianDiffusion`.
+"""
+from .diffusion import GaussianDiffusion
+from .unet import Unet
+
+__all__ = ["Unet", "GaussianDiffusion"]

@@ -1,0 +1,34 @@
+// tcgen05 / TMEM implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ld {
+
+// weights re-packed for the tensor-core kernel (see ld_conv_tc.cu for the layout)
+struct ConvTcW {
+  bool ready = false;
+  int Cin = 0, Cout = 0, ks = 1, stride = 1, pad = 0;
+  int ntile = 0;         // output channels per CTA (UMMA N)
+  void* w = nullptr;     // bf16, [n_tile][cchunk][tap][kc/8][ntile][8] with kc = 64 (null if Cin % 64)
+  void* w32 = nullptr;   // same with kc = 32 (used when a concat source is not a multiple of 64 channels)
+  float* bias = nullptr; // fp32 [Cout] or null
+};
+
+struct ConvTcArgs {
+  const void* src0 = nullptr; const void* src1 = nullptr;  // bf16 NHWC, virtual concat along C
+  int C0 = 0, C1 = 0;
+  int N = 0, H = 0, W = 0;     // output extent
+  int Hin = 0, Win = 0;        // stored source extent
+  int up = 0;                  // read src0 through a nearest x2 up-sampling
+  void* dst = nullptr;         // bf16 [N,H,W,Cout]
+  const void* res = nullptr;   // optional bf16 residual added in the epilogue
+};
+
+// host: pack fp32 [taps][Cin][Cout] weights; leaves `ready == false` for unsupported shapes
+int conv_tc_pack(const float* w_tap_cin_cout, const float* bias, int Cin, int Cout, int ks, int stride, int pad, ConvTcW* out);
+bool conv_tc_supports(const ConvTcW& w, const ConvTcArgs& a);
+// returns number of kernels launched, < 0 on error
+int conv_tc_launch(const ConvTcW& w, const ConvTcArgs& a, cudaStream_t s);
+
+}  // namespace ld

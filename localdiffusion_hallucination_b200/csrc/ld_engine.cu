@@ -1,0 +1,1175 @@
+// Host engine behind the C ABI of include/ld_sampler.h: weight registry + repacking, the UNet
+// "plan" (a fixed launch sequence over a liveness-managed workspace), the per-timestep sampler
+// loop with CUDA-graph replay, and the extern "C" entry points.
+//
+// Reference behaviour restated here (no code shared): Unet.__init__/forward ddpm.py:286-451,
+// ResUnet unet_model.py:91-137, p_sample_loop / p_sample / p_mean_variance / model_predictions
+// ddpm.py:668-860, 929-977.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ld_sampler.h"
+#include "ld_conv_tc.h"
+#include "ld_kernels.h"
+
+namespace ld {
+
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess)                                                                             \
+      return fail(LD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// -------------------------------------------------------------------------------------------------
+// weight registry
+// -------------------------------------------------------------------------------------------------
+struct WSpec {
+  std::string key;
+  std::vector<int64_t> shape;
+  std::vector<float> host;
+  bool loaded = false;
+  size_t numel() const { size_t n = 1; for (auto s : shape) n *= (size_t)s; return n; }
+};
+
+struct DevArr { float* p = nullptr; size_t n = 0; };
+
+// a packed convolution ready for the kernels
+struct ConvW {
+  int Cin = 0, Cout = 0, ks = 1, stride = 1, pad = 0;
+  float* w = nullptr;     // fp32 [taps][Cin][Cout]  (CUDA-core path, c1 and cout1 kernels)
+  float* bias = nullptr;  // fp32 [Cout] or null
+  ConvTcW tc;             // bf16 tcgen05 packing (empty in fp32 mode)
+};
+
+struct ResW { ConvW c1, c2, res; bool has_res = false, has_film = false; int film_off = 0; float *g1, *b1, *g2, *b2; int Cin, Cout; };
+struct AttnW { bool full; int C; float* g; ConvW qkv; ConvW out; float* g2 = nullptr; };
+struct CondW { ConvW a, b, id; float *ga, *ba, *gb, *bb, *gi, *bi; int Cin, Cmid, Cout; };
+
+// -------------------------------------------------------------------------------------------------
+// plan: fixed launch sequence
+// -------------------------------------------------------------------------------------------------
+struct Ten { void* p = nullptr; int N = 0, H = 0, W = 0, C = 0; int buf = -1; };
+
+struct Plan {
+  std::vector<std::function<int(cudaStream_t)>> ops;
+  std::vector<void*> bufs; std::vector<size_t> cap; std::vector<char> busy;
+  void* zero_arena = nullptr; size_t zero_bytes = 0, zero_used = 0;
+  size_t total_bytes = 0;
+  int N = 0, H = 0, W = 0;
+  std::vector<std::pair<std::string, Ten>> tags;  // debug taps (only with option debug_keep)
+  // external I/O of the plan
+  const float* x = nullptr; const float* cond = nullptr; const void* cond_feat = nullptr; float* out = nullptr;
+  ~Plan() {
+    for (void* b : bufs) cudaFree(b);
+    if (zero_arena) cudaFree(zero_arena);
+  }
+};
+
+struct Staged {
+  std::unique_ptr<Plan> cond, unet;
+  float *x = nullptr, *c = nullptr, *o = nullptr; void* feat = nullptr; int64_t* t = nullptr;
+  void free_all() { cudaFree(x); cudaFree(c); cudaFree(o); cudaFree(feat); cudaFree(t); x = c = o = nullptr; feat = nullptr; t = nullptr; }
+};
+
+struct Engine {
+  ld_model_desc d{};
+  int device = 0;
+  bool bf = false;
+  bool use_tc = false;
+  std::vector<WSpec> specs;
+  std::unordered_map<std::string, int> index;
+  bool finalized = false;
+  std::vector<void*> dev_allocs;
+  std::map<std::string, float*> vec;  // small fp32 vectors (GN gamma/beta, RMSNorm g, biases)
+  // model
+  std::vector<int> dims;
+  ConvW init_conv, final_conv;
+  float *tw1, *tb1, *tw2, *tb2, *film_w, *film_b;
+  int film_total = 0;
+  std::vector<ResW> res;                  // all resnet blocks by name index
+  std::map<std::string, int> res_index;
+  std::map<std::string, AttnW> attn;
+  std::vector<CondW> cond_blocks;
+  std::map<std::string, ConvW> samp;      // down/up sampling convs
+  int cond_C = 0, cond_div = 8;
+  // schedule
+  int T = 0;
+  float *coef1 = nullptr, *coef2 = nullptr, *sigma = nullptr;
+  // runtime
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  int64_t launches = 0;
+  int64_t opt_micro_batch = 0, opt_use_graph = 1, opt_debug_keep = 0;
+  std::map<std::string, std::unique_ptr<Plan>> plans;
+  std::map<std::string, Staged> staged;   // stand-alone entry points (ld_unet_forward / ld_cond_encode)
+  // sampler-owned state
+  struct SampState {
+    int B = 0, H = 0, W = 0, tloop = 0;
+    float *xs = nullptr, *o = nullptr, *bm = nullptr, *cond = nullptr, *cond_out = nullptr, *cond_in = nullptr;
+    void *feat_pair = nullptr, *feat_full = nullptr;
+    unsigned int* counters = nullptr;
+    int* t_dev = nullptr;
+    int64_t* t64 = nullptr;
+    std::vector<void*> allocs;
+    cudaGraphExec_t g_branch = nullptr, g_single = nullptr;
+    std::string key;
+  } ss;
+
+  ~Engine() {
+    free_samp();
+    plans.clear();
+    for (auto& kv : staged) { kv.second.cond.reset(); kv.second.unet.reset(); kv.second.free_all(); }
+    staged.clear();
+    for (void* p : dev_allocs) cudaFree(p);
+    if (coef1) cudaFree(coef1);
+    if (coef2) cudaFree(coef2);
+    if (sigma) cudaFree(sigma);
+    if (ev_in) cudaEventDestroy(ev_in);
+    if (ev_out) cudaEventDestroy(ev_out);
+    if (own_stream) cudaStreamDestroy(own_stream);
+  }
+  void free_samp() {
+    if (ss.g_branch) cudaGraphExecDestroy(ss.g_branch);
+    if (ss.g_single) cudaGraphExecDestroy(ss.g_single);
+    for (void* p : ss.allocs) cudaFree(p);
+    ss = SampState();
+  }
+  size_t esz() const { return bf ? 2 : 4; }
+};
+
+// -------------------------------------------------------------------------------------------------
+// spec generation (state_dict keys + shapes)
+// -------------------------------------------------------------------------------------------------
+static void add_spec(Engine& E, const std::string& key, std::vector<int64_t> shape) {
+  WSpec s; s.key = key; s.shape = std::move(shape);
+  E.index[key] = (int)E.specs.size();
+  E.specs.push_back(std::move(s));
+}
+static void spec_conv(Engine& E, const std::string& p, int co, int ci, int k, bool bias = true) {
+  add_spec(E, p + ".weight", {co, ci, k, k});
+  if (bias) add_spec(E, p + ".bias", {co});
+}
+static void spec_norm(Engine& E, const std::string& p, int c) { add_spec(E, p + ".weight", {c}); add_spec(E, p + ".bias", {c}); }
+static void spec_res(Engine& E, const std::string& p, int ci, int co, int td) {
+  add_spec(E, p + ".mlp.1.weight", {2 * co, td});
+  add_spec(E, p + ".mlp.1.bias", {2 * co});
+  spec_conv(E, p + ".block1.proj", co, ci, 3); spec_norm(E, p + ".block1.norm", co);
+  spec_conv(E, p + ".block2.proj", co, co, 3); spec_norm(E, p + ".block2.norm", co);
+  if (ci != co) spec_conv(E, p + ".res_conv", co, ci, 1);
+}
+static void spec_attn(Engine& E, const std::string& p, int c, bool full) {
+  const int hid = E.d.attn_heads * E.d.attn_dim_head;
+  add_spec(E, p + ".norm.g", {1, c, 1, 1});
+  spec_conv(E, p + ".to_qkv", 3 * hid, c, 1, false);
+  if (full) spec_conv(E, p + ".to_out", c, hid, 1);
+  else { spec_conv(E, p + ".to_out.0", c, hid, 1); add_spec(E, p + ".to_out.1.g", {1, c, 1, 1}); }
+}
+static void spec_cond(Engine& E, const std::string& p, int ci, int cm, int co) {
+  spec_conv(E, p + ".convblock.0", cm, ci, 3); spec_norm(E, p + ".convblock.1", cm);
+  spec_conv(E, p + ".convblock.3", co, cm, 3); spec_norm(E, p + ".convblock.4", co);
+  spec_conv(E, p + ".identity.0", co, ci, 3); spec_norm(E, p + ".identity.1", co);
+}
+static void build_specs(Engine& E) {
+  const ld_model_desc& d = E.d;
+  const int L = d.n_levels, td = 4 * d.dim;
+  E.dims.clear(); E.dims.push_back(d.init_dim);
+  for (int i = 0; i < L; ++i) E.dims.push_back(d.dim * d.dim_mults[i]);
+  spec_cond(E, "cond_model.residual_conv1.0", 1, 32, 32);
+  spec_cond(E, "cond_model.residual_conv2.0", 32, 32, 64);
+  spec_cond(E, "cond_model.residual_conv3.0", 64, 64, 128);
+  if (d.cond_mode == LD_COND_MRI) spec_cond(E, "cond_model.mid_conv.0", 128, 128, 256);
+  spec_conv(E, "init_conv", d.init_dim, d.channels, 7);
+  add_spec(E, "time_mlp.1.weight", {td, d.dim}); add_spec(E, "time_mlp.1.bias", {td});
+  add_spec(E, "time_mlp.3.weight", {td, td}); add_spec(E, "time_mlp.3.bias", {td});
+  char b[64];
+  for (int i = 0; i < L; ++i) {
+    const int di = E.dims[i], dn = E.dims[i + 1];
+    snprintf(b, sizeof b, "downs.%d", i); std::string p = b;
+    spec_res(E, p + ".0", di, di, td); spec_res(E, p + ".1", di, di, td);
+    spec_attn(E, p + ".2", di, d.full_attn[i] != 0);
+    if (i < L - 1) spec_conv(E, p + ".3.1", dn, 4 * di, 1); else spec_conv(E, p + ".3", dn, di, 3);
+  }
+  for (int i = 0; i < L; ++i) {
+    const int di = E.dims[L - 1 - i], dn = E.dims[L - i];  // (dim_in, dim_out) reversed
+    snprintf(b, sizeof b, "ups.%d", i); std::string p = b;
+    spec_res(E, p + ".0", dn + di, dn, td); spec_res(E, p + ".1", dn + di, dn, td);
+    spec_attn(E, p + ".2", dn, d.full_attn[L - 1 - i] != 0);
+    if (i < L - 1) spec_conv(E, p + ".3.1", di, dn, 3); else spec_conv(E, p + ".3", di, dn, 3);
+  }
+  const int mid = E.dims[L];
+  spec_res(E, "mid_block1", mid, mid, td);
+  spec_attn(E, "mid_attn", mid, true);
+  spec_res(E, "mid_block2", mid, mid, td);
+  spec_res(E, "conv_fusion", 2 * mid, mid, td);
+  spec_res(E, "final_res_block", 2 * d.dim, d.dim, td);
+  spec_conv(E, "final_conv", d.channels, d.dim, 1);
+}
+
+// -------------------------------------------------------------------------------------------------
+// weight upload / packing
+// -------------------------------------------------------------------------------------------------
+static const WSpec& W(const Engine& E, const std::string& key) { return E.specs[E.index.at(key)]; }
+static bool has(const Engine& E, const std::string& key) { return E.index.count(key) != 0; }
+
+static int upload(Engine& E, const std::vector<float>& h, float** out) {
+  float* p = nullptr;
+  CK(cudaMalloc(&p, h.size() * sizeof(float)));
+  E.dev_allocs.push_back(p);
+  CK(cudaMemcpy(p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  *out = p;
+  return 0;
+}
+static int upload_key(Engine& E, const std::string& key, float** out) { return upload(E, W(E, key).host, out); }
+
+// [Cout,Cin,k,k] -> [tap][Cin][Cout];  unshuffle=true: [Cout,4*Cs,1,1] -> 2x2/stride-2 taps (p1,p2) over Cs
+static int pack_conv(Engine& E, const std::string& p, bool bias, bool unshuffle, ConvW* cw) {
+  const WSpec& w = W(E, p + ".weight");
+  const int co = (int)w.shape[0];
+  int ci = (int)w.shape[1], k = (int)w.shape[2];
+  std::vector<float> pk(w.host.size());
+  if (unshuffle) {
+    const int cs = ci / 4;
+    for (int o = 0; o < co; ++o)
+      for (int c = 0; c < cs; ++c)
+        for (int q = 0; q < 4; ++q) pk[((size_t)q * cs + c) * co + o] = w.host[(size_t)o * ci + c * 4 + q];
+    cw->Cin = cs; cw->ks = 2; cw->stride = 2; cw->pad = 0;
+  } else {
+    for (int o = 0; o < co; ++o)
+      for (int c = 0; c < ci; ++c)
+        for (int t = 0; t < k * k; ++t) pk[((size_t)t * ci + c) * co + o] = w.host[((size_t)o * ci + c) * k * k + t];
+    cw->Cin = ci; cw->ks = k; cw->stride = 1; cw->pad = k / 2;
+  }
+  cw->Cout = co;
+  int r = upload(E, pk, &cw->w);
+  if (r) return r;
+  cw->bias = nullptr;
+  if (bias) { r = upload_key(E, p + ".bias", &cw->bias); if (r) return r; }
+  if (E.use_tc && cw->Cin >= 32 && cw->Cout >= 32) {
+    std::vector<float> bh;
+    if (bias) bh = W(E, p + ".bias").host;
+    r = conv_tc_pack(pk.data(), bias ? bh.data() : nullptr, cw->Cin, cw->Cout, cw->ks, cw->stride, cw->pad, &cw->tc);
+    if (r) return fail(LD_ERR_CUDA, "conv_tc_pack(%s) failed", p.c_str());
+  }
+  return 0;
+}
+static int vecp(Engine& E, const std::string& key, float** out) {
+  auto it = E.vec.find(key);
+  if (it != E.vec.end()) { *out = it->second; return 0; }
+  float* p; int r = upload_key(E, key, &p); if (r) return r;
+  E.vec[key] = p; *out = p; return 0;
+}
+
+static int pack_res(Engine& E, const std::string& p, bool film, std::vector<float>& fw, std::vector<float>& fb) {
+  ResW r;
+  int rc;
+  if ((rc = pack_conv(E, p + ".block1.proj", true, false, &r.c1))) return rc;
+  if ((rc = pack_conv(E, p + ".block2.proj", true, false, &r.c2))) return rc;
+  r.Cin = r.c1.Cin; r.Cout = r.c1.Cout;
+  r.has_res = has(E, p + ".res_conv.weight");
+  if (r.has_res && (rc = pack_conv(E, p + ".res_conv", true, false, &r.res))) return rc;
+  if ((rc = vecp(E, p + ".block1.norm.weight", &r.g1))) return rc;
+  if ((rc = vecp(E, p + ".block1.norm.bias", &r.b1))) return rc;
+  if ((rc = vecp(E, p + ".block2.norm.weight", &r.g2))) return rc;
+  if ((rc = vecp(E, p + ".block2.norm.bias", &r.b2))) return rc;
+  r.has_film = film;
+  if (film) {
+    r.film_off = (int)fb.size();
+    const WSpec& w = W(E, p + ".mlp.1.weight"); const WSpec& b = W(E, p + ".mlp.1.bias");
+    fw.insert(fw.end(), w.host.begin(), w.host.end());
+    fb.insert(fb.end(), b.host.begin(), b.host.end());
+  }
+  E.res_index[p] = (int)E.res.size();
+  E.res.push_back(r);
+  return 0;
+}
+static int pack_attn(Engine& E, const std::string& p, int C, bool full) {
+  AttnW a; a.full = full; a.C = C;
+  int rc;
+  if ((rc = vecp(E, p + ".norm.g", &a.g))) return rc;
+  if ((rc = pack_conv(E, p + ".to_qkv", false, false, &a.qkv))) return rc;
+  if (full) { if ((rc = pack_conv(E, p + ".to_out", true, false, &a.out))) return rc; }
+  else {
+    if ((rc = pack_conv(E, p + ".to_out.0", true, false, &a.out))) return rc;
+    if ((rc = vecp(E, p + ".to_out.1.g", &a.g2))) return rc;
+  }
+  E.attn[p] = a;
+  return 0;
+}
+static int pack_cond(Engine& E, const std::string& p) {
+  CondW c; int rc;
+  if ((rc = pack_conv(E, p + ".convblock.0", true, false, &c.a))) return rc;
+  if ((rc = pack_conv(E, p + ".convblock.3", true, false, &c.b))) return rc;
+  if ((rc = pack_conv(E, p + ".identity.0", true, false, &c.id))) return rc;
+  if ((rc = vecp(E, p + ".convblock.1.weight", &c.ga))) return rc;
+  if ((rc = vecp(E, p + ".convblock.1.bias", &c.ba))) return rc;
+  if ((rc = vecp(E, p + ".convblock.4.weight", &c.gb))) return rc;
+  if ((rc = vecp(E, p + ".convblock.4.bias", &c.bb))) return rc;
+  if ((rc = vecp(E, p + ".identity.1.weight", &c.gi))) return rc;
+  if ((rc = vecp(E, p + ".identity.1.bias", &c.bi))) return rc;
+  c.Cin = c.a.Cin; c.Cmid = c.a.Cout; c.Cout = c.b.Cout;
+  E.cond_blocks.push_back(c);
+  return 0;
+}
+
+static int finalize(Engine& E) {
+  for (auto& s : E.specs)
+    if (!s.loaded) return fail(LD_ERR_STATE, "weight '%s' was never loaded", s.key.c_str());
+  const int L = E.d.n_levels;
+  int rc;
+  std::vector<float> fw, fb;
+  if ((rc = pack_cond(E, "cond_model.residual_conv1.0"))) return rc;
+  if ((rc = pack_cond(E, "cond_model.residual_conv2.0"))) return rc;
+  if ((rc = pack_cond(E, "cond_model.residual_conv3.0"))) return rc;
+  if (E.d.cond_mode == LD_COND_MRI) { if ((rc = pack_cond(E, "cond_model.mid_conv.0"))) return rc; E.cond_C = 256; E.cond_div = 8; }
+  else { E.cond_C = 128; E.cond_div = 4; }
+  if ((rc = pack_conv(E, "init_conv", true, false, &E.init_conv))) return rc;
+  if ((rc = pack_conv(E, "final_conv", true, false, &E.final_conv))) return rc;
+  if ((rc = upload_key(E, "time_mlp.1.weight", &E.tw1))) return rc;
+  if ((rc = upload_key(E, "time_mlp.1.bias", &E.tb1))) return rc;
+  if ((rc = upload_key(E, "time_mlp.3.weight", &E.tw2))) return rc;
+  if ((rc = upload_key(E, "time_mlp.3.bias", &E.tb2))) return rc;
+  char b[64];
+  for (int i = 0; i < L; ++i) {
+    snprintf(b, sizeof b, "downs.%d", i); std::string p = b;
+    if ((rc = pack_res(E, p + ".0", true, fw, fb))) return rc;
+    if ((rc = pack_res(E, p + ".1", true, fw, fb))) return rc;
+    if ((rc = pack_attn(E, p + ".2", E.dims[i], E.d.full_attn[i] != 0))) return rc;
+    ConvW cw;
+    if (i < L - 1) rc = pack_conv(E, p + ".3.1", true, true, &cw); else rc = pack_conv(E, p + ".3", true, false, &cw);
+    if (rc) return rc;
+    E.samp[p + ".3"] = cw;
+  }
+  if ((rc = pack_res(E, "mid_block1", true, fw, fb))) return rc;
+  if ((rc = pack_attn(E, "mid_attn", E.dims[L], true))) return rc;
+  if ((rc = pack_res(E, "mid_block2", true, fw, fb))) return rc;
+  if ((rc = pack_res(E, "conv_fusion", false, fw, fb))) return rc;  // ddpm.py:436: no time embedding
+  for (int i = 0; i < L; ++i) {
+    snprintf(b, sizeof b, "ups.%d", i); std::string p = b;
+    if ((rc = pack_res(E, p + ".0", true, fw, fb))) return rc;
+    if ((rc = pack_res(E, p + ".1", true, fw, fb))) return rc;
+    if ((rc = pack_attn(E, p + ".2", E.dims[L - i], E.d.full_attn[L - 1 - i] != 0))) return rc;
+    ConvW cw;
+    if (i < L - 1) rc = pack_conv(E, p + ".3.1", true, false, &cw); else rc = pack_conv(E, p + ".3", true, false, &cw);
+    if (rc) return rc;
+    E.samp[p + ".3"] = cw;
+  }
+  if ((rc = pack_res(E, "final_res_block", true, fw, fb))) return rc;
+  E.film_total = (int)fb.size();
+  if ((rc = upload(E, fw, &E.film_w))) return rc;
+  if ((rc = upload(E, fb, &E.film_b))) return rc;
+  for (auto& s : E.specs) { std::vector<float>().swap(s.host); }
+  E.finalized = true;
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// plan builder
+// -------------------------------------------------------------------------------------------------
+struct Builder {
+  Engine& E; Plan& P; int err = 0;
+  float* film = nullptr;  // [N][film_total]
+  Builder(Engine& e, Plan& p) : E(e), P(p) {}
+
+  Ten alloc(int N, int H, int W, int C, size_t elem) {
+    const size_t bytes = (size_t)N * H * W * C * elem;
+    int best = -1;
+    for (size_t i = 0; i < P.bufs.size(); ++i)
+      if (!P.busy[i] && P.cap[i] >= bytes && (best < 0 || P.cap[i] < P.cap[best])) best = (int)i;
+    if (best < 0) {
+      void* p = nullptr;
+      if (cudaMalloc(&p, bytes) != cudaSuccess) { err = fail(LD_ERR_CUDA, "workspace cudaMalloc(%zu) failed", bytes); return Ten(); }
+      P.bufs.push_back(p); P.cap.push_back(bytes); P.busy.push_back(0); P.total_bytes += bytes;
+      best = (int)P.bufs.size() - 1;
+    }
+    P.busy[best] = 1;
+    Ten t; t.p = P.bufs[best]; t.N = N; t.H = H; t.W = W; t.C = C; t.buf = best;
+    return t;
+  }
+  Ten act(int N, int H, int W, int C) { return alloc(N, H, W, C, E.esz()); }
+  void release(Ten& t) { if (t.buf >= 0 && !E.opt_debug_keep) P.busy[t.buf] = 0; t.buf = -1; }
+  void tag(const std::string& name, const Ten& t) { if (E.opt_debug_keep) P.tags.emplace_back(name, t); }
+  // zero-initialised scratch (GN statistics, linear-attention accumulators): one memset per forward
+  void* zalloc(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    size_t off = P.zero_used; P.zero_used += bytes;
+    return (void*)off;  // resolved after the arena is allocated
+  }
+  template <typename F> void op(F f) { P.ops.emplace_back(std::move(f)); }
+
+  // ---- convolution dispatch -----------------------------------------------------------------
+  Ten conv(const ConvW& cw, const Ten& a, const Ten* b, bool up, const Ten* resid, int outH, int outW) {
+    Ten o = act(a.N, outH, outW, cw.Cout);
+    if (err) return o;
+    const bool bf = E.bf;
+    ConvTcArgs ta;
+    if (E.use_tc && cw.tc.ready) {
+      ta.src0 = a.p; ta.C0 = a.C; ta.src1 = b ? b->p : nullptr; ta.C1 = b ? b->C : 0;
+      ta.N = a.N; ta.H = outH; ta.W = outW; ta.Hin = a.H; ta.Win = a.W; ta.up = up ? 1 : 0;
+      ta.dst = o.p; ta.res = resid ? resid->p : nullptr;
+      if (conv_tc_supports(cw.tc, ta)) {
+        const ConvTcW* w = &cw.tc;
+        op([ta, w](cudaStream_t s) { return conv_tc_launch(*w, ta, s); });
+        return o;
+      }
+    }
+    ConvP p{};
+    p.src0 = a.p; p.C0 = a.C; p.src1 = b ? b->p : nullptr; p.C1 = b ? b->C : 0;
+    p.N = a.N; p.H = outH; p.W = outW; p.Hin = a.H; p.Win = a.W;
+    p.ks = cw.ks; p.stride = cw.stride; p.pad = cw.pad; p.up = up ? 1 : 0;
+    p.w = cw.w; p.bias = cw.bias; p.Cout = cw.Cout; p.dst = o.p; p.res = resid ? resid->p : nullptr;
+    p.M = (long long)a.N * outH * outW;
+    op([p, bf](cudaStream_t s) { return launch_conv_simt(p, bf, s); });
+    return o;
+  }
+  Ten conv_same(const ConvW& cw, const Ten& a, const Ten* b = nullptr, const Ten* resid = nullptr) {
+    return conv(cw, a, b, false, resid, a.H, a.W);
+  }
+  double* stats(const Ten& x, int G) {
+    double* st = (double*)zalloc((size_t)x.N * G * 2 * sizeof(double));
+    Plan* pp = &P; const bool bf = E.bf; Ten xx = x;
+    op([pp, st, xx, G, bf](cudaStream_t s) {
+      return launch_gn_stats(xx.p, (double*)((char*)pp->zero_arena + (size_t)st), xx.N, xx.H * xx.W, xx.C, G, bf, s);
+    });
+    return st;
+  }
+  // out = act(GN(xa)*film) (+ xb variants), see GnApplyP
+  Ten gn_apply(const Ten& xa, double* stA, const float* gA, const float* bA, int GA, int film_off, int act,
+               const Ten* xb, int modeB, double* stB = nullptr, const float* gB = nullptr, const float* bB = nullptr,
+               int GB = 1) {
+    Ten o = act_t(xa);
+    GnApplyP p{};
+    p.xa = xa.p; p.statsA = stA; p.gA = gA; p.bA = bA; p.GA = GA;
+    p.xb = xb ? xb->p : nullptr; p.statsB = stB; p.gB = gB; p.bB = bB; p.GB = GB; p.modeB = modeB;
+    p.film = film_off >= 0 ? film + film_off : nullptr; p.film_stride = E.film_total;
+    p.act = act; p.out = o.p; p.N = xa.N; p.HW = xa.H * xa.W; p.C = xa.C; p.eps = 1e-5f;
+    Plan* pp = &P; const bool bf = E.bf;
+    op([pp, p, bf](cudaStream_t s) {
+      GnApplyP q = p;
+      q.statsA = (const double*)((char*)pp->zero_arena + (size_t)p.statsA);
+      if (p.statsB) q.statsB = (const double*)((char*)pp->zero_arena + (size_t)p.statsB);
+      return launch_gn_apply(q, bf, s);
+    });
+    return o;
+  }
+  Ten act_t(const Ten& like) { return act(like.N, like.H, like.W, like.C); }
+
+  // ---- ResnetBlock (ddpm.py:200-212) -----------------------------------------------------------
+  Ten resblock(const std::string& name, Ten& a, Ten* b) {
+    const ResW& r = E.res[E.res_index.at(name)];
+    const int G = E.d.resnet_groups;
+    Ten h1 = conv_same(r.c1, a, b);
+    double* s1 = stats(h1, G);
+    Ten a1 = gn_apply(h1, s1, r.g1, r.b1, G, r.has_film ? r.film_off : -1, 1, nullptr, 0);
+    release(h1);
+    Ten h2 = conv_same(r.c2, a1);
+    release(a1);
+    double* s2 = stats(h2, G);
+    Ten o;
+    if (r.has_res) {
+      Ten rs = conv_same(r.res, a, b);
+      o = gn_apply(h2, s2, r.g2, r.b2, G, -1, 1, &rs, 1);
+      release(rs);
+    } else {
+      o = gn_apply(h2, s2, r.g2, r.b2, G, -1, 1, &a, 1);
+    }
+    release(h2);
+    return o;
+  }
+  // ---- attention + residual (ddpm.py:425,431,444) ------------------------------------------------
+  Ten attention(const std::string& name, Ten& x) {
+    const AttnW& a = E.attn.at(name);
+    const bool bf = E.bf;
+    const int heads = E.d.attn_heads, hid = heads * 32;
+    Ten xn = act_t(x);
+    {
+      Ten xx = x, o = xn; const float* g = a.g;
+      op([xx, o, g, bf](cudaStream_t s) { return launch_rmsnorm(xx.p, g, nullptr, o.p, (long long)xx.N * xx.H * xx.W, xx.C, bf, s); });
+    }
+    Ten qkv = conv_same(a.qkv, xn);
+    release(xn);
+    Ten out;
+    if (a.full) {
+      Ten ao = act(x.N, x.H, x.W, hid);
+      {
+        Ten q = qkv, o = ao;
+        op([q, o, heads, bf](cudaStream_t s) { return launch_attention_simt(q.p, o.p, q.N, q.H * q.W, heads, bf, s); });
+      }
+      out = conv_same(a.out, ao, nullptr, &x);
+      release(ao);
+    } else {
+      out = act_t(x);
+      LinAttnP p{};
+      p.qkv = qkv.p; p.N = x.N; p.HW = x.H * x.W; p.heads = heads; p.C = x.C;
+      p.chunks = std::max(1, std::min(64, p.HW / 1024));
+      Ten t_part = alloc(x.N, 1, 1, p.chunks * hid, 4), t_max = alloc(x.N, 1, 1, hid, 4), t_mn = alloc(x.N, 1, 1, hid * x.C, 4);
+      p.kmax_part = (float*)t_part.p; p.kmax = (float*)t_max.p; p.Mn = (float*)t_mn.p;
+      p.ctx = (float*)zalloc((size_t)x.N * hid * 32 * 4); p.ksum = (float*)zalloc((size_t)x.N * hid * 4);
+      p.wout = a.out.w; p.bout = a.out.bias; p.g2 = a.g2; p.x = x.p; p.out = out.p;
+      Plan* pp = &P;
+      op([pp, p, bf](cudaStream_t s) {
+        LinAttnP q = p;
+        q.ctx = (float*)((char*)pp->zero_arena + (size_t)p.ctx);
+        q.ksum = (float*)((char*)pp->zero_arena + (size_t)p.ksum);
+        return launch_linear_attention(q, bf, s);
+      });
+      release(t_part); release(t_max); release(t_mn);
+    }
+    release(qkv);
+    return out;
+  }
+  // ---- conditional encoder block (unet_model.py:37-51) -------------------------------------------
+  Ten cond_block(const CondW& c, const Ten* xin, const float* img, int N, int H, int W) {
+    const bool bf = E.bf;
+    Ten a, id;
+    if (c.Cin == 1) {
+      a = act(N, H, W, c.Cmid); id = act(N, H, W, c.Cout);
+      const ConvW *ca = &c.a, *ci = &c.id; Ten aa = a, ii = id;
+      op([=](cudaStream_t s) { return launch_conv_c1(img, ca->w, ca->bias, aa.p, N, H, W, ca->Cout, 3, bf, s); });
+      op([=](cudaStream_t s) { return launch_conv_c1(img, ci->w, ci->bias, ii.p, N, H, W, ci->Cout, 3, bf, s); });
+    } else {
+      a = conv_same(c.a, *xin); id = conv_same(c.id, *xin);
+    }
+    double* sa = stats(a, 16);
+    Ten a1 = gn_apply(a, sa, c.ga, c.ba, 16, -1, 2, nullptr, 0);
+    release(a);
+    Ten b2 = conv_same(c.b, a1);
+    release(a1);
+    double* sb = stats(b2, 16);
+    double* si = stats(id, 16);
+    Ten o = gn_apply(b2, sb, c.gb, c.bb, 16, -1, 2, &id, 2, si, c.gi, c.bi, 16);
+    release(b2); release(id);
+    return o;
+  }
+  Ten maxpool(Ten& x) {
+    Ten o = act(x.N, x.H / 2, x.W / 2, x.C);
+    Ten xx = x, oo = o; const bool bf = E.bf;
+    op([xx, oo, bf](cudaStream_t s) { return launch_maxpool2(xx.p, oo.p, xx.N, xx.H, xx.W, xx.C, bf, s); });
+    release(x);
+    return o;
+  }
+  int finish() {
+    if (err) return err;
+    if (P.zero_used) {
+      if (cudaMalloc(&P.zero_arena, P.zero_used) != cudaSuccess) return fail(LD_ERR_CUDA, "zero arena cudaMalloc failed");
+      P.zero_bytes = P.zero_used; P.total_bytes += P.zero_used;
+    }
+    return 0;
+  }
+};
+
+// cond encoder plan: cond fp32 [N,H,W] -> feat T [N,H/f,W/f,Cf]  (unet_model.py:122-137)
+static int build_cond_plan(Engine& E, Plan& P, int N, int H, int W, const float* cond, void* feat_out) {
+  Builder B(E, P);
+  P.N = N; P.H = H; P.W = W;
+  Ten x = B.cond_block(E.cond_blocks[0], nullptr, cond, N, H, W);
+  x = B.maxpool(x);
+  Ten y = B.cond_block(E.cond_blocks[1], &x, nullptr, N, x.H, x.W); B.release(x);
+  y = B.maxpool(y);
+  Ten z = B.cond_block(E.cond_blocks[2], &y, nullptr, N, y.H, y.W); B.release(y);
+  if (E.d.cond_mode == LD_COND_MRI) {
+    z = B.maxpool(z);
+    Ten w = B.cond_block(E.cond_blocks[3], &z, nullptr, N, z.H, z.W); B.release(z);
+    z = w;
+  }
+  if (B.err) return B.err;
+  const size_t bytes = (size_t)N * z.H * z.W * z.C * E.esz();
+  void* src = z.p;
+  B.op([src, feat_out, bytes](cudaStream_t s) {
+    return cudaMemcpyAsync(feat_out, src, bytes, cudaMemcpyDeviceToDevice, s) == cudaSuccess ? 0 : -1;
+  });
+  return B.finish();
+}
+
+// UNet plan (ddpm.py:404-451) with the conditional features supplied (hoisted out of the loop)
+static int build_unet_plan(Engine& E, Plan& P, int N, int H, int W, const float* x, const void* cond_feat,
+                           const int64_t* t64, const int* t_scalar, float* out) {
+  Builder B(E, P);
+  const bool bf = E.bf;
+  const int L = E.d.n_levels;
+  P.N = N; P.H = H; P.W = W;
+  // time embedding + FiLM vectors
+  Ten st = B.alloc(N, 1, 1, 4 * E.d.dim, 4), fl = B.alloc(N, 1, 1, E.film_total, 4);
+  B.film = (float*)fl.p;
+  {
+    TimeP tp{};
+    tp.t = t64; tp.t_scalar = t_scalar; tp.N = N; tp.dim = E.d.dim; tp.theta = E.d.sinusoidal_theta;
+    tp.neg_step = (float)(-(std::log((double)E.d.sinusoidal_theta) / (double)(E.d.dim / 2 - 1)));
+    tp.w1 = E.tw1; tp.b1 = E.tb1; tp.w2 = E.tw2; tp.b2 = E.tb2; tp.st = (float*)st.p;
+    tp.wf = E.film_w; tp.bf_ = E.film_b; tp.total = E.film_total; tp.film = (float*)fl.p;
+    B.op([tp](cudaStream_t s) { return launch_time_film(tp, s); });
+  }
+  Ten h = B.act(N, H, W, E.d.init_dim);
+  {
+    const ConvW* c = &E.init_conv; Ten hh = h;
+    B.op([=](cudaStream_t s) { return launch_conv_c1(x, c->w, c->bias, hh.p, N, H, W, c->Cout, 7, bf, s); });
+  }
+  B.tag("init_conv", h);
+  Ten r = h;  // ddpm.py:414 (clone not needed: h is never written again)
+  std::vector<Ten> skips;
+  Ten cur = h;
+  bool cur_is_r = true;
+  char nb[64];
+  for (int i = 0; i < L; ++i) {
+    snprintf(nb, sizeof nb, "downs.%d", i); std::string p = nb;
+    Ten a = B.resblock(p + ".0", cur, nullptr);
+    if (!cur_is_r) B.release(cur);
+    cur_is_r = false;
+    skips.push_back(a);
+    B.tag(p + ".0", a);
+    Ten b = B.resblock(p + ".1", a, nullptr);
+    B.tag(p + ".1", b);
+    Ten c = B.attention(p + ".2", b);
+    B.tag(p + ".2", c);
+    B.release(b);
+    skips.push_back(c);
+    const ConvW& dw = E.samp.at(p + ".3");
+    if (i < L - 1) cur = B.conv(dw, c, nullptr, false, nullptr, c.H / 2, c.W / 2);
+    else cur = B.conv_same(dw, c);
+    B.tag(p + ".3", cur);
+  }
+  {
+    Ten a = B.resblock("mid_block1", cur, nullptr); B.release(cur);
+    B.tag("mid_block1", a);
+    Ten b = B.attention("mid_attn", a); B.release(a);
+    B.tag("mid_attn", b);
+    Ten c = B.resblock("mid_block2", b, nullptr); B.release(b);
+    B.tag("mid_block2", c);
+    Ten cf; cf.p = const_cast<void*>(cond_feat); cf.N = N; cf.H = c.H; cf.W = c.W; cf.C = E.cond_C;
+    cur = B.resblock("conv_fusion", c, &cf); B.release(c);
+    B.tag("conv_fusion", cur);
+  }
+  for (int i = 0; i < L; ++i) {
+    snprintf(nb, sizeof nb, "ups.%d", i); std::string p = nb;
+    Ten s1 = skips.back(); skips.pop_back();
+    Ten a = B.resblock(p + ".0", cur, &s1); B.release(cur); B.release(s1);
+    B.tag(p + ".0", a);
+    Ten s2 = skips.back(); skips.pop_back();
+    Ten b = B.resblock(p + ".1", a, &s2); B.release(a); B.release(s2);
+    B.tag(p + ".1", b);
+    Ten c = B.attention(p + ".2", b); B.release(b);
+    B.tag(p + ".2", c);
+    const ConvW& uw = E.samp.at(p + ".3");
+    if (i < L - 1) cur = B.conv(uw, c, nullptr, true, nullptr, c.H * 2, c.W * 2);
+    else cur = B.conv_same(uw, c);
+    B.tag(p + ".3", cur);
+    B.release(c);
+  }
+  Ten f = B.resblock("final_res_block", cur, &r); B.release(cur); B.release(r);
+  B.tag("final_res_block", f);
+  if (B.err) return B.err;
+  {
+    const ConvW* c = &E.final_conv; Ten ff = f;
+    B.op([=](cudaStream_t s) { return launch_conv_cout1(ff.p, c->w, c->bias, out, (long long)N * H * W, ff.C, bf, s); });
+  }
+  B.release(f);
+  return B.finish();
+}
+
+static int run_plan(Engine& E, Plan& P, cudaStream_t s) {
+  if (P.zero_arena && cudaMemsetAsync(P.zero_arena, 0, P.zero_bytes, s) != cudaSuccess)
+    return fail(LD_ERR_CUDA, "memset of the zero arena failed");
+  for (auto& f : P.ops) {
+    int n = f(s);
+    if (n < 0) return fail(LD_ERR_CUDA, "kernel launch failed in plan");
+    E.launches += n;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(LD_ERR_CUDA, "launch error: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+static int check_shape(const Engine& E, int H, int W) {
+  const int f = 1 << (E.d.n_levels - 1);
+  if (H % f || W % f)  // ddpm.py:405
+    return fail(LD_ERR_INVALID, "your input dimensions (%d, %d) need to be divisible by %d, given the unet", H, W, f);
+  if (H % E.cond_div || W % E.cond_div) return fail(LD_ERR_INVALID, "input dimensions must be divisible by %d for the conditional encoder", E.cond_div);
+  if ((H >> (E.d.n_levels - 1)) != H / E.cond_div)
+    return fail(LD_ERR_INVALID, "UNet bottleneck (S/%d) and conditional encoder (S/%d) resolutions differ", f, E.cond_div);
+  return 0;
+}
+
+}  // namespace ld
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace ld;
+struct ld_handle { Engine E; };
+
+extern "C" {
+
+const char* ld_last_error(void) { return g_err; }
+const char* ld_version(void) { return "ld_sampler 0.1 sm_100a"; }
+
+int ld_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+  }
+  return ok;
+}
+
+int ld_create(const ld_model_desc* d, int device, ld_handle** out) {
+  if (!d || !out) return fail(LD_ERR_INVALID, "null argument");
+  if (d->n_levels < 1 || d->n_levels > LD_MAX_LEVELS) return fail(LD_ERR_INVALID, "n_levels out of range");
+  if (d->channels != 1) return fail(LD_ERR_INVALID, "only channels == 1 is supported on this path");
+  if (d->attn_dim_head != 32) return fail(LD_ERR_INVALID, "attn_dim_head must be 32");
+  if (d->dim % 32 || d->init_dim % 32) return fail(LD_ERR_INVALID, "dim and init_dim must be multiples of 32");
+  if (d->dim * d->dim_mults[d->n_levels - 1] != (d->cond_mode == LD_COND_MRI ? 256 : 128))
+    return fail(LD_ERR_INVALID, "dim*dim_mults[-1] must equal the conditional encoder width (ddpm.py:380, unet_model.py:100)");
+  if ((1 << (d->n_levels - 1)) != (d->cond_mode == LD_COND_MRI ? 8 : 4))
+    return fail(LD_ERR_INVALID, "number of levels does not match the conditional encoder depth");
+  ld_handle* h = new ld_handle();
+  h->E.d = *d; h->E.device = device;
+  h->E.bf = d->precision == LD_PREC_BF16;
+  h->E.use_tc = h->E.bf;
+  build_specs(h->E);
+  *out = h;
+  return 0;
+}
+
+int ld_destroy(ld_handle* h) {
+  if (!h) return 0;
+  if (ld_device_count() > 0) cudaSetDevice(h->E.device);
+  delete h;
+  return 0;
+}
+
+int ld_num_weights(const ld_handle* h) { return h ? (int)h->E.specs.size() : 0; }
+int ld_weight_info(const ld_handle* h, int i, const char** key, int64_t shape[4], int* ndim) {
+  if (!h || i < 0 || i >= (int)h->E.specs.size()) return fail(LD_ERR_INVALID, "weight index out of range");
+  const WSpec& s = h->E.specs[i];
+  if (key) *key = s.key.c_str();
+  if (ndim) *ndim = (int)s.shape.size();
+  if (shape) for (size_t k = 0; k < s.shape.size() && k < 4; ++k) shape[k] = s.shape[k];
+  return 0;
+}
+int ld_load_weight(ld_handle* h, const char* key, const float* data, const int64_t* shape, int ndim) {
+  if (!h || !key || !data) return fail(LD_ERR_INVALID, "null argument");
+  Engine& E = h->E;
+  if (E.finalized) return fail(LD_ERR_STATE, "weights already finalized");
+  auto it = E.index.find(key);
+  if (it == E.index.end()) return fail(LD_ERR_KEY, "unexpected key '%s'", key);
+  WSpec& s = E.specs[it->second];
+  if (s.loaded) return fail(LD_ERR_KEY, "key '%s' loaded twice", key);
+  if (ndim != (int)s.shape.size()) return fail(LD_ERR_KEY, "size mismatch for '%s' (ndim %d vs %zu)", key, ndim, s.shape.size());
+  for (int i = 0; i < ndim; ++i)
+    if (shape[i] != s.shape[i]) return fail(LD_ERR_KEY, "size mismatch for '%s' (dim %d: %lld vs %lld)", key, i, (long long)shape[i], (long long)s.shape[i]);
+  s.host.assign(data, data + s.numel());
+  s.loaded = true;
+  return 0;
+}
+int ld_finalize_weights(ld_handle* h) {
+  if (!h) return fail(LD_ERR_INVALID, "null handle");
+  if (ld_device_count() == 0) return fail(LD_ERR_NO_DEVICE, "no sm_100 CUDA device is available (there is no CPU fallback)");
+  Engine& E = h->E;
+  if (E.finalized) return fail(LD_ERR_STATE, "weights already finalized");
+  CK(cudaSetDevice(E.device));
+  if (!E.own_stream) {
+    CK(cudaStreamCreateWithFlags(&E.own_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&E.ev_in, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&E.ev_out, cudaEventDisableTiming));
+  }
+  return finalize(E);
+}
+
+int ld_set_schedule(ld_handle* h, int T, const float* c1, const float* c2, const float* logvar, const float* sigma) {
+  if (!h || T <= 0 || !c1 || !c2 || (!logvar && !sigma)) return fail(LD_ERR_INVALID, "bad schedule");
+  if (ld_device_count() == 0) return fail(LD_ERR_NO_DEVICE, "no sm_100 CUDA device is available (there is no CPU fallback)");
+  Engine& E = h->E;
+  CK(cudaSetDevice(E.device));
+  std::vector<float> sg(T);
+  for (int i = 0; i < T; ++i) sg[i] = sigma ? sigma[i] : expf(0.5f * logvar[i]);  // ddpm.py:853
+  if (E.coef1) { cudaFree(E.coef1); cudaFree(E.coef2); cudaFree(E.sigma); }
+  CK(cudaMalloc(&E.coef1, T * sizeof(float))); CK(cudaMalloc(&E.coef2, T * sizeof(float))); CK(cudaMalloc(&E.sigma, T * sizeof(float)));
+  CK(cudaMemcpy(E.coef1, c1, T * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(E.coef2, c2, T * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(E.sigma, sg.data(), T * sizeof(float), cudaMemcpyHostToDevice));
+  E.T = T;
+  return 0;
+}
+
+static int need_ready(Engine& E) {
+  if (ld_device_count() == 0) return fail(LD_ERR_NO_DEVICE, "no sm_100 CUDA device is available (there is no CPU fallback)");
+  if (!E.finalized) return fail(LD_ERR_STATE, "weights not finalized");
+  if (cudaSetDevice(E.device) != cudaSuccess) return fail(LD_ERR_CUDA, "cudaSetDevice failed");
+  return 0;
+}
+
+// plans for the stand-alone entry points read/write engine-owned staging buffers
+static int get_staged(ld_handle* h, int N, int H, int W, Staged** out) {
+  Engine& E = h->E;
+  char k[64]; snprintf(k, sizeof k, "%dx%dx%d", N, H, W);
+  auto it = E.staged.find(k);
+  if (it != E.staged.end()) { *out = &it->second; return 0; }
+  // keep at most one staged shape per handle (the workspace can be large)
+  for (auto& kv : E.staged) { kv.second.cond.reset(); kv.second.unet.reset(); kv.second.free_all(); }
+  E.staged.clear();
+  Staged& S = E.staged[k];
+  const size_t img = (size_t)N * H * W * sizeof(float);
+  const int fh = H / E.cond_div, fw = W / E.cond_div;
+  CK(cudaMalloc(&S.x, img)); CK(cudaMalloc(&S.c, img)); CK(cudaMalloc(&S.o, img));
+  CK(cudaMalloc(&S.feat, (size_t)N * fh * fw * E.cond_C * E.esz()));
+  CK(cudaMalloc(&S.t, N * sizeof(int64_t)));
+  S.cond.reset(new Plan()); S.unet.reset(new Plan());
+  int rc = build_cond_plan(E, *S.cond, N, H, W, S.c, S.feat);
+  if (rc) return rc;
+  rc = build_unet_plan(E, *S.unet, N, H, W, S.x, S.feat, S.t, nullptr, S.o);
+  if (rc) return rc;
+  *out = &S;
+  return 0;
+}
+
+int ld_unet_forward(ld_handle* h, const float* x, const float* cond, const int64_t* t, float* out, int N, int H, int W, void* stream) {
+  if (!h || !x || !cond || !t || !out) return fail(LD_ERR_INVALID, "null argument");
+  Engine& E = h->E;
+  int rc = need_ready(E); if (rc) return rc;
+  if ((rc = check_shape(E, H, W))) return rc;
+  Staged* S; if ((rc = get_staged(h, N, H, W, &S))) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t img = (size_t)N * H * W * sizeof(float);
+  CK(cudaMemcpyAsync(S->x, x, img, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(S->c, cond, img, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(S->t, t, N * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+  if ((rc = run_plan(E, *S->cond, s))) return rc;
+  if ((rc = run_plan(E, *S->unet, s))) return rc;
+  CK(cudaMemcpyAsync(out, S->o, img, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int ld_cond_encode(ld_handle* h, const float* cond, float* feat, int N, int H, int W, void* stream) {
+  if (!h || !cond || !feat) return fail(LD_ERR_INVALID, "null argument");
+  Engine& E = h->E;
+  int rc = need_ready(E); if (rc) return rc;
+  if ((rc = check_shape(E, H, W))) return rc;
+  Staged* S; if ((rc = get_staged(h, N, H, W, &S))) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(S->c, cond, (size_t)N * H * W * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if ((rc = run_plan(E, *S->cond, s))) return rc;
+  const int fh = H / E.cond_div, fw = W / E.cond_div;
+  E.launches += launch_nhwc_to_nchw_f32(S->feat, feat, N, fh * fw, E.cond_C, E.bf, s);
+  return 0;
+}
+
+// ---- sampler ----------------------------------------------------------------------------------
+static int dalloc(Engine& E, void** p, size_t bytes) {
+  CK(cudaMalloc(p, bytes));
+  E.ss.allocs.push_back(*p);
+  return 0;
+}
+
+static int prepare_sampler(Engine& E, const ld_sample_desc& sd) {
+  char k[128];
+  const bool pair_unet = sd.branch_out && !(sd.mask_x && sd.ood_uses_cond);
+  snprintf(k, sizeof k, "%dx%dx%d/b%d/p%d", sd.batch, sd.height, sd.width, sd.branch_out, (int)pair_unet);
+  if (E.ss.key == k) return 0;
+  E.free_samp(); E.plans.clear();
+  auto& S = E.ss;
+  S.B = sd.batch; S.H = sd.height; S.W = sd.width;
+  const size_t n = (size_t)sd.batch * sd.height * sd.width;
+  const int fh = sd.height / E.cond_div, fw = sd.width / E.cond_div;
+  const size_t featB = (size_t)sd.batch * fh * fw * E.cond_C * E.esz();
+  int rc;
+  if ((rc = dalloc(E, (void**)&S.xs, 2 * n * 4))) return rc;
+  if ((rc = dalloc(E, (void**)&S.o, 2 * n * 4))) return rc;
+  if ((rc = dalloc(E, (void**)&S.bm, n * 4))) return rc;
+  if ((rc = dalloc(E, (void**)&S.cond, n * 4))) return rc;
+  if ((rc = dalloc(E, (void**)&S.cond_out, 2 * n * 4))) return rc;  // [cond_out; cond_in] contiguous
+  S.cond_in = S.cond_out + n;
+  if ((rc = dalloc(E, &S.feat_pair, 2 * featB))) return rc;
+  if ((rc = dalloc(E, &S.feat_full, featB))) return rc;
+  if ((rc = dalloc(E, (void**)&S.counters, 4 * sizeof(unsigned int)))) return rc;
+  if ((rc = dalloc(E, (void**)&S.t_dev, sizeof(int)))) return rc;
+  const int B = sd.batch, H = sd.height, W = sd.width;
+  // conditional-feature plans (hoisted out of the loop: the encoder does not depend on t)
+  if (sd.branch_out) {
+    auto p = std::unique_ptr<Plan>(new Plan());
+    if (pair_unet) rc = build_cond_plan(E, *p, 2 * B, H, W, S.cond_out, S.feat_pair);
+    else rc = build_cond_plan(E, *p, B, H, W, S.cond_in, S.feat_pair);
+    if (rc) return rc;
+    E.plans["cond_pair"] = std::move(p);
+    p.reset(new Plan());
+    // branched UNet: x = [x_out; x_in] (or x_in only when the OOD output is discarded, ddpm.py:704-708)
+    if (pair_unet) rc = build_unet_plan(E, *p, 2 * B, H, W, S.xs, S.feat_pair, nullptr, S.t_dev, S.o);
+    else rc = build_unet_plan(E, *p, B, H, W, S.xs + n, S.feat_pair, nullptr, S.t_dev, S.o + n);
+    if (rc) return rc;
+    E.plans["unet_pair"] = std::move(p);
+  }
+  {
+    auto p = std::unique_ptr<Plan>(new Plan());
+    if ((rc = build_cond_plan(E, *p, B, H, W, S.cond, S.feat_full))) return rc;
+    E.plans["cond_full"] = std::move(p);
+    p.reset(new Plan());
+    if ((rc = build_unet_plan(E, *p, B, H, W, S.xs, S.feat_full, nullptr, S.t_dev, S.o))) return rc;
+    E.plans["unet_full"] = std::move(p);
+  }
+  S.key = k;
+  return 0;
+}
+
+static StepP make_step(Engine& E, const ld_sample_desc& sd, int kind, const float* noise, float* x0_trace) {
+  auto& S = E.ss;
+  const long long n = (long long)sd.batch * sd.height * sd.width;
+  StepP p{};
+  p.kind = kind;
+  p.o_out = S.o; p.o_in = S.o + n;
+  p.x_out = S.xs; p.x_in = S.xs + n;
+  p.bm = S.bm; p.cond_out = S.cond_out; p.z = noise;
+  p.t_ptr = S.t_dev; p.coef1 = E.coef1; p.coef2 = E.coef2; p.sigma = E.sigma;
+  p.mask_x = sd.mask_x; p.ood_uses_cond = sd.ood_uses_cond; p.lo = sd.min_val; p.hi = sd.max_val;
+  p.n = n; p.z_stride = n; p.tloop = sd.num_timesteps; p.counters = S.counters;
+  p.x0_trace = x0_trace; p.trace_stride = 2 * n;
+  return p;
+}
+
+static int capture(Engine& E, cudaGraphExec_t* exec, const std::function<int(cudaStream_t)>& body) {
+  cudaStream_t s = E.own_stream;
+  CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  int rc = body(s);
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(s, &g);
+  if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+  if (e != cudaSuccess) return fail(LD_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+  e = cudaGraphInstantiate(exec, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return fail(LD_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int ld_sample(ld_handle* h, const ld_sample_desc* sdp, const float* cond, const float* mask, const float* noise, float* out,
+              float* x0_trace, void* stream) {
+  if (!h || !sdp || !cond || !noise || !out) return fail(LD_ERR_INVALID, "null argument");
+  Engine& E = h->E;
+  const ld_sample_desc sd = *sdp;
+  int rc = need_ready(E); if (rc) return rc;
+  if (!E.T) return fail(LD_ERR_STATE, "schedule not set");
+  if (sd.num_timesteps < 1 || sd.num_timesteps > E.T) return fail(LD_ERR_INVALID, "num_timesteps out of range");
+  if (sd.branch_out && !mask) return fail(LD_ERR_INVALID, "branch mode needs a mask");
+  if ((rc = check_shape(E, sd.height, sd.width))) return rc;
+  if ((rc = prepare_sampler(E, sd))) return rc;
+  auto& S = E.ss;
+  cudaStream_t cs = (cudaStream_t)stream, s = E.own_stream;
+  const long long n = (long long)sd.batch * sd.height * sd.width;
+  const bool pair_unet = sd.branch_out && !(sd.mask_x && sd.ood_uses_cond);
+  // hand over from the caller's stream to the engine stream
+  CK(cudaEventRecord(E.ev_in, cs));
+  CK(cudaStreamWaitEvent(s, E.ev_in, 0));
+  CK(cudaMemsetAsync(S.counters, 0, 4 * sizeof(unsigned int), s));
+  CK(cudaMemcpyAsync(S.cond, cond, n * 4, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(S.xs, noise, n * 4, cudaMemcpyDeviceToDevice, s));          // x_T (ddpm.py:935)
+  const int t0 = sd.num_timesteps - 1;
+  CK(cudaMemcpyAsync(S.t_dev, &t0, sizeof(int), cudaMemcpyHostToDevice, s));
+  bool branched = sd.branch_out != 0;
+  if (branched) {
+    CK(cudaMemcpyAsync(S.xs + n, noise, n * 4, cudaMemcpyDeviceToDevice, s));    // img = [img, img] (ddpm.py:957)
+    PrepP pp{}; pp.cond = S.cond; pp.mask = mask; pp.bm = S.bm; pp.cond_out = S.cond_out; pp.cond_in = S.cond_in;
+    pp.floor = sd.cond_in_floor; pp.n = n; pp.counters = S.counters;
+    E.launches += launch_prep_cond(pp, s);
+    if ((rc = run_plan(E, *E.plans["cond_pair"], s))) return rc;
+  }
+  const bool will_fuse = branched && sd.start_intermediate && sd.start_timestep >= 0;
+  if (!branched || will_fuse) { if ((rc = run_plan(E, *E.plans["cond_full"], s))) return rc; }
+
+  Plan* up = branched ? E.plans["unet_pair"].get() : nullptr;
+  Plan* uf = E.plans["unet_full"].get();
+  auto body_branch = [&](cudaStream_t st) -> int {
+    int r = run_plan(E, *up, st); if (r) return r;
+    StepP p = make_step(E, sd, 0, noise, x0_trace);
+    if (!pair_unet) p.o_out = nullptr;
+    E.launches += launch_step(p, st); E.launches += launch_dec_t(S.t_dev, st);
+    return 0;
+  };
+  auto body_single = [&](cudaStream_t st) -> int {
+    int r = run_plan(E, *uf, st); if (r) return r;
+    StepP p = make_step(E, sd, 2, noise, x0_trace);
+    E.launches += launch_step(p, st); E.launches += launch_dec_t(S.t_dev, st);
+    return 0;
+  };
+  // graphs bake the tape / trace pointers: re-capture on every call (cheap next to T replays)
+  if (S.g_branch) { cudaGraphExecDestroy(S.g_branch); S.g_branch = nullptr; }
+  if (S.g_single) { cudaGraphExecDestroy(S.g_single); S.g_single = nullptr; }
+  const bool use_graph = E.opt_use_graph != 0;
+  int64_t per_branch = 0, per_single = 0;
+  if (use_graph) {
+    int64_t l0 = E.launches;
+    if (branched) { if ((rc = capture(E, &S.g_branch, body_branch))) return rc; per_branch = E.launches - l0; }
+    l0 = E.launches;
+    if ((rc = capture(E, &S.g_single, body_single))) return rc;
+    per_single = E.launches - l0;
+    E.launches -= per_branch + per_single;  // captured, not launched
+  }
+  for (int t = sd.num_timesteps - 1; t >= 0; --t) {
+    if (branched) {
+      const bool fuse = sd.start_intermediate && t <= sd.start_timestep;  // ddpm.py:779
+      if (fuse) {
+        if ((rc = run_plan(E, *up, s))) return rc;
+        StepP p = make_step(E, sd, 1, noise, x0_trace);
+        if (!pair_unet) p.o_out = nullptr;
+        E.launches += launch_step(p, s); E.launches += launch_dec_t(S.t_dev, s);
+        branched = false;  // config['branch_out'] = False (ddpm.py:780)
+      } else if (use_graph) {
+        CK(cudaGraphLaunch(S.g_branch, s)); E.launches += per_branch;
+      } else if ((rc = body_branch(s))) return rc;
+    } else {
+      if (use_graph) { CK(cudaGraphLaunch(S.g_single, s)); E.launches += per_single; }
+      else if ((rc = body_single(s))) return rc;
+    }
+  }
+  // result (ddpm.py:964-970)
+  if (sd.return_pair) {
+    CK(cudaMemcpyAsync(out, S.xs, n * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(out + n, branched ? S.xs + n : S.xs, n * 4, cudaMemcpyDeviceToDevice, s));
+  } else {
+    CK(cudaMemcpyAsync(out, S.xs, n * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  unsigned int cnt[4];
+  CK(cudaMemcpyAsync(cnt, S.counters, sizeof cnt, cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(E.ev_out, s));
+  CK(cudaStreamWaitEvent(cs, E.ev_out, 0));
+  CK(cudaStreamSynchronize(s));
+  if (sd.branch_out && sd.mask_x && (cnt[0] == 0 || cnt[1] == 0)) return fail(LD_ERR_MASK, "mask should be binary");
+  if (sd.branch_out && will_fuse && sd.num_timesteps - 1 >= 0 && !(cnt[2] > 0 && cnt[3] > 0) && (sd.start_timestep >= 0))
+    return fail(LD_ERR_MASK, "x_out and x_in should be masked");
+  return 0;
+}
+
+int ld_posterior_step(ld_handle* h, int kind, int t, float* x_out, float* x_in, float* x0_out, float* x0_in, const float* cond,
+                      const float* mask, const float* z, const ld_sample_desc* sd, int64_t n, void* stream) {
+  if (!h || !sd || !x_out || !x0_out) return fail(LD_ERR_INVALID, "null argument");
+  Engine& E = h->E;
+  if (ld_device_count() == 0) return fail(LD_ERR_NO_DEVICE, "no sm_100 CUDA device is available (there is no CPU fallback)");
+  if (!E.T || t < 0 || t >= E.T) return fail(LD_ERR_STATE, "schedule not set or t out of range");
+  CK(cudaSetDevice(E.device));
+  if (kind != 2 && (!mask || !cond || !x_in || !x0_in)) return fail(LD_ERR_INVALID, "branched step needs mask, cond and both branches");
+  cudaStream_t s = (cudaStream_t)stream;
+  float *bm = nullptr, *co = nullptr, *ci = nullptr, *oo = nullptr, *oi = nullptr; unsigned int* cnt = nullptr; int* td = nullptr;
+  CK(cudaMalloc(&bm, n * 4)); CK(cudaMalloc(&co, n * 4)); CK(cudaMalloc(&ci, n * 4));
+  CK(cudaMalloc(&oo, n * 4)); CK(cudaMalloc(&oi, n * 4));
+  CK(cudaMalloc(&cnt, 16)); CK(cudaMalloc(&td, 4));
+  CK(cudaMemsetAsync(cnt, 0, 16, s));
+  CK(cudaMemcpyAsync(td, &t, 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(oo, x0_out, n * 4, cudaMemcpyDeviceToDevice, s));
+  if (x0_in) CK(cudaMemcpyAsync(oi, x0_in, n * 4, cudaMemcpyDeviceToDevice, s));
+  if (kind != 2) {
+    PrepP pp{}; pp.cond = cond; pp.mask = mask; pp.bm = bm; pp.cond_out = co; pp.cond_in = ci; pp.floor = sd->cond_in_floor;
+    pp.n = n; pp.counters = cnt;
+    E.launches += launch_prep_cond(pp, s);
+  }
+  StepP p{};
+  p.kind = kind; p.o_out = oo; p.o_in = oi; p.x_out = x_out; p.x_in = x_in; p.x0_out = x0_out; p.x0_in = x0_in;
+  p.bm = bm; p.cond_out = co; p.z = z; p.t_ptr = td; p.coef1 = E.coef1; p.coef2 = E.coef2; p.sigma = E.sigma;
+  p.mask_x = sd->mask_x; p.ood_uses_cond = sd->ood_uses_cond; p.lo = sd->min_val; p.hi = sd->max_val;
+  p.n = n; p.z_stride = 0; p.tloop = t; p.counters = cnt;
+  E.launches += launch_step(p, s);
+  CK(cudaStreamSynchronize(s));
+  cudaFree(bm); cudaFree(co); cudaFree(ci); cudaFree(oo); cudaFree(oi); cudaFree(cnt); cudaFree(td);
+  return 0;
+}
+
+// ---- test hooks ---------------------------------------------------------------------------------
+static Plan* last_staged_unet(Engine& E) {
+  if (E.staged.empty()) return nullptr;
+  return E.staged.begin()->second.unet.get();
+}
+int ld_debug_num_taps(ld_handle* h) {
+  Plan* P = h ? last_staged_unet(h->E) : nullptr;
+  return P ? (int)P->tags.size() : 0;
+}
+int ld_debug_tap_info(ld_handle* h, int i, const char** name, int32_t dims[4]) {
+  Plan* P = h ? last_staged_unet(h->E) : nullptr;
+  if (!P || i < 0 || i >= (int)P->tags.size()) return fail(LD_ERR_INVALID, "tap index out of range");
+  *name = P->tags[i].first.c_str();
+  const Ten& t = P->tags[i].second;
+  dims[0] = t.N; dims[1] = t.C; dims[2] = t.H; dims[3] = t.W;
+  return 0;
+}
+int ld_debug_tap_fetch(ld_handle* h, int i, float* out_nchw, void* stream) {
+  Plan* P = h ? last_staged_unet(h->E) : nullptr;
+  if (!P || i < 0 || i >= (int)P->tags.size()) return fail(LD_ERR_INVALID, "tap index out of range");
+  const Ten& t = P->tags[i].second;
+  launch_nhwc_to_nchw_f32(t.p, out_nchw, t.N, t.H * t.W, t.C, h->E.bf, (cudaStream_t)stream);
+  return 0;
+}
+
+int ld_debug_conv(int kernel, const float* x0, int C0, const float* x1, int C1, int N, int Hin, int Win, int up, int H, int W,
+                  const float* w_host, const float* bias_host, int Cout, int ks, const float* res, float* out, void* stream) {
+  if (ld_device_count() == 0) return fail(LD_ERR_NO_DEVICE, "no sm_100 CUDA device is available (there is no CPU fallback)");
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool bf = kernel != 0;
+  const int Cin = C0 + C1, taps = ks * ks;
+  const size_t esz = bf ? 2 : 4;
+  std::vector<float> pk((size_t)taps * Cin * Cout);
+  for (int o = 0; o < Cout; ++o)
+    for (int c = 0; c < Cin; ++c)
+      for (int t = 0; t < taps; ++t) pk[((size_t)t * Cin + c) * Cout + o] = w_host[((size_t)o * Cin + c) * taps + t];
+  float *dw = nullptr, *db = nullptr; void *a0 = nullptr, *a1 = nullptr, *ar = nullptr, *ao = nullptr;
+  const size_t nin = (size_t)N * Hin * Win, nout = (size_t)N * H * W;
+  CK(cudaMalloc(&dw, pk.size() * 4)); CK(cudaMemcpy(dw, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
+  if (bias_host) { CK(cudaMalloc(&db, Cout * 4)); CK(cudaMemcpy(db, bias_host, Cout * 4, cudaMemcpyHostToDevice)); }
+  CK(cudaMalloc(&a0, nin * C0 * esz)); launch_convert(x0, false, a0, bf, (long long)nin * C0, s);
+  if (x1) { CK(cudaMalloc(&a1, nin * C1 * esz)); launch_convert(x1, false, a1, bf, (long long)nin * C1, s); }
+  if (res) { CK(cudaMalloc(&ar, nout * Cout * esz)); launch_convert(res, false, ar, bf, (long long)nout * Cout, s); }
+  CK(cudaMalloc(&ao, nout * Cout * esz));
+  int rc = 0;
+  if (kernel == 2) {
+    ConvTcW tw;
+    if (conv_tc_pack(pk.data(), bias_host, Cin, Cout, ks, 1, ks / 2, &tw) || !tw.ready) rc = fail(LD_ERR_INVALID, "conv_tc_pack: unsupported shape");
+    else {
+      ConvTcArgs ta; ta.src0 = a0; ta.C0 = C0; ta.src1 = a1; ta.C1 = C1; ta.N = N; ta.H = H; ta.W = W; ta.Hin = Hin; ta.Win = Win;
+      ta.up = up; ta.dst = ao; ta.res = ar;
+      if (conv_tc_launch(tw, ta, s) < 0) rc = fail(LD_ERR_INVALID, "conv_tc_launch: unsupported arguments");
+    }
+    cudaStreamSynchronize(s);
+    cudaFree(tw.w); cudaFree(tw.w32); cudaFree(tw.bias);
+  } else {
+    ConvP p{};
+    p.src0 = a0; p.C0 = C0; p.src1 = a1; p.C1 = C1; p.N = N; p.H = H; p.W = W; p.Hin = Hin; p.Win = Win;
+    p.ks = ks; p.stride = 1; p.pad = ks / 2; p.up = up; p.w = dw; p.bias = db; p.Cout = Cout; p.dst = ao; p.res = ar;
+    p.M = (long long)nout;
+    launch_conv_simt(p, bf, s);
+  }
+  launch_convert(ao, bf, out, false, (long long)nout * Cout, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  cudaFree(dw); cudaFree(db); cudaFree(a0); cudaFree(a1); cudaFree(ar); cudaFree(ao);
+  if (e != cudaSuccess) return fail(LD_ERR_CUDA, "debug conv failed: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+int64_t ld_launch_count(const ld_handle* h) { return h ? h->E.launches : 0; }
+int64_t ld_workspace_bytes(const ld_handle* h) {
+  if (!h) return 0;
+  int64_t b = 0;
+  for (auto& kv : h->E.plans) b += (int64_t)kv.second->total_bytes;
+  return b;
+}
+int ld_set_option(ld_handle* h, const char* name, int64_t value) {
+  if (!h || !name) return fail(LD_ERR_INVALID, "null argument");
+  if (!strcmp(name, "micro_batch")) h->E.opt_micro_batch = value;
+  else if (!strcmp(name, "use_graph")) h->E.opt_use_graph = value;
+  else if (!strcmp(name, "debug_keep")) h->E.opt_debug_keep = value;
+  else if (!strcmp(name, "use_tc")) { if (h->E.finalized) return fail(LD_ERR_STATE, "use_tc must be set before finalize"); h->E.use_tc = value != 0 && h->E.bf; }
+  else return fail(LD_ERR_INVALID, "unknown option '%s'", name);
+  return 0;
+}
+
+}  // extern "C"

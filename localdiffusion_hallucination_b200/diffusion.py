@@ -1,0 +1,168 @@
+"""`GaussianDiffusion` -- the reference's sampler API (ddpm.py:496-1125) hosted on the sm_100a engine.
+
+Host side (this file): constructor contract, the 13 schedule buffers, the per-call `config`
+fix-ups and their mutation semantics (ddpm.py:1080-1119), noise-tape generation in the reference's
+draw order.  Device side (C ABI `ld_sample`): the whole T-step loop -- IND/OOD UNet launch, masked
+x0, clamp, posterior update, one-off fusion composite -- with no host round trip per step.
+"""
+import ctypes as C
+
+import torch
+from torch import nn
+
+from . import _lib
+from .schedule import make_buffers
+
+_NON_MRI = ("mnist", "mvtec", "oct", "imagenet")
+
+
+class GaussianDiffusion(nn.Module):
+    def __init__(self, config, model, *, image_size, timesteps=1000, sampling_timesteps=None, objective="pred_v",
+                 beta_schedule="sigmoid", schedule_fn_kwargs=dict(), ddim_sampling_eta=0.0, auto_normalize=False,
+                 offset_noise_strength=0.0, min_snr_loss_weight=False, min_snr_gamma=5):
+        super().__init__()
+        assert not (type(self) == GaussianDiffusion and model.channels != model.out_dim)  # ddpm.py:515
+        assert not model.random_or_learned_sinusoidal_cond  # ddpm.py:516
+        self.config = config  # shared by reference and mutated, like the reference (ddpm.py:518)
+        self.branch_out = self.config["branch_out"]
+        self.start_intermediate = self.config["start_intermediate"]
+        self.model = model
+        self.cnt = -1
+        self.channels = model.channels
+        self.self_condition = model.self_condition
+        self.image_size = image_size
+        self.objective = objective
+        assert objective in {"pred_noise", "pred_x0", "pred_v"}, \
+            "objective must be either pred_noise (predict noise) or pred_x0 (predict image start) or pred_v"
+        bufs = make_buffers(beta_schedule, timesteps, objective, min_snr_loss_weight, min_snr_gamma, **schedule_fn_kwargs)
+        for k, v in bufs.items():
+            self.register_buffer(k, v)
+        self.num_timesteps = int(timesteps)
+        self.num_timesteps_ori = int(timesteps)
+        self.sampling_timesteps = sampling_timesteps if sampling_timesteps is not None else timesteps
+        assert self.sampling_timesteps <= timesteps  # ddpm.py:561
+        self.is_ddim_sampling = self.sampling_timesteps < timesteps
+        self.ddim_sampling_eta = ddim_sampling_eta
+        if auto_normalize:
+            raise NotImplementedError("auto_normalize=True is not used by the reference's drivers (test.py:138)")
+        self._schedule_on = None
+        self.last_x_start = None
+
+    def call_classifier(self):  # ddpm.py:622-625
+        if self.config.get("classifier", False):
+            raise NotImplementedError("the PatchCore classifier gate is outside the sampler hot path (SURVEY.md §2)")
+
+    @property
+    def device(self):
+        return self.betas.device
+
+    # ---------------------------------------------------------------------------------------
+    def _push_schedule(self, h):
+        key = (h.value, self.device)
+        if self._schedule_on == key:
+            return
+        c1 = self.posterior_mean_coef1.detach().cpu().contiguous()
+        c2 = self.posterior_mean_coef2.detach().cpu().contiguous()
+        lv = self.posterior_log_variance_clipped.detach().cpu().contiguous()
+        sg = (0.5 * lv).exp().contiguous()  # ddpm.py:853
+        _lib.check(_lib.lib().ld_set_schedule(h, c1.numel(), c1.data_ptr(), c2.data_ptr(), lv.data_ptr(), sg.data_ptr()))
+        self._schedule_on = key
+
+    def make_noise_tape(self, shape, steps, device):
+        """x_T then one draw per step for t = steps-1 .. 1, in the reference's order (ddpm.py:934-935, 852/857)."""
+        torch.manual_seed(10)
+        tape = torch.empty((steps,) + tuple(shape), device=device)
+        for i in range(steps):
+            tape[i] = torch.randn(shape, device=device)
+        return tape
+
+    @torch.inference_mode()
+    def sample(self, cond_img, gt, batch_size=16, return_all_timesteps=False, return_all_outputs=False, mask=None,
+               ood_confidence_ad=False, min_max_val=None, instance=0, noise=None):
+        """Same signature as the reference (ddpm.py:1078) plus `noise=`: an optional host- or
+        device-resident tape `[T, B, C, S, S]` (x_T first) replacing the seed-10 device draws."""
+        cfg = self.config
+        self.instance = instance
+        self.cnt += 1
+        self.min_max_val = min_max_val
+        # --- per-call flag fix-ups, ddpm.py:1093-1117 ---
+        if cfg["branch_out"] == False:  # noqa: E712 (mirrors the reference's comparison)
+            cfg["branch_out"] = self.branch_out
+        if cfg["start_intermediate"] == False:  # noqa: E712
+            cfg["start_intermediate"] = self.start_intermediate
+        self.start_intermediate = bool(cfg["start_intermediate"])
+        if cfg["ood_AD"] or cfg["ood_confidence"]:
+            cfg["mask_cond"] = True
+            cfg["mask_x"] = True
+        if cfg["branch_out"]:
+            u = torch.unique(mask)
+            if len(u) == 1 and u == 1:
+                cfg["mask_cond"] = cfg["mask_x"] = cfg["branch_out"] = cfg["start_intermediate"] = False
+        if self.is_ddim_sampling:
+            raise NotImplementedError("DDIM branch sampling (ddpm.py:979-1075) is a 'next' row (SURVEY.md §8f)")
+        if return_all_timesteps:
+            raise NotImplementedError("return_all_timesteps stacks branch lists and fails in the reference (ddpm.py:964)")
+        if cfg["branch_out"] and self.objective != "pred_x0":
+            raise UnboundLocalError("branch sampling needs objective='pred_x0' (ddpm.py:731-761)")
+        if self.objective != "pred_x0":
+            raise NotImplementedError("only objective='pred_x0' is on the sampler hot path")
+        if cfg.get("classifier", False) and cfg["start_intermediate"]:
+            raise NotImplementedError("classifier gate is out of scope (ddpm.py:883-916)")
+
+        h = self.model.engine()
+        dev = self.model._handle_device
+        self._push_schedule(h)
+        B, Cc, S = batch_size, self.channels, self.image_size
+        steps = self.num_timesteps
+        use_gt = bool(self.start_intermediate and cfg.get("use_gt", False))
+        if use_gt:
+            steps = int(cfg["use_gt_timestep"])
+        if noise is None:
+            noise = self.make_noise_tape((B, Cc, S, S), steps, dev)
+        noise = noise.to(dev, torch.float32)
+        assert noise.shape[0] >= steps and tuple(noise.shape[1:]) == (B, Cc, S, S)
+        if use_gt:  # ddpm.py:937-944: start from q_sample(gt, t)
+            tg = int(cfg["use_gt_timestep"])
+            noise = noise.clone()
+            noise[0] = self.sqrt_alphas_cumprod[tg] * gt.to(dev) + self.sqrt_one_minus_alphas_cumprod[tg] * noise[0]
+            self.num_timesteps = tg
+        noise = noise.contiguous()
+        cond = cond_img.to(dev, torch.float32).contiguous()
+        assert tuple(cond.shape) == (B, Cc, S, S)
+        mk = mask.to(dev, torch.float32).contiguous() if mask is not None else None
+
+        sd = _lib.SampleDesc()
+        sd.batch, sd.height, sd.width, sd.num_timesteps = B, S, S, steps
+        sd.branch_out = int(bool(cfg["branch_out"]))
+        sd.start_intermediate = int(bool(cfg["start_intermediate"]))
+        sd.start_timestep = int(cfg["start_timestep"])
+        sd.mask_x = int(bool(cfg["mask_x"]))
+        data = cfg["data"]
+        sd.ood_uses_cond = int(any(s in data for s in _NON_MRI) and "mri" not in data)  # ddpm.py:704-708
+        sd.cond_in_floor = 0.5 if data == "mnist" else 0.95  # ddpm.py:683-686
+        sd.min_val, sd.max_val = float(min_max_val[0]), float(min_max_val[1])
+        pair = (not self.start_intermediate) and bool(self.branch_out)  # ddpm.py:965-970
+        sd.return_pair = int(pair)
+        sd.record_x0 = int(return_all_outputs)
+        out = torch.empty((2, B, Cc, S, S) if pair else (B, Cc, S, S), device=dev)
+        trace = torch.zeros((steps, 2, B, Cc, S, S), device=dev) if return_all_outputs else None
+        will_fuse = sd.branch_out and sd.start_intermediate
+        rc = _lib.lib().ld_sample(h, C.byref(sd), cond.data_ptr(), mk.data_ptr() if mk is not None else None,
+                                  noise.data_ptr(), out.data_ptr(), trace.data_ptr() if trace is not None else None,
+                                  C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        if will_fuse:  # the fusion step flips these for the rest of the call (ddpm.py:780-781)
+            cfg["branch_out"] = False
+            cfg["mask_x"] = False
+        _lib.check(rc)
+        if return_all_outputs:  # ddpm.py:973-974: (ret, x_start_lst, confidence_map)
+            lst = []
+            branched = bool(sd.branch_out)
+            for i in range(steps):
+                t = steps - 1 - i
+                if branched and not (sd.start_intermediate and t <= sd.start_timestep):
+                    lst.append([trace[i, 0].cpu(), trace[i, 1].cpu()])
+                else:
+                    branched = False
+                    lst.append(trace[i, 0].cpu())
+            return out, lst, []
+        return out

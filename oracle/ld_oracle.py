@@ -157,44 +157,52 @@ def _attn(sd, hp: UnetHP, pfx: str, x: Tensor, full: bool) -> Tensor:
     return linear_attention(sd, pfx, x, hp.heads, hp.dim_head)
 
 
-def unet_forward(sd: Dict[str, Tensor], hp: UnetHP, x: Tensor, cond: Tensor, t: Tensor) -> Tensor:
+def unet_forward(sd: Dict[str, Tensor], hp: UnetHP, x: Tensor, cond: Tensor, t: Tensor, taps: Optional[dict] = None) -> Tensor:
     """ddpm.py:404-451 (`Unet.forward`), self_condition off.
 
     `sd` is `Unet.state_dict()` (keys without the `model.` prefix).  `t` is int64 `[B]`.
+    `taps`, when given, receives named intermediate activations (for layer-wise parity tests).
     """
+    def tap(name, v):
+        if taps is not None:
+            taps[name] = v
+        return v
+
     L = len(hp.dim_mults)
     assert x.shape[-1] % (2 ** (L - 1)) == 0 and x.shape[-2] % (2 ** (L - 1)) == 0  # ddpm.py:405
     g = hp.groups
-    x = F.conv2d(x, sd["init_conv.weight"], sd["init_conv.bias"], padding=3)
+    x = tap("init_conv", F.conv2d(x, sd["init_conv.weight"], sd["init_conv.bias"], padding=3))
     r = x
     temb = time_embedding(sd, hp, t.float())
     skips: List[Tensor] = []
     for i in range(L):
         p = "downs.%d." % i
-        x = resnet_block(sd, p + "0", x, temb, g)
+        x = tap(p + "0", resnet_block(sd, p + "0", x, temb, g))
         skips.append(x)
-        x = resnet_block(sd, p + "1", x, temb, g)
-        x = _attn(sd, hp, p + "2", x, hp.full_attn[i]) + x
+        x = tap(p + "1", resnet_block(sd, p + "1", x, temb, g))
+        x = tap(p + "2", _attn(sd, hp, p + "2", x, hp.full_attn[i]) + x)
         skips.append(x)
         if i < L - 1:  # ddpm.py:120-124: pixel-unshuffle (c p1 p2) then 1x1
             x = F.conv2d(F.pixel_unshuffle(x, 2), sd[p + "3.1.weight"], sd[p + "3.1.bias"])
         else:  # ddpm.py:372
             x = F.conv2d(x, sd[p + "3.weight"], sd[p + "3.bias"], padding=1)
-    x = resnet_block(sd, "mid_block1", x, temb, g)
-    x = full_attention(sd, "mid_attn", x, hp.heads, hp.dim_head) + x
-    x = resnet_block(sd, "mid_block2", x, temb, g)
+        tap(p + "3", x)
+    x = tap("mid_block1", resnet_block(sd, "mid_block1", x, temb, g))
+    x = tap("mid_attn", full_attention(sd, "mid_attn", x, hp.heads, hp.dim_head) + x)
+    x = tap("mid_block2", resnet_block(sd, "mid_block2", x, temb, g))
     x = torch.cat((x, cond_encoder(sd, hp, cond)), dim=1)  # ddpm.py:434-435
-    x = resnet_block(sd, "conv_fusion", x, None, g)  # ddpm.py:436 -- called WITHOUT t
+    x = tap("conv_fusion", resnet_block(sd, "conv_fusion", x, None, g))  # ddpm.py:436 -- called WITHOUT t
     for i in range(L):
         p = "ups.%d." % i
-        x = resnet_block(sd, p + "0", torch.cat((x, skips.pop()), dim=1), temb, g)
-        x = resnet_block(sd, p + "1", torch.cat((x, skips.pop()), dim=1), temb, g)
-        x = _attn(sd, hp, p + "2", x, hp.full_attn[L - 1 - i]) + x
+        x = tap(p + "0", resnet_block(sd, p + "0", torch.cat((x, skips.pop()), dim=1), temb, g))
+        x = tap(p + "1", resnet_block(sd, p + "1", torch.cat((x, skips.pop()), dim=1), temb, g))
+        x = tap(p + "2", _attn(sd, hp, p + "2", x, hp.full_attn[L - 1 - i]) + x)
         if i < L - 1:  # ddpm.py:114-118: nearest x2 then 3x3
             x = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), sd[p + "3.1.weight"], sd[p + "3.1.bias"], padding=1)
         else:  # ddpm.py:391
             x = F.conv2d(x, sd[p + "3.weight"], sd[p + "3.bias"], padding=1)
-    x = resnet_block(sd, "final_res_block", torch.cat((x, r), dim=1), temb, g)
+        tap(p + "3", x)
+    x = tap("final_res_block", resnet_block(sd, "final_res_block", torch.cat((x, r), dim=1), temb, g))
     return F.conv2d(x, sd["final_conv.weight"], sd["final_conv.bias"])
 
 

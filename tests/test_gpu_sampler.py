@@ -1,0 +1,116 @@
+"""GPU: `GaussianDiffusion.sample` through the C ABI against golden vectors / the oracle."""
+import ctypes as C
+
+import pytest
+import torch
+
+from localdiffusion_hallucination_b200 import GaussianDiffusion, _lib
+from oracle import ld_oracle as lo
+from tests import util
+from tests.golden import cases
+from tests.test_oracle_golden import SAMPLER_CASES, sampler_inputs
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def run_case(key, precision, **opts):
+    name, data, S, T, s, B, over, sched, cond, mask, mm = sampler_inputs(key)
+    m = util.make_model(name, precision, device=DEV, **opts)
+    cfg = cases.base_config(data, s, **over)
+    gd = GaussianDiffusion(cfg, m, image_size=S, timesteps=T, beta_schedule=sched, objective="pred_x0").to(DEV)
+    out = gd.sample(cond, None, batch_size=B, mask=mask, min_max_val=mm, noise=cases.noise_tape(B, S, T))
+    return out, cfg, mm, gd
+
+
+@pytest.mark.parametrize("key", list(SAMPLER_CASES))
+def test_sampler_fp32_matches_reference_golden(golden, key):
+    out, cfg, mm, _ = run_case(key, "fp32")
+    ref = torch.from_numpy(golden[f"{key}_out"])
+    assert tuple(out.shape) == tuple(ref.shape)
+    assert util.max_abs(out, ref) < 2e-3 * mm[1]
+    assert util.psnr(out, ref, mm[1]) > 60.0
+    assert repr(cfg) == str(golden[f"{key}_cfg_after"])  # config-dict mutation semantics (ddpm.py:780-781, 1093-1117)
+
+
+@pytest.mark.parametrize("key", ["c1", "c1mri", "c2s", "c1pair"])
+def test_sampler_bf16_psnr(golden, key):
+    """north_star: final images >= 40 dB PSNR on the bf16 path (peak = clamp range)."""
+    out, cfg, mm, _ = run_case(key, "bf16")
+    ref = torch.from_numpy(golden[f"{key}_out"])
+    assert util.psnr(out, ref, mm[1]) > 40.0
+
+
+def test_graph_replay_equals_eager_launches(golden):
+    a, *_ = run_case("c1mri", "fp32", use_graph=1)
+    b, *_ = run_case("c1mri", "fp32", use_graph=0)
+    assert torch.equal(a, b)
+
+
+def test_second_call_restores_flags_and_reproduces():
+    name, data, S, T, s, B, over, sched, cond, mask, mm = sampler_inputs("c1mri")
+    m = util.make_model(name, "fp32", device=DEV)
+    cfg = cases.base_config(data, s)
+    gd = GaussianDiffusion(cfg, m, image_size=S, timesteps=T, objective="pred_x0").to(DEV)
+    tape = cases.noise_tape(B, S, T)
+    a = gd.sample(cond, None, batch_size=B, mask=mask, min_max_val=mm, noise=tape)
+    assert cfg["branch_out"] is False and cfg["mask_x"] is False
+    b = gd.sample(cond, None, batch_size=B, mask=mask, min_max_val=mm, noise=tape)
+    assert torch.equal(a, b)
+
+
+def test_return_all_outputs_structure():
+    name, data, S, T, s, B, over, sched, cond, mask, mm = sampler_inputs("c1mri")
+    m = util.make_model(name, "fp32", device=DEV)
+    gd = GaussianDiffusion(cases.base_config(data, s), m, image_size=S, timesteps=T, objective="pred_x0").to(DEV)
+    ret, x0s, conf = gd.sample(cond, None, batch_size=B, mask=mask, min_max_val=mm, noise=cases.noise_tape(B, S, T),
+                               return_all_outputs=True)
+    assert len(x0s) == T and conf == []
+    assert isinstance(x0s[0], list) and len(x0s[0]) == 2 and not isinstance(x0s[-1], list)
+    # OOD-branch x0 is exactly min_val outside the mask (ddpm.py:700-703): bit-exact mask / branch indexing
+    bm = (mask >= 1.0)
+    assert torch.equal(x0s[0][0][~bm], torch.full_like(x0s[0][0][~bm], mm[0]))
+    assert float(x0s[-1].min()) >= mm[0] and float(x0s[-1].max()) <= mm[1]
+
+
+def test_non_binary_mask_raises_assertion():
+    m = util.make_model("mnist", "fp32", device=DEV)
+    gd = GaussianDiffusion(cases.base_config("mri", 2), m, image_size=32, timesteps=4, objective="pred_x0").to(DEV)
+    with pytest.raises(AssertionError):
+        gd.sample(cases.cond_uniform(1, 32), None, batch_size=1, mask=0.3 * torch.rand(1, 1, 32, 32), min_max_val=(0.0, 2.0),
+                  noise=cases.noise_tape(1, 32, 4))
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_posterior_step_is_bit_exact(kind):
+    """Mask / branch indexing and the DDPM update are bit-exact against the oracle given the same UNet outputs."""
+    lib = _lib.lib()
+    T, t, n = 50, 7, 4 * 32 * 32
+    m = util.make_model("mnist", "fp32", device=DEV)
+    cfg = cases.base_config("mri", t if kind == 1 else 0)
+    gd = GaussianDiffusion(cfg, m, image_size=32, timesteps=T, objective="pred_x0").to(DEV)
+    h = m.engine()
+    gd._push_schedule(h)
+    g = torch.Generator().manual_seed(3)
+    o_out, o_in = 3 * torch.randn(4, 1, 32, 32, generator=g), 3 * torch.randn(4, 1, 32, 32, generator=g)
+    x_out, x_in, z = (torch.randn(4, 1, 32, 32, generator=g) for _ in range(3))
+    cond, mask = cases.cond_uniform(4, 32), cases.mask_left_columns(4, 32)
+    mask[:, :, 5:9, 20:25] = 0.7  # soft, non-OOD values
+    # oracle, with the denoiser stubbed to return the same "UNet outputs"
+    outs = iter([o_out, o_in] if kind != 2 else [o_out])
+    ocfg = cases.base_config("mri", t if kind == 1 else 0, branch_out=kind != 2)
+    smp = lo.Sampler(ocfg, {}, util.hp_of("mnist"), image_size=32, timesteps=T, model_fn=lambda *a: next(outs).clone())
+    x = [x_out.clone(), x_in.clone()] if kind != 2 else x_out.clone()
+    ref, x0 = smp._p_sample(x, mask, (0.0, 2.0), cond, t, lambda: z.clone())
+    # device
+    sd = _lib.SampleDesc()
+    sd.mask_x, sd.ood_uses_cond, sd.cond_in_floor, sd.min_val, sd.max_val = 1, 0, 0.95, 0.0, 2.0
+    d = [v.clone().to(DEV).contiguous() for v in (x_out, x_in, o_out, o_in, cond, mask, z)]
+    _lib.check(lib.ld_posterior_step(h, kind, t, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), d[4].data_ptr(),
+                                     d[5].data_ptr(), d[6].data_ptr(), C.byref(sd), n, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    if kind == 0:
+        assert torch.equal(d[0].cpu(), ref[0]) and torch.equal(d[1].cpu(), ref[1])
+        assert torch.equal(d[2].cpu(), x0[0]) and torch.equal(d[3].cpu(), x0[1])
+    else:
+        assert torch.equal(d[0].cpu(), ref) and torch.equal(d[2].cpu(), x0)
