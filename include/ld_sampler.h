@@ -164,6 +164,10 @@ LD_API int ld_debug_tap_fetch(ld_handle* h, int index, float* out_nchw, void* st
 LD_API int ld_debug_conv(int kernel, const float* x0, int C0, const float* x1, int C1, int N, int Hin,
                          int Win, int up, int H, int W, const float* w_host, const float* bias_host,
                          int Cout, int ks, const float* res, float* out, void* stream);
+/* Average device time (ms, CUDA events on `stream`) of `iters` launches of one convolution kernel on
+ * synthetic operands; used by bench.py for the roofline of the dominant kernel. */
+LD_API int ld_debug_conv_time(int kernel, int C0, int C1, int N, int H, int W, int up, int Cout, int ks,
+                              int iters, float* ms_out, void* stream);
 
 #ifdef __cplusplus
 }

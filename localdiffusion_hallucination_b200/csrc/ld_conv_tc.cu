@@ -316,15 +316,26 @@ size_t smem_bytes(int NT) {
   return (size_t)SA * Geo<KS, KC>::A_STAGE + (size_t)SB * NT * KC * 2 + (2 * SA + 2 * SB + 1) * 8 + 16;
 }
 
+// opt in to > 48 KB dynamic shared memory once per instantiation (done at pack time, outside any graph capture)
+template <int NT, int KS, int KC>
+int configure_one() {
+  const size_t sm = smem_bytes<KS, KC>(NT);
+  return cudaFuncSetAttribute(conv_tc_kernel<NT, KS, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) == cudaSuccess ? 0 : -1;
+}
+template <int KS, int KC>
+int configure_nt(int NT) {
+  switch (NT) {
+    case 32: return configure_one<32, KS, KC>();
+    case 64: return configure_one<64, KS, KC>();
+    case 128: return configure_one<128, KS, KC>();
+    case 256: return configure_one<256, KS, KC>();
+  }
+  return -1;
+}
+
 template <int NT, int KS, int KC>
 int launch_one(const KParams& p, dim3 grid, cudaStream_t s) {
-  const size_t sm = smem_bytes<KS, KC>(NT);
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(conv_tc_kernel<NT, KS, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return -1;
-    configured = true;
-  }
-  conv_tc_kernel<NT, KS, KC><<<grid, kThreads, sm, s>>>(p);
+  conv_tc_kernel<NT, KS, KC><<<grid, kThreads, smem_bytes<KS, KC>(NT), s>>>(p);
   return 1;
 }
 
@@ -381,6 +392,8 @@ int conv_tc_pack(const float* w, const float* bias, int Cin, int Cout, int ks, i
     if (cudaMalloc(&out->bias, Cout * sizeof(float)) != cudaSuccess) return -1;
     if (cudaMemcpy(out->bias, bias, Cout * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
   }
+  if (ks == 3) { if (configure_nt<3, 64>(nt) || configure_nt<3, 32>(nt)) return -1; }
+  else { if (configure_nt<1, 64>(nt) || configure_nt<1, 32>(nt)) return -1; }
   out->ready = true;
   return 0;
 }

