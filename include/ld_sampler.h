@@ -164,6 +164,16 @@ LD_API int ld_debug_tap_fetch(ld_handle* h, int index, float* out_nchw, void* st
 LD_API int ld_debug_conv(int kernel, const float* x0, int C0, const float* x1, int C1, int N, int Hin,
                          int Win, int up, int H, int W, const float* w_host, const float* bias_host,
                          int Cout, int ks, const float* res, float* out, void* stream);
+/* Test hook: 3x3 tcgen05 convolution with the fused GroupNorm prologue (normalise-on-load of the source, ddpm.py:174-185)
+ * and the fused GroupNorm statistics of its output.  x0/out: fp32 NHWC device; w/bias: host, torch layout. */
+LD_API int ld_debug_conv_fused(const float* x0, int C0, int N, int H, int W, const float* w_host, const float* bias_host,
+                               int Cout, const double* pro_stats, const float* pro_gamma, const float* pro_beta,
+                               const float* pro_film, int pro_film_stride, int pro_G, int pro_act, double* stats_out,
+                               int stats_G, float* out, void* stream);
+/* Test hook: the fused tcgen05 LinearAttention block, attn(x) + x (ddpm.py:214-251, 425).  x/out: fp32 NHWC device;
+ * wqkv [384][C], g [C], wout [C][128], bout [C], g2 [C]: host fp32 in the reference's parameter layout. */
+LD_API int ld_debug_linattn(const float* x, int C, int N, int HW, const float* wqkv, const float* g, const float* wout,
+                            const float* bout, const float* g2, float* out, void* stream);
 /* Average device time (ms, CUDA events on `stream`) of `iters` launches of one convolution kernel on
  * synthetic operands; used by bench.py for the roofline of the dominant kernel. */
 LD_API int ld_debug_conv_time(int kernel, int C0, int C1, int N, int H, int W, int up, int Cout, int ks,

@@ -23,6 +23,15 @@ struct ConvTcArgs {
   int up = 0;                  // read src0 through a nearest x2 up-sampling
   void* dst = nullptr;         // bf16 [N,H,W,Cout]
   const void* res = nullptr;   // optional bf16 residual added in the epilogue
+  // fused "normalise on load" prologue on src0 (3x3, single source, no up-sampling):
+  //   x' = act(GroupNorm(x; pro_stats, gamma, beta) * (scale + 1) + shift)   (ddpm.py:174-185, unet_model.py:21-22)
+  const double* pro_stats = nullptr;   // [N][pro_G][2] {sum, sumsq} of src0 (as written by `stats` of its producer)
+  const float* pro_gamma = nullptr; const float* pro_beta = nullptr;   // [C0]
+  const float* pro_film = nullptr; int pro_film_stride = 0;            // per image [2*C0] (scale, shift) or null
+  int pro_G = 0, pro_act = 0;          // act: 0 none, 1 SiLU, 2 ReLU
+  float pro_eps = 1e-5f;
+  // fused GroupNorm statistics of the output (3x3 only): stats[n][stats_G][2] += {sum, sumsq}; zeroed by the caller
+  double* stats = nullptr; int stats_G = 0;
 };
 
 // host: pack fp32 [taps][Cin][Cout] weights; leaves `ready == false` for unsupported shapes

@@ -19,6 +19,7 @@
 #include "../../include/ld_sampler.h"
 #include "ld_conv_tc.h"
 #include "ld_kernels.h"
+#include "ld_linattn_tc.h"
 
 namespace ld {
 
@@ -59,7 +60,7 @@ struct ConvW {
 };
 
 struct ResW { ConvW c1, c2, res; bool has_res = false, has_film = false; int film_off = 0; float *g1, *b1, *g2, *b2; int Cin, Cout; };
-struct AttnW { bool full; int C; float* g; ConvW qkv; ConvW out; float* g2 = nullptr; };
+struct AttnW { bool full; int C; float* g; ConvW qkv; ConvW out; float* g2 = nullptr; LinAttnTcW la; };
 struct CondW { ConvW a, b, id; float *ga, *ba, *gb, *bb, *gi, *bi; int Cin, Cmid, Cout; };
 
 // -------------------------------------------------------------------------------------------------
@@ -116,7 +117,8 @@ struct Engine {
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   int64_t launches = 0;
-  int64_t opt_micro_batch = 0, opt_use_graph = 1, opt_debug_keep = 0;
+  int64_t opt_micro_batch = 0, opt_use_graph = 1, opt_debug_keep = 0, opt_la_exact = 0;
+  unsigned int* la_flag = nullptr;        // soft-max underflow counter of the fused LinearAttention
   std::map<std::string, std::unique_ptr<Plan>> plans;
   std::map<std::string, Staged> staged;   // stand-alone entry points (ld_unet_forward / ld_cond_encode)
   // sampler-owned state
@@ -138,6 +140,8 @@ struct Engine {
     for (auto& kv : staged) { kv.second.cond.reset(); kv.second.unet.reset(); kv.second.free_all(); }
     staged.clear();
     for (void* p : dev_allocs) cudaFree(p);
+    for (auto& kv : attn) linattn_tc_free(&kv.second.la);
+    if (la_flag) cudaFree(la_flag);
     if (coef1) cudaFree(coef1);
     if (coef2) cudaFree(coef2);
     if (sigma) cudaFree(sigma);
@@ -308,6 +312,10 @@ static int pack_attn(Engine& E, const std::string& p, int C, bool full) {
   else {
     if ((rc = pack_conv(E, p + ".to_out.0", true, false, &a.out))) return rc;
     if ((rc = vecp(E, p + ".to_out.1.g", &a.g2))) return rc;
+    if (E.use_tc && E.d.attn_heads == 4 && E.d.attn_dim_head == 32 &&
+        linattn_tc_pack(W(E, p + ".to_qkv.weight").host.data(), W(E, p + ".norm.g").host.data(), W(E, p + ".to_out.0.weight").host.data(),
+                        W(E, p + ".to_out.0.bias").host.data(), W(E, p + ".to_out.1.g").host.data(), C, E.d.attn_heads, &a.la))
+      return fail(LD_ERR_CUDA, "linattn_tc_pack(%s) failed", p.c_str());
   }
   E.attn[p] = a;
   return 0;
@@ -371,6 +379,8 @@ static int finalize(Engine& E) {
     E.samp[p + ".3"] = cw;
   }
   if ((rc = pack_res(E, "final_res_block", true, fw, fb))) return rc;
+  CK(cudaMalloc(&E.la_flag, sizeof(unsigned int)));
+  CK(cudaMemset(E.la_flag, 0, sizeof(unsigned int)));
   E.film_total = (int)fb.size();
   if ((rc = upload(E, fw, &E.film_w))) return rc;
   if ((rc = upload(E, fb, &E.film_b))) return rc;
@@ -408,46 +418,88 @@ struct Builder {
   // zero-initialised scratch (GN statistics, linear-attention accumulators): one memset per forward
   void* zalloc(size_t bytes) {
     bytes = (bytes + 255) & ~(size_t)255;
+    if (P.zero_used == 0) P.zero_used = 256;  // offset 0 is reserved: a null offset means "absent"
     size_t off = P.zero_used; P.zero_used += bytes;
     return (void*)off;  // resolved after the arena is allocated
   }
   template <typename F> void op(F f) { P.ops.emplace_back(std::move(f)); }
 
   // ---- convolution dispatch -----------------------------------------------------------------
-  Ten conv(const ConvW& cw, const Ten& a, const Ten* b, bool up, const Ten* resid, int outH, int outW) {
-    Ten o = act(a.N, outH, outW, cw.Cout);
-    if (err) return o;
+  // GroupNorm (+FiLM) + activation of the SOURCE tensor, applied while the conv stages its input
+  struct ProSpec { double* st; const float* g; const float* b; int G; int film_off; int act; };
+  // conv with optional fused prologue (normalise-on-load) and fused GroupNorm statistics of the output.
+  // `stats_off` / `pro->st` are zero-arena offsets.  Whatever the selected kernel cannot fuse is run as a
+  // separate pass, so callers are uniform across the fp32 (CUDA-core) and bf16 (tcgen05) paths.
+  Ten conv(const ConvW& cw, const Ten& a_in, const Ten* b, bool up, const Ten* resid, int outH, int outW,
+           const ProSpec* pro = nullptr, double* stats_off = nullptr, int stats_G = 0) {
     const bool bf = E.bf;
+    Plan* pp = &P;
+    Ten a = a_in;
+    bool own_a = false;
     ConvTcArgs ta;
+    bool use_tc = false;
     if (E.use_tc && cw.tc.ready) {
       ta.src0 = a.p; ta.C0 = a.C; ta.src1 = b ? b->p : nullptr; ta.C1 = b ? b->C : 0;
       ta.N = a.N; ta.H = outH; ta.W = outW; ta.Hin = a.H; ta.Win = a.W; ta.up = up ? 1 : 0;
-      ta.dst = o.p; ta.res = resid ? resid->p : nullptr;
-      if (conv_tc_supports(cw.tc, ta)) {
-        const ConvTcW* w = &cw.tc;
-        op([ta, w](cudaStream_t s) { return conv_tc_launch(*w, ta, s); });
-        return o;
-      }
+      ta.res = resid ? resid->p : nullptr;
+      use_tc = conv_tc_supports(cw.tc, ta);
     }
-    ConvP p{};
-    p.src0 = a.p; p.C0 = a.C; p.src1 = b ? b->p : nullptr; p.C1 = b ? b->C : 0;
-    p.N = a.N; p.H = outH; p.W = outW; p.Hin = a.H; p.Win = a.W;
-    p.ks = cw.ks; p.stride = cw.stride; p.pad = cw.pad; p.up = up ? 1 : 0;
-    p.w = cw.w; p.bias = cw.bias; p.Cout = cw.Cout; p.dst = o.p; p.res = resid ? resid->p : nullptr;
-    p.M = (long long)a.N * outH * outW;
-    op([p, bf](cudaStream_t s) { return launch_conv_simt(p, bf, s); });
+    bool pro_fused = false, stats_fused = false;
+    if (use_tc && pro) {
+      ConvTcArgs t2 = ta;
+      t2.pro_stats = (const double*)8; t2.pro_G = pro->G; t2.pro_act = pro->act;
+      pro_fused = conv_tc_supports(cw.tc, t2);
+    }
+    if (use_tc && stats_off) {
+      ConvTcArgs t2 = ta;
+      t2.stats = (double*)8; t2.stats_G = stats_G;
+      stats_fused = conv_tc_supports(cw.tc, t2);
+    }
+    if (pro && !pro_fused) {  // materialise the normalised activation
+      a = gn_apply(a_in, pro->st, pro->g, pro->b, pro->G, pro->film_off, pro->act, nullptr, 0);
+      own_a = true;
+      ta.src0 = a.p;
+    }
+    Ten o = act(a.N, outH, outW, cw.Cout);
+    if (err) return o;
+    if (use_tc) {
+      ta.dst = o.p;
+      const ConvTcW* w = &cw.tc;
+      const size_t pro_off = pro_fused ? (size_t)pro->st : 0, st_off = stats_fused ? (size_t)stats_off : 0;
+      if (pro_fused) {
+        ta.pro_gamma = pro->g; ta.pro_beta = pro->b; ta.pro_G = pro->G; ta.pro_act = pro->act; ta.pro_eps = 1e-5f;
+        ta.pro_film = pro->film_off >= 0 ? film + pro->film_off : nullptr; ta.pro_film_stride = E.film_total;
+      }
+      if (stats_fused) ta.stats_G = stats_G;
+      op([ta, w, pp, pro_fused, stats_fused, pro_off, st_off](cudaStream_t s) {
+        ConvTcArgs q = ta;
+        if (pro_fused) q.pro_stats = (const double*)((char*)pp->zero_arena + pro_off);
+        if (stats_fused) q.stats = (double*)((char*)pp->zero_arena + st_off);
+        return conv_tc_launch(*w, q, s);
+      });
+    } else {
+      ConvP p{};
+      p.src0 = a.p; p.C0 = a.C; p.src1 = b ? b->p : nullptr; p.C1 = b ? b->C : 0;
+      p.N = a.N; p.H = outH; p.W = outW; p.Hin = a.H; p.Win = a.W;
+      p.ks = cw.ks; p.stride = cw.stride; p.pad = cw.pad; p.up = up ? 1 : 0;
+      p.w = cw.w; p.bias = cw.bias; p.Cout = cw.Cout; p.dst = o.p; p.res = resid ? resid->p : nullptr;
+      p.M = (long long)a.N * outH * outW;
+      op([p, bf](cudaStream_t s) { return launch_conv_simt(p, bf, s); });
+    }
+    if (own_a) release(a);
+    if (stats_off && !stats_fused) stats_into(o, stats_G, stats_off);
     return o;
   }
-  Ten conv_same(const ConvW& cw, const Ten& a, const Ten* b = nullptr, const Ten* resid = nullptr) {
-    return conv(cw, a, b, false, resid, a.H, a.W);
+  Ten conv_same(const ConvW& cw, const Ten& a, const Ten* b = nullptr, const Ten* resid = nullptr,
+                const ProSpec* pro = nullptr, double* stats_off = nullptr, int stats_G = 0) {
+    return conv(cw, a, b, false, resid, a.H, a.W, pro, stats_off, stats_G);
   }
-  double* stats(const Ten& x, int G) {
-    double* st = (double*)zalloc((size_t)x.N * G * 2 * sizeof(double));
+  double* stats_alloc(int N, int G) { return (double*)zalloc((size_t)N * G * 2 * sizeof(double)); }
+  void stats_into(const Ten& x, int G, double* st) {
     Plan* pp = &P; const bool bf = E.bf; Ten xx = x;
     op([pp, st, xx, G, bf](cudaStream_t s) {
       return launch_gn_stats(xx.p, (double*)((char*)pp->zero_arena + (size_t)st), xx.N, xx.H * xx.W, xx.C, G, bf, s);
     });
-    return st;
   }
   // out = act(GN(xa)*film) (+ xb variants), see GnApplyP
   Ten gn_apply(const Ten& xa, double* stA, const float* gA, const float* bA, int GA, int film_off, int act,
@@ -471,16 +523,17 @@ struct Builder {
   Ten act_t(const Ten& like) { return act(like.N, like.H, like.W, like.C); }
 
   // ---- ResnetBlock (ddpm.py:200-212) -----------------------------------------------------------
+  // block1: conv (+ statistics in its epilogue); block2: conv whose staging applies GN1 + FiLM + SiLU and whose
+  // epilogue gathers the GN2 statistics; one elementwise pass: SiLU(GN2(h2)) + res_conv(x).
   Ten resblock(const std::string& name, Ten& a, Ten* b) {
     const ResW& r = E.res[E.res_index.at(name)];
     const int G = E.d.resnet_groups;
-    Ten h1 = conv_same(r.c1, a, b);
-    double* s1 = stats(h1, G);
-    Ten a1 = gn_apply(h1, s1, r.g1, r.b1, G, r.has_film ? r.film_off : -1, 1, nullptr, 0);
+    double* s1 = stats_alloc(a.N, G);
+    Ten h1 = conv_same(r.c1, a, b, nullptr, nullptr, s1, G);
+    ProSpec pr{s1, r.g1, r.b1, G, r.has_film ? r.film_off : -1, 1};
+    double* s2 = stats_alloc(a.N, G);
+    Ten h2 = conv_same(r.c2, h1, nullptr, nullptr, &pr, s2, G);
     release(h1);
-    Ten h2 = conv_same(r.c2, a1);
-    release(a1);
-    double* s2 = stats(h2, G);
     Ten o;
     if (r.has_res) {
       Ten rs = conv_same(r.res, a, b);
@@ -497,6 +550,24 @@ struct Builder {
     const AttnW& a = E.attn.at(name);
     const bool bf = E.bf;
     const int heads = E.d.attn_heads, hid = heads * 32;
+    if (!a.full && a.la.ready && !E.opt_la_exact) {
+      // fused tcgen05 LinearAttention: x is read twice, the result written once (ld_linattn_tc.cu)
+      Ten out = act_t(x);
+      Ten mn = alloc(x.N, 1, 1, 128 * x.C, 2);
+      LinAttnTcArgs la;
+      la.x = x.p; la.out = out.p; la.N = x.N; la.HW = x.H * x.W; la.Mn = mn.p; la.flag = E.la_flag;
+      const size_t ctx_off = (size_t)zalloc((size_t)x.N * 128 * 32 * 4), ks_off = (size_t)zalloc((size_t)x.N * 128 * 4);
+      const LinAttnTcW* w = &a.la;
+      Plan* pp = &P;
+      op([pp, la, w, ctx_off, ks_off](cudaStream_t s) {
+        LinAttnTcArgs q = la;
+        q.ctx = (float*)((char*)pp->zero_arena + ctx_off);
+        q.ksum = (float*)((char*)pp->zero_arena + ks_off);
+        return linattn_tc_launch(*w, q, s);
+      });
+      release(mn);
+      return out;
+    }
     Ten xn = act_t(x);
     {
       Ten xx = x, o = xn; const float* g = a.g;
@@ -538,21 +609,20 @@ struct Builder {
   Ten cond_block(const CondW& c, const Ten* xin, const float* img, int N, int H, int W) {
     const bool bf = E.bf;
     Ten a, id;
+    double *sa = stats_alloc(N, 16), *si = stats_alloc(N, 16), *sb = stats_alloc(N, 16);
     if (c.Cin == 1) {
       a = act(N, H, W, c.Cmid); id = act(N, H, W, c.Cout);
       const ConvW *ca = &c.a, *ci = &c.id; Ten aa = a, ii = id;
       op([=](cudaStream_t s) { return launch_conv_c1(img, ca->w, ca->bias, aa.p, N, H, W, ca->Cout, 3, bf, s); });
       op([=](cudaStream_t s) { return launch_conv_c1(img, ci->w, ci->bias, ii.p, N, H, W, ci->Cout, 3, bf, s); });
+      stats_into(a, 16, sa); stats_into(id, 16, si);
     } else {
-      a = conv_same(c.a, *xin); id = conv_same(c.id, *xin);
+      a = conv_same(c.a, *xin, nullptr, nullptr, nullptr, sa, 16);
+      id = conv_same(c.id, *xin, nullptr, nullptr, nullptr, si, 16);
     }
-    double* sa = stats(a, 16);
-    Ten a1 = gn_apply(a, sa, c.ga, c.ba, 16, -1, 2, nullptr, 0);
+    ProSpec pr{sa, c.ga, c.ba, 16, -1, 2};
+    Ten b2 = conv_same(c.b, a, nullptr, nullptr, &pr, sb, 16);
     release(a);
-    Ten b2 = conv_same(c.b, a1);
-    release(a1);
-    double* sb = stats(b2, 16);
-    double* si = stats(id, 16);
     Ten o = gn_apply(b2, sb, c.gb, c.bb, 16, -1, 2, &id, 2, si, c.gi, c.bi, 16);
     release(b2); release(id);
     return o;
@@ -1042,11 +1112,16 @@ int ld_sample(ld_handle* h, const ld_sample_desc* sdp, const float* cond, const 
   } else {
     CK(cudaMemcpyAsync(out, S.xs, n * 4, cudaMemcpyDeviceToDevice, s));
   }
-  unsigned int cnt[4];
+  unsigned int cnt[4], la_under = 0;
   CK(cudaMemcpyAsync(cnt, S.counters, sizeof cnt, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&la_under, E.la_flag, sizeof la_under, cudaMemcpyDeviceToHost, s));
   CK(cudaEventRecord(E.ev_out, s));
   CK(cudaStreamWaitEvent(cs, E.ev_out, 0));
   CK(cudaStreamSynchronize(s));
+  if (la_under) {
+    cudaMemset(E.la_flag, 0, sizeof(unsigned int));
+    return fail(LD_ERR_STATE, "LinearAttention soft-max shift underflowed (%u rows): set option la_exact=1 for the exact-max path", la_under);
+  }
   if (sd.branch_out && sd.mask_x && (cnt[0] == 0 || cnt[1] == 0)) return fail(LD_ERR_MASK, "mask should be binary");
   if (sd.branch_out && will_fuse && sd.num_timesteps - 1 >= 0 && !(cnt[2] > 0 && cnt[3] > 0) && (sd.start_timestep >= 0))
     return fail(LD_ERR_MASK, "x_out and x_in should be masked");
@@ -1155,6 +1230,65 @@ int ld_debug_conv(int kernel, const float* x0, int C0, const float* x1, int C1, 
   return rc;
 }
 
+// 3x3 tcgen05 convolution with the fused GroupNorm prologue / statistics epilogue (test hook).
+int ld_debug_conv_fused(const float* x0, int C0, int N, int H, int W, const float* w_host, const float* bias_host, int Cout,
+                        const double* pro_stats, const float* pro_gamma, const float* pro_beta, const float* pro_film,
+                        int pro_film_stride, int pro_G, int pro_act, double* stats_out, int stats_G, float* out, void* stream) {
+  if (ld_device_count() == 0) return fail(LD_ERR_NO_DEVICE, "no sm_100 CUDA device is available (there is no CPU fallback)");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int taps = 9;
+  std::vector<float> pk((size_t)taps * C0 * Cout);
+  for (int o = 0; o < Cout; ++o)
+    for (int c = 0; c < C0; ++c)
+      for (int t = 0; t < taps; ++t) pk[((size_t)t * C0 + c) * Cout + o] = w_host[((size_t)o * C0 + c) * taps + t];
+  const size_t npx = (size_t)N * H * W;
+  void *a0 = nullptr, *ao = nullptr;
+  CK(cudaMalloc(&a0, npx * C0 * 2)); launch_convert(x0, false, a0, true, (long long)npx * C0, s);
+  CK(cudaMalloc(&ao, npx * Cout * 2));
+  if (stats_out) CK(cudaMemsetAsync(stats_out, 0, (size_t)N * stats_G * 2 * sizeof(double), s));
+  ConvTcW tw;
+  int rc = 0;
+  if (conv_tc_pack(pk.data(), bias_host, C0, Cout, 3, 1, 1, &tw) || !tw.ready) rc = fail(LD_ERR_INVALID, "conv_tc_pack: unsupported shape");
+  else {
+    ConvTcArgs ta; ta.src0 = a0; ta.C0 = C0; ta.N = N; ta.H = H; ta.W = W; ta.Hin = H; ta.Win = W; ta.dst = ao;
+    ta.pro_stats = pro_stats; ta.pro_gamma = pro_gamma; ta.pro_beta = pro_beta; ta.pro_film = pro_film;
+    ta.pro_film_stride = pro_film_stride; ta.pro_G = pro_G; ta.pro_act = pro_act; ta.pro_eps = 1e-5f;
+    ta.stats = stats_out; ta.stats_G = stats_G;
+    if (conv_tc_launch(tw, ta, s) < 0) rc = fail(LD_ERR_INVALID, "conv_tc_launch: unsupported arguments");
+  }
+  launch_convert(ao, true, out, false, (long long)npx * Cout, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  cudaFree(tw.w); cudaFree(tw.w32); cudaFree(tw.bias); cudaFree(a0); cudaFree(ao);
+  if (e != cudaSuccess) return fail(LD_ERR_CUDA, "debug fused conv failed: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+// Fused tcgen05 LinearAttention block, attn(x) + x (test hook).  x/out: fp32 NHWC device; weights: host, torch layout.
+int ld_debug_linattn(const float* x, int C, int N, int HW, const float* wqkv, const float* g, const float* wout, const float* bout,
+                     const float* g2, float* out, void* stream) {
+  if (ld_device_count() == 0) return fail(LD_ERR_NO_DEVICE, "no sm_100 CUDA device is available (there is no CPU fallback)");
+  cudaStream_t s = (cudaStream_t)stream;
+  LinAttnTcW w;
+  if (linattn_tc_pack(wqkv, g, wout, bout, g2, C, 4, &w) || !w.ready) return fail(LD_ERR_INVALID, "linattn_tc_pack: unsupported shape");
+  const size_t n = (size_t)N * HW * C;
+  void *xb = nullptr, *ob = nullptr, *mn = nullptr; float *ctx = nullptr, *ks = nullptr; unsigned int* flag = nullptr;
+  CK(cudaMalloc(&xb, n * 2)); CK(cudaMalloc(&ob, n * 2)); CK(cudaMalloc(&mn, (size_t)N * 128 * C * 2));
+  CK(cudaMalloc(&ctx, (size_t)N * 128 * 32 * 4)); CK(cudaMalloc(&ks, (size_t)N * 128 * 4)); CK(cudaMalloc(&flag, 4));
+  CK(cudaMemsetAsync(ctx, 0, (size_t)N * 128 * 32 * 4, s)); CK(cudaMemsetAsync(ks, 0, (size_t)N * 128 * 4, s)); CK(cudaMemsetAsync(flag, 0, 4, s));
+  launch_convert(x, false, xb, true, (long long)n, s);
+  LinAttnTcArgs a; a.x = xb; a.out = ob; a.N = N; a.HW = HW; a.ctx = ctx; a.ksum = ks; a.Mn = mn; a.flag = flag;
+  int rc = linattn_tc_launch(w, a, s) < 0 ? fail(LD_ERR_INVALID, "linattn_tc_launch failed") : 0;
+  launch_convert(ob, true, out, false, (long long)n, s);
+  unsigned int under = 0;
+  cudaMemcpyAsync(&under, flag, 4, cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  cudaFree(xb); cudaFree(ob); cudaFree(mn); cudaFree(ctx); cudaFree(ks); cudaFree(flag);
+  linattn_tc_free(&w);
+  if (e != cudaSuccess) return fail(LD_ERR_CUDA, "debug linattn failed: %s", cudaGetErrorString(e));
+  if (!rc && under) return fail(LD_ERR_STATE, "soft-max shift underflowed (%u rows)", under);
+  return rc;
+}
+
 // Time one convolution kernel in isolation with CUDA events on its launch stream (bench.py roofline leg).
 int ld_debug_conv_time(int kernel, int C0, int C1, int N, int H, int W, int up, int Cout, int ks, int iters, float* ms_out,
                        void* stream) {
@@ -1212,6 +1346,7 @@ int ld_set_option(ld_handle* h, const char* name, int64_t value) {
   if (!strcmp(name, "micro_batch")) h->E.opt_micro_batch = value;
   else if (!strcmp(name, "use_graph")) h->E.opt_use_graph = value;
   else if (!strcmp(name, "debug_keep")) h->E.opt_debug_keep = value;
+  else if (!strcmp(name, "la_exact")) h->E.opt_la_exact = value;
   else if (!strcmp(name, "use_tc")) { if (h->E.finalized) return fail(LD_ERR_STATE, "use_tc must be set before finalize"); h->E.use_tc = value != 0 && h->E.bf; }
   else return fail(LD_ERR_INVALID, "unknown option '%s'", name);
   return 0;

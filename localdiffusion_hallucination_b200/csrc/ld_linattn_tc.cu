@@ -1,0 +1,572 @@
+// LinearAttention (ddpm.py:214-251) fused into two tcgen05 kernels for sm_100a (heads = 4, dim_head = 32).
+//
+// The reference materialises qkv = to_qkv(RMSNorm(x)) ([384, H*W] per image, 768 B per pixel in bf16), two
+// soft-maxes and two einsums.  Here x is read twice and the result written once; qkv never leaves the SM:
+//
+//   pass A  `la_ctx_kernel`   per 64-pixel half tile:
+//        producers   x -> x/|x| (RMSNorm, g*sqrt(C) folded into the weights) -> bf16 -> smem  [64 px][C]
+//        MMA1        K^T[128 (h,d)][64 px], V^T[128 (h,e)][64 px] = W'_{k,v} . xhat^T      (tcgen05, TMEM)
+//        transform   thread = row: ek = exp(k - bound_d) -> bf16 -> smem P[(h,d)][px];  v -> bf16 -> smem V[(h,e)][px]
+//        MMA2        CTX[128 (h,d)][128 (h',e)] += P . V^T  accumulated in TMEM over all tiles of the CTA
+//        end         diagonal (h == h') blocks and the row sums of ek are added to ctx[n], ksum[n]
+//      soft-max over the pixel axis is shift invariant; instead of a separate max pass the shift is the
+//      analytic bound |k_d| <= |W'_k[d,:]| (|xhat| = 1).  `la_fold_kernel` raises a flag if a row sum underflowed.
+//   fold   `la_fold_kernel`   Mn[n][c][(h,d)] = 32^-0.5 * sum_e Wout[c][(h,e)] ctx[n][h][d][e] / ksum[n][(h,d)]  (bf16, UMMA layout)
+//   pass B  `la_out_kernel`   per 128-pixel tile (two transform warp-groups ping-pong on alternate tiles):
+//        MMA1        Q[128 px][128 (h,d)] = xhat . W'_q^T
+//        transform   thread = pixel: per-head soft-max over d -> bf16 -> smem P[px][(h,d)]
+//        MMA2        O[128 px][C] = P . Mn^T
+//        epilogue    + bias -> RMSNorm(g2) -> + x (residual of ddpm.py:425) -> bf16 -> global
+#include <cuda_bf16.h>
+#include <math.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "ld_linattn_tc.h"
+#include "ld_tc_common.cuh"
+
+namespace ld {
+
+using namespace tc;
+
+namespace {
+
+constexpr int kThreads = 13 * 32;  // warps 0-3 producers, 4 MMA, 5-12 transform/epilogue
+constexpr int kMmaWarp = 4;
+constexpr int kXfWarp0 = 5;
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct CtxParams {
+  const __nv_bfloat16* x;   // [N][HW][C]
+  const __nv_bfloat16* wkv; // packed [2][C/8][128][8]
+  const float* kb2;         // [128] log2(e) * bound of |k_d|
+  float* ctx;               // [N][4][32][32]
+  float* ksum;              // [N][128]
+  int HW, slices;
+};
+struct OutParams {
+  const __nv_bfloat16* x;   // [N][HW][C]
+  const __nv_bfloat16* wq;  // packed [C/8][128][8]
+  const __nv_bfloat16* Mn;  // [N] packed [16][C][8]
+  const float* bout; const float* g2;
+  __nv_bfloat16* out;
+  int HW, slices;
+};
+
+// stage ROWS pixels of x/|x| as a K-major operand: 16-byte chunk (pixel p, channels 8*c8..) at c8*ROWS*16 + p*16
+template <int C, int ROWS>
+__device__ __forceinline__ void stage_xhat(const __nv_bfloat16* __restrict__ ximg, int px0, int HW, uint8_t* stage, int tid) {
+  constexpr int LP = C / 8;                 // lanes per pixel
+  constexpr int ITEMS = ROWS * LP / 128;
+  constexpr int BATCH = ITEMS < 8 ? ITEMS : 8;
+  const int c8 = tid % LP;
+#pragma unroll 1
+  for (int it0 = 0; it0 < ITEMS; it0 += BATCH) {
+    uint4 v[BATCH];
+#pragma unroll
+    for (int k = 0; k < BATCH; ++k) {
+      const int p = ((it0 + k) * 128 + tid) / LP;
+      v[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (px0 + p < HW) v[k] = __ldg(reinterpret_cast<const uint4*>(ximg + (size_t)(px0 + p) * C + c8 * 8));
+    }
+#pragma unroll
+    for (int k = 0; k < BATCH; ++k) {
+      const int p = ((it0 + k) * 128 + tid) / LP;
+      const uint32_t in[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+      float f[8];
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = unpack_bf16x2(in[j]);
+        f[2 * j] = t.x; f[2 * j + 1] = t.y;
+        ss = fmaf(t.x, t.x, ss); ss = fmaf(t.y, t.y, ss);
+      }
+#pragma unroll
+      for (int o = 1; o < LP; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);   // F.normalize(x, dim=1) (ddpm.py:132)
+      uint32_t o4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o4[j] = pack_bf16x2(f[2 * j] * inv, f[2 * j + 1] * inv);
+      *reinterpret_cast<uint4*>(stage + (size_t)c8 * (ROWS * 16) + p * 16) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+    }
+  }
+}
+
+// ================================================================================================
+// pass A: context
+// ================================================================================================
+template <int C>
+struct CtxCfg {
+  static constexpr int XS = 3;
+  static constexpr int X_STAGE = 64 * C * 2;
+  static constexpr int W_BYTES = 2 * 128 * C * 2;
+  static constexpr int PV_BYTES = 128 * 64 * 2;       // one P or V buffer
+  static constexpr int SMEM_MIN = W_BYTES + XS * X_STAGE + 4 * PV_BYTES + 128 * 4 + 16 * 8 + 16;
+  static constexpr int SMEM = SMEM_MIN > 117 * 1024 ? SMEM_MIN : 117 * 1024;   // one CTA per SM: it owns all 512 TMEM columns
+};
+
+template <int C>
+__global__ void __launch_bounds__(kThreads, 1) la_ctx_kernel(const CtxParams p) {
+  using K = CtxCfg<C>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* w_s = smem;
+  uint8_t* x_s = w_s + K::W_BYTES;
+  uint8_t* pv_s = x_s + K::XS * K::X_STAGE;           // [buf][P | V]
+  float* kb_s = reinterpret_cast<float*>(pv_s + 4 * K::PV_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kb_s + 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t w_full = smem_u32(bars), x_full = w_full + 8, x_empty = x_full + 8 * K::XS, d1_full = x_empty + 8 * K::XS,
+                 d1_empty = d1_full + 16, pv_full = d1_empty + 16, pv_empty = pv_full + 16, d2_full = pv_empty + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.y;
+  const int HT = (p.HW + 63) / 64;
+  const int h0 = (int)((long long)HT * blockIdx.x / p.slices), h1 = (int)((long long)HT * (blockIdx.x + 1) / p.slices);
+  const int nh = h1 - h0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(w_full, 1);
+    for (int i = 0; i < K::XS; ++i) { mbar_init(x_full + 8 * i, 4); mbar_init(x_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(d1_full + 8 * i, 1); mbar_init(d1_empty + 8 * i, 256);
+      mbar_init(pv_full + 8 * i, 256); mbar_init(pv_empty + 8 * i, 1);
+    }
+    mbar_init(d2_full, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 128) kb_s[threadIdx.x] = p.kb2[threadIdx.x];
+  if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: D1 buffer b: K^T at b*128, V^T at b*128 + 64;  CTX at 256..383
+  if (nh <= 0) {
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+    return;
+  }
+
+  if (warp < 4) {
+    // ---------------------------------------------------------------- producers ------------------
+    const __nv_bfloat16* ximg = p.x + (size_t)n * p.HW * C;
+    for (int i = 0; i < nh; ++i) {
+      const int s = i % K::XS;
+      mbar_wait(x_empty + 8 * s, ((i / K::XS) & 1) ^ 1);
+      stage_xhat<C, 64>(ximg, (h0 + i) * 64, p.HW, x_s + s * K::X_STAGE, threadIdx.x);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(x_full + 8 * s);
+    }
+  } else if (warp == kMmaWarp) {
+    // ---------------------------------------------------------------- MMA issue ------------------
+    // the whole warp runs the loop (barrier waits), one elected lane issues tcgen05.mma / commit
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, K::W_BYTES);
+      bulk_g2s(smem_u32(w_s), p.wkv, K::W_BYTES, w_full);
+    }
+    __syncwarp();
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc1 = make_idesc(128, 64), idesc2 = make_idesc(128, 128);
+    const uint32_t hi128 = desc_hi(128);
+    const uint32_t w_lo = desc_lo(smem_u32(w_s), 2048), x_lo0 = desc_lo(smem_u32(x_s), 1024), pv_lo0 = desc_lo(smem_u32(pv_s), 2048);
+    auto mma2 = [&](int j) {
+      const int b = j & 1;
+      mbar_wait(pv_full + 8 * b, (j >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t p_lo = pv_lo0 + (uint32_t)(b * 2 * (K::PV_BYTES >> 4)), v_lo = p_lo + (K::PV_BYTES >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // K = 64 pixels = 4 x 16
+          umma_bf16_lh(tmem_base + 256, p_lo + (uint32_t)(2 * k * 128), hi128, v_lo + (uint32_t)(2 * k * 128), hi128, idesc2,
+                       (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(pv_empty + 8 * b);
+      }
+      __syncwarp();
+    };
+    for (int i = 0; i < nh; ++i) {
+      const int s = i % K::XS, b = i & 1;
+      mbar_wait(x_full + 8 * s, (i / K::XS) & 1);
+      mbar_wait(d1_empty + 8 * b, ((i >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t x_lo = x_lo0 + (uint32_t)(s * (K::X_STAGE >> 4));
+#pragma unroll
+        for (int half = 0; half < 2; ++half)          // K^T rows, then V^T rows
+#pragma unroll
+          for (int k = 0; k < C / 16; ++k)
+            umma_bf16_lh(tmem_base + (uint32_t)(b * 128 + half * 64), w_lo + (uint32_t)(half * (C * 16) + 2 * k * 128), hi128,
+                         x_lo + (uint32_t)(2 * k * 64), hi128, idesc1, k > 0 ? 1u : 0u);
+        umma_commit(x_empty + 8 * s);
+        umma_commit(d1_full + 8 * b);
+      }
+      __syncwarp();
+      if (i >= 1) mma2(i - 1);
+    }
+    mma2(nh - 1);
+    if (elect_one()) umma_commit(d2_full);
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------- transform ------------------
+    const int q = warp & 3, hsel = (warp - kXfWarp0) >> 2;   // TMEM lane quarter, pixel-column half
+    const int r = q * 32 + lane;                             // row: (h,d) for K^T, (h,e) for V^T
+    const float mb = kb_s[r];
+    float ksum = 0.f;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int i = 0; i < nh; ++i) {
+      const int b = i & 1;
+      const int nvalid = p.HW - (h0 + i) * 64 - hsel * 32;   // valid pixel columns of my 32
+      mbar_wait(d1_full + 8 * b, (i >> 1) & 1);
+      tc_fence_after();
+      uint32_t kr[32], vr[32];
+      tmem_ld32(lane_base + (uint32_t)(b * 128 + hsel * 32), kr);
+      tmem_ld32(lane_base + (uint32_t)(b * 128 + 64 + hsel * 32), vr);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(d1_empty + 8 * b);
+      uint32_t pk[16], pv[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float e0 = exp2f(fmaf(__uint_as_float(kr[2 * j]), kLog2e, -mb));
+        float e1 = exp2f(fmaf(__uint_as_float(kr[2 * j + 1]), kLog2e, -mb));
+        if (2 * j >= nvalid) e0 = 0.f;
+        if (2 * j + 1 >= nvalid) e1 = 0.f;
+        pk[j] = pack_bf16x2(e0, e1);
+        const float2 rb = unpack_bf16x2(pk[j]);   // the sum uses the values the tensor core will see
+        ksum += rb.x + rb.y;
+        pv[j] = pack_bf16x2(__uint_as_float(vr[2 * j]), __uint_as_float(vr[2 * j + 1]));
+      }
+      mbar_wait(pv_empty + 8 * b, ((i >> 1) & 1) ^ 1);
+      uint8_t* pbuf = pv_s + (size_t)b * 2 * K::PV_BYTES;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {   // 4 chunks of 8 pixels; chunk index along K = hsel*4 + c
+        const size_t off = (size_t)(hsel * 4 + c) * 2048 + r * 16;
+        *reinterpret_cast<uint4*>(pbuf + off) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        *reinterpret_cast<uint4*>(pbuf + K::PV_BYTES + off) = make_uint4(pv[4 * c], pv[4 * c + 1], pv[4 * c + 2], pv[4 * c + 3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(pv_full + 8 * b);
+    }
+    atomicAdd(p.ksum + (size_t)n * 128 + r, ksum);
+    if (hsel == 0) {
+      mbar_wait(d2_full, 0);
+      tc_fence_after();
+      uint32_t cr[32];
+      tmem_ld32(lane_base + 256u + (uint32_t)(q * 32), cr);   // diagonal block: columns of my own head
+      tmem_ld_wait();
+      float* dst = p.ctx + ((size_t)n * 128 + r) * 32;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) atomicAdd(dst + e, __uint_as_float(cr[e]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+}
+
+// ================================================================================================
+// fold: Mn[n][c][(h,d)] (bf16, K-major UMMA image [16 chunks of 8 (h,d)][C][8])
+// ================================================================================================
+__global__ void la_fold_kernel(const float* __restrict__ ctx, const float* __restrict__ ksum, const float* __restrict__ wout,
+                               __nv_bfloat16* __restrict__ Mn, int C, unsigned int* __restrict__ flag) {
+  const int n = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 128 * C) return;
+  const int c = idx / 128, j = idx % 128;
+  const int h = j >> 5;
+  const float* cx = ctx + ((size_t)n * 128 + j) * 32;
+  float a = 0.f;
+#pragma unroll 8
+  for (int e = 0; e < 32; ++e) a = fmaf(wout[(size_t)(h * 32 + e) * C + c], cx[e], a);
+  const float ks = ksum[(size_t)n * 128 + j];
+  if (!(ks > 1e-30f) && c == 0 && flag) atomicAdd(flag, 1u);
+  const float v = a * 0.17677669529663687f / ks;
+  Mn[(size_t)n * 128 * C + (size_t)(j >> 3) * (C * 8) + c * 8 + (j & 7)] = __float2bfloat16_rn(v);
+}
+
+// ================================================================================================
+// pass B: output
+// ================================================================================================
+template <int C>
+struct OutCfg {
+  static constexpr int XS = C >= 128 ? 2 : 3;
+  static constexpr int X_STAGE = 128 * C * 2;
+  static constexpr int WQ_BYTES = 128 * C * 2;
+  static constexpr int MN_BYTES = 128 * C * 2;
+  static constexpr int P_BYTES = 128 * 128 * 2;
+  static constexpr int SMEM_MIN = WQ_BYTES + MN_BYTES + XS * X_STAGE + 2 * P_BYTES + 2 * C * 4 + 20 * 8 + 16;
+  static constexpr int SMEM = SMEM_MIN > 117 * 1024 ? SMEM_MIN : 117 * 1024;   // one CTA per SM: it owns all 512 TMEM columns
+};
+
+template <int C>
+__global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) {
+  using K = OutCfg<C>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* wq_s = smem;
+  uint8_t* mn_s = wq_s + K::WQ_BYTES;
+  uint8_t* x_s = mn_s + K::MN_BYTES;
+  uint8_t* p_s = x_s + K::XS * K::X_STAGE;
+  float* bg_s = reinterpret_cast<float*>(p_s + 2 * K::P_BYTES);   // bias[C], g2*sqrt(C)[C]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bg_s + 2 * C);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  const uint32_t w_full = smem_u32(bars), x_full = w_full + 8, x_empty = x_full + 8 * 3, d1_full = x_empty + 8 * 3,
+                 d1_empty = d1_full + 16, p_full = d1_empty + 16, p_empty = p_full + 16, d2_full = p_empty + 16,
+                 d2_empty = d2_full + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.y;
+  const int NTL = (p.HW + 127) / 128;
+  const int t0 = (int)((long long)NTL * blockIdx.x / p.slices), t1 = (int)((long long)NTL * (blockIdx.x + 1) / p.slices);
+  const int nt = t1 - t0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(w_full, 1);
+    for (int i = 0; i < K::XS; ++i) { mbar_init(x_full + 8 * i, 4); mbar_init(x_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(d1_full + 8 * i, 1); mbar_init(d1_empty + 8 * i, 128);
+      mbar_init(p_full + 8 * i, 128); mbar_init(p_empty + 8 * i, 1);
+      mbar_init(d2_full + 8 * i, 1); mbar_init(d2_empty + 8 * i, 128);
+    }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < C; i += kThreads) { bg_s[i] = p.bout[i]; bg_s[C + i] = p.g2[i] * sqrtf((float)C); }
+  if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: Q of warp-group g at g*128;  O of warp-group g at 256 + g*C
+  if (nt <= 0) {
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+    return;
+  }
+  const __nv_bfloat16* ximg = p.x + (size_t)n * p.HW * C;
+
+  if (warp < 4) {
+    // ---------------------------------------------------------------- producers ------------------
+    for (int i = 0; i < nt; ++i) {
+      const int s = i % K::XS;
+      mbar_wait(x_empty + 8 * s, ((i / K::XS) & 1) ^ 1);
+      stage_xhat<C, 128>(ximg, (t0 + i) * 128, p.HW, x_s + s * K::X_STAGE, threadIdx.x);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(x_full + 8 * s);
+    }
+  } else if (warp == kMmaWarp) {
+    // ---------------------------------------------------------------- MMA issue ------------------
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, K::WQ_BYTES + K::MN_BYTES);
+      bulk_g2s(smem_u32(wq_s), p.wq, K::WQ_BYTES, w_full);
+      bulk_g2s(smem_u32(mn_s), p.Mn + (size_t)n * 128 * C, K::MN_BYTES, w_full);
+    }
+    __syncwarp();
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc1 = make_idesc(128, 128), idesc2 = make_idesc(128, C);
+    const uint32_t hi128 = desc_hi(128);
+    const uint32_t wq_lo = desc_lo(smem_u32(wq_s), 2048), mn_lo = desc_lo(smem_u32(mn_s), C * 16), x_lo0 = desc_lo(smem_u32(x_s), 2048),
+                   p_lo0 = desc_lo(smem_u32(p_s), 2048);
+    auto mma2 = [&](int j) {
+      const int g = j & 1, u = j >> 1;
+      mbar_wait(p_full + 8 * g, u & 1);
+      mbar_wait(d2_empty + 8 * g, (u & 1) ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t p_lo = p_lo0 + (uint32_t)(g * (K::P_BYTES >> 4));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // K = 128 (h,d) = 8 x 16
+          umma_bf16_lh(tmem_base + 256u + (uint32_t)(g * C), p_lo + (uint32_t)(2 * k * 128), hi128, mn_lo + (uint32_t)(2 * k * C), hi128,
+                       idesc2, k > 0 ? 1u : 0u);
+        umma_commit(p_empty + 8 * g);
+        umma_commit(d2_full + 8 * g);
+      }
+      __syncwarp();
+    };
+    for (int i = 0; i < nt; ++i) {
+      const int s = i % K::XS, g = i & 1, u = i >> 1;
+      mbar_wait(x_full + 8 * s, (i / K::XS) & 1);
+      mbar_wait(d1_empty + 8 * g, (u & 1) ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t x_lo = x_lo0 + (uint32_t)(s * (K::X_STAGE >> 4));
+#pragma unroll
+        for (int k = 0; k < C / 16; ++k)
+          umma_bf16_lh(tmem_base + (uint32_t)(g * 128), x_lo + (uint32_t)(2 * k * 128), hi128, wq_lo + (uint32_t)(2 * k * 128), hi128, idesc1,
+                       k > 0 ? 1u : 0u);
+        umma_commit(x_empty + 8 * s);
+        umma_commit(d1_full + 8 * g);
+      }
+      __syncwarp();
+      if (i >= 1) mma2(i - 1);
+    }
+    mma2(nt - 1);
+  } else {
+    // ---------------------------------------------------------------- transform + epilogue -------
+    const int q = warp & 3, g = (warp - kXfWarp0) >> 2;
+    const int m = q * 32 + lane;                    // pixel row inside the tile
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint8_t* pbuf = p_s + (size_t)g * K::P_BYTES;
+    int u = 0;
+    for (int i = g; i < nt; i += 2, ++u) {
+      mbar_wait(d1_full + 8 * g, u & 1);
+      tc_fence_after();
+      mbar_wait(p_empty + 8 * g, (u & 1) ^ 1);      // MMA2 of my previous tile has consumed P
+#pragma unroll 1
+      for (int h = 0; h < 4; ++h) {
+        uint32_t qr[32];
+        tmem_ld32(lane_base + (uint32_t)(g * 128 + h * 32), qr);
+        tmem_ld_wait();
+        if (h == 3) { tc_fence_before(); mbar_arrive(d1_empty + 8 * g); }
+        float mx = __uint_as_float(qr[0]);
+#pragma unroll
+        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(qr[j]));
+        const float mxl = mx * kLog2e;
+        float e[32], su = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { e[j] = exp2f(fmaf(__uint_as_float(qr[j]), kLog2e, -mxl)); su += e[j]; }
+        const float sc = 1.0f / su;   // softmax(dim=-2) (ddpm.py:242); the dim_head^-0.5 of ddpm.py:245 is folded into Mn
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t o4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o4[j] = pack_bf16x2(e[8 * c + 2 * j] * sc, e[8 * c + 2 * j + 1] * sc);
+          *reinterpret_cast<uint4*>(pbuf + (size_t)(h * 4 + c) * 2048 + m * 16) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(p_full + 8 * g);
+      // epilogue of this tile: two sweeps over the TMEM row (sum of squares, then normalise + store)
+      mbar_wait(d2_full + 8 * g, u & 1);
+      tc_fence_after();
+      const int px = (t0 + i) * 128 + m;
+      float ss = 0.f;
+#pragma unroll 1
+      for (int j0 = 0; j0 < C; j0 += 32) {
+        uint32_t rr[32];
+        tmem_ld32(lane_base + 256u + (uint32_t)(g * C + j0), rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { const float v = __uint_as_float(rr[j]) + bg_s[j0 + j]; ss = fmaf(v, v, ss); }
+      }
+      const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);       // to_out RMSNorm (ddpm.py:231,251)
+      const __nv_bfloat16* xr = ximg + (size_t)px * C;
+      __nv_bfloat16* orow = p.out + ((size_t)n * p.HW + px) * C;
+#pragma unroll 1
+      for (int j0 = 0; j0 < C; j0 += 32) {
+        uint32_t rr[32];
+        tmem_ld32(lane_base + 256u + (uint32_t)(g * C + j0), rr);
+        tmem_ld_wait();
+        if (j0 + 32 == C) { tc_fence_before(); mbar_arrive(d2_empty + 8 * g); }
+        if (px < p.HW) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 xv = *reinterpret_cast<const uint4*>(xr + j0 + 8 * c);
+            const uint32_t xi[4] = {xv.x, xv.y, xv.z, xv.w};
+            uint32_t o4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int cc = 8 * c + 2 * j;
+              const float2 xf = unpack_bf16x2(xi[j]);
+              const float a = fmaf((__uint_as_float(rr[cc]) + bg_s[j0 + cc]) * inv, bg_s[C + j0 + cc], xf.x);
+              const float b = fmaf((__uint_as_float(rr[cc + 1]) + bg_s[j0 + cc + 1]) * inv, bg_s[C + j0 + cc + 1], xf.y);
+              o4[j] = pack_bf16x2(a, b);
+            }
+            *reinterpret_cast<uint4*>(orow + j0 + 8 * c) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+}
+
+int g_sms = 0;
+int sms() {
+  if (!g_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev); }
+  return g_sms;
+}
+
+template <int C>
+int configure_c() {
+  if (cudaFuncSetAttribute(la_ctx_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, CtxCfg<C>::SMEM) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(la_out_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, OutCfg<C>::SMEM) != cudaSuccess) return -1;
+  return 0;
+}
+
+template <int C>
+int launch_c(const LinAttnTcW& w, const LinAttnTcArgs& a, cudaStream_t s) {
+  // slices per image: fill the machine (one CTA per SM) but keep at least 4 half tiles per CTA
+  const int HT = (a.HW + 63) / 64, NTL = (a.HW + 127) / 128;
+  int slA = (sms() + a.N - 1) / a.N; if (slA > HT / 4) slA = HT / 4; if (slA < 1) slA = 1;
+  int slB = (sms() + a.N - 1) / a.N; if (slB > NTL / 2) slB = NTL / 2; if (slB < 1) slB = 1;
+  CtxParams cp{(const __nv_bfloat16*)a.x, (const __nv_bfloat16*)w.wkv, w.kb2, a.ctx, a.ksum, a.HW, slA};
+  la_ctx_kernel<C><<<dim3(slA, a.N), kThreads, CtxCfg<C>::SMEM, s>>>(cp);
+  la_fold_kernel<<<dim3((128 * C + 255) / 256, a.N), 256, 0, s>>>(a.ctx, a.ksum, w.wout, (__nv_bfloat16*)a.Mn, C, a.flag);
+  OutParams op{(const __nv_bfloat16*)a.x, (const __nv_bfloat16*)w.wq, (const __nv_bfloat16*)a.Mn, w.bout, w.g2,
+               (__nv_bfloat16*)a.out, a.HW, slB};
+  la_out_kernel<C><<<dim3(slB, a.N), kThreads, OutCfg<C>::SMEM, s>>>(op);
+  return 3;
+}
+
+}  // namespace
+
+int linattn_tc_pack(const float* wqkv, const float* g, const float* wout, const float* bout, const float* g2, int C, int heads,
+                    LinAttnTcW* out) {
+  out->ready = false;
+  if (heads != 4 || !(C == 32 || C == 64 || C == 128)) return 0;
+  out->C = C;
+  const float sq = sqrtf((float)C);
+  // fold RMSNorm's g * sqrt(C) (ddpm.py:131-132) into the 1x1 to_qkv weights (ddpm.py:227); rows: q 0..127, k 128..255, v 256..383
+  auto pack_rows = [&](int row0, int nblocks, std::vector<__nv_bfloat16>& dst) {
+    dst.resize((size_t)nblocks * 128 * C);
+    for (int b = 0; b < nblocks; ++b)
+      for (int c8 = 0; c8 < C / 8; ++c8)
+        for (int r = 0; r < 128; ++r)
+          for (int e = 0; e < 8; ++e) {
+            const int c = c8 * 8 + e;
+            dst[(((size_t)b * (C / 8) + c8) * 128 + r) * 8 + e] = __float2bfloat16_rn(wqkv[(size_t)(row0 + b * 128 + r) * C + c] * g[c] * sq);
+          }
+  };
+  std::vector<__nv_bfloat16> q, kv;
+  pack_rows(0, 1, q);
+  pack_rows(128, 2, kv);
+  std::vector<float> kb(128);
+  for (int r = 0; r < 128; ++r) {
+    double ss = 0;
+    for (int c8 = 0; c8 < C / 8; ++c8)
+      for (int e = 0; e < 8; ++e) { const double v = (double)__bfloat162float(kv[((size_t)c8 * 128 + r) * 8 + e]); ss += v * v; }
+    kb[r] = (float)(sqrt(ss) * 1.01 * 1.4426950408889634);   // |k_d| <= |W'_k[d,:]| * |xhat|, |xhat| <= 1 + 2^-8
+  }
+  std::vector<float> wo((size_t)128 * C);
+  for (int j = 0; j < 128; ++j)
+    for (int c = 0; c < C; ++c) wo[(size_t)j * C + c] = wout[(size_t)c * 128 + j];   // torch [C][128] -> [128][C]
+  auto up = [](const void* h, size_t bytes, void** d) {
+    if (cudaMalloc(d, bytes) != cudaSuccess) return -1;
+    return cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : -1;
+  };
+  if (up(q.data(), q.size() * 2, &out->wq) || up(kv.data(), kv.size() * 2, &out->wkv) || up(kb.data(), 128 * 4, (void**)&out->kb2) ||
+      up(wo.data(), wo.size() * 4, (void**)&out->wout) || up(bout, C * 4, (void**)&out->bout) || up(g2, C * 4, (void**)&out->g2))
+    return -1;
+  int rc = C == 32 ? configure_c<32>() : C == 64 ? configure_c<64>() : configure_c<128>();
+  if (rc) return -1;
+  out->ready = true;
+  return 0;
+}
+
+void linattn_tc_free(LinAttnTcW* w) {
+  cudaFree(w->wq); cudaFree(w->wkv); cudaFree(w->kb2); cudaFree(w->wout); cudaFree(w->bout); cudaFree(w->g2);
+  *w = LinAttnTcW();
+}
+
+int linattn_tc_launch(const LinAttnTcW& w, const LinAttnTcArgs& a, cudaStream_t s) {
+  if (!w.ready) return -1;
+  switch (w.C) {
+    case 32: return launch_c<32>(w, a, s);
+    case 64: return launch_c<64>(w, a, s);
+    case 128: return launch_c<128>(w, a, s);
+  }
+  return -1;
+}
+
+}  // namespace ld

@@ -1,0 +1,36 @@
+// Fused tcgen05 LinearAttention (ddpm.py:214-251) for sm_100a: see ld_linattn_tc.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ld {
+
+struct LinAttnTcW {
+  bool ready = false;
+  int C = 0;
+  void* wq = nullptr;    // bf16 [C/8][128][8]: to_qkv rows 0..127 (q), RMSNorm g*sqrt(C) folded in
+  void* wkv = nullptr;   // bf16 [2][C/8][128][8]: rows 128..255 (k) and 256..383 (v)
+  float* kb2 = nullptr;  // [128] log2(e) * upper bound of |k_d| (soft-max shift)
+  float* wout = nullptr; // fp32 [128][C] to_out.0 weight, transposed
+  float* bout = nullptr; // fp32 [C]
+  float* g2 = nullptr;   // fp32 [C] to_out.1.g
+};
+
+struct LinAttnTcArgs {
+  const void* x = nullptr;   // bf16 [N][HW][C] (input of the attention block AND its residual)
+  void* out = nullptr;       // bf16 [N][HW][C]
+  int N = 0, HW = 0;
+  float* ctx = nullptr;      // [N][128][32] fp32, zeroed by the caller
+  float* ksum = nullptr;     // [N][128] fp32, zeroed by the caller
+  void* Mn = nullptr;        // [N][128*C] bf16 scratch
+  unsigned int* flag = nullptr;  // optional: incremented when a soft-max row sum underflowed
+};
+
+// host weights in torch layout: wqkv [384][C], g [C], wout [C][128], bout [C], g2 [C]
+int linattn_tc_pack(const float* wqkv, const float* g, const float* wout, const float* bout, const float* g2, int C, int heads,
+                    LinAttnTcW* out);
+void linattn_tc_free(LinAttnTcW* w);
+// returns the number of kernels launched (3), < 0 on error
+int linattn_tc_launch(const LinAttnTcW& w, const LinAttnTcArgs& a, cudaStream_t s);
+
+}  // namespace ld

@@ -67,3 +67,94 @@ def test_conv_kernels_match_torch(case, kernel):
         assert util.rel_err(out, ref(False)) < 1e-5
     else:  # bf16 storage: compare against the same op on bf16-rounded operands; only the output rounding remains
         assert util.rel_err(out, ref(True)) < 4e-3
+
+
+# (C0, Cout, N, H, W, pro_G (0 = no prologue), act, film, stats_G (0 = none))
+FUSED_CASES = [
+    (32, 32, 2, 32, 32, 8, 1, True, 8),      # ResnetBlock block2 at dim 32 (ddpm.py:174-185)
+    (64, 64, 1, 20, 12, 8, 1, True, 8),      # ragged tiles
+    (128, 128, 2, 16, 16, 8, 1, False, 8),   # streamed weights, 16 channels per group
+    (256, 256, 1, 8, 8, 8, 1, True, 8),      # 32 channels per group
+    (32, 32, 3, 16, 24, 16, 2, False, 16),   # BasicBlock (unet_model.py:20-25): 16 groups, ReLU
+    (32, 64, 2, 16, 16, 0, 0, False, 16),    # statistics only
+    (64, 32, 40, 16, 8, 8, 1, True, 0),      # prologue only, many images per persistent CTA
+]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES)
+def test_conv_fused_groupnorm_prologue_and_stats(case):
+    C0, Cout, N, H, W, pG, act, use_film, sG = case
+    lib = _lib.lib()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(C0 + 3 * Cout + H + pG)
+    x = (torch.randn(N, H, W, C0, generator=g) * 1.7 + 0.3).bfloat16().float()
+    w = (torch.randn(Cout, C0, 3, 3, generator=g) / (C0 * 9) ** 0.5)
+    b = torch.randn(Cout, generator=g)
+    gamma, beta = torch.rand(C0, generator=g) + 0.5, torch.randn(C0, generator=g) * 0.2
+    film = torch.randn(N, 2 * C0, generator=g) * 0.3
+    xin = x
+    args = dict(ps=None, ga=None, be=None, fi=None)
+    if pG:
+        xg = x.double().view(N, H * W, pG, C0 // pG)
+        st = torch.stack([xg.sum(dim=(1, 3)), (xg * xg).sum(dim=(1, 3))], dim=-1).contiguous()  # [N, G, 2]
+        cnt = H * W * (C0 // pG)
+        mean, var = st[..., 0] / cnt, st[..., 1] / cnt - (st[..., 0] / cnt) ** 2
+        rstd = 1.0 / torch.sqrt(var + 1e-5)
+        xn = (xg - mean[:, None, :, None]) * rstd[:, None, :, None]
+        xn = xn.view(N, H, W, C0) * gamma.double() + beta.double()
+        if use_film:
+            xn = xn * (film[:, None, None, :C0].double() + 1.0) + film[:, None, None, C0:].double()
+        xn = torch.nn.functional.silu(xn) if act == 1 else (torch.relu(xn) if act == 2 else xn)
+        xin = xn.float().bfloat16().float()
+        args = dict(ps=st.to(dev), ga=gamma.to(dev), be=beta.to(dev), fi=film.to(dev) if use_film else None)
+    ref = F.conv2d(xin.permute(0, 3, 1, 2).double(), w.bfloat16().double(), b.double(), padding=1).permute(0, 2, 3, 1)
+    out = torch.empty(N, H, W, Cout, device=dev)
+    stats = torch.full((N, max(sG, 1), 2), 7.0, dtype=torch.float64, device=dev)
+    xd = x.to(dev)
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    rc = lib.ld_debug_conv_fused(xd.data_ptr(), C0, N, H, W, w.contiguous().data_ptr(), b.contiguous().data_ptr(), Cout,
+                                 ptr(args["ps"]), ptr(args["ga"]), ptr(args["be"]), ptr(args["fi"]), 2 * C0, pG, act,
+                                 stats.data_ptr() if sG else None, sG, out.data_ptr(),
+                                 C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc)
+    # prologue output is re-rounded to bf16 (and SiLU uses tanh.approx): one extra bf16 ulp on some operands
+    assert util.rel_err(out, ref) < (8e-3 if pG else 4e-3)
+    if sG:
+        rg = ref.view(N, H * W, sG, Cout // sG)
+        want = torch.stack([rg.sum(dim=(1, 3)), (rg * rg).sum(dim=(1, 3))], dim=-1)
+        got = stats.cpu()
+        scale = want[..., 1].sqrt().unsqueeze(-1) * (H * W * (Cout // sG)) ** 0.5  # |sum| <= sqrt(n * sumsq)
+        assert float(((got[..., 0] - want[..., 0]).abs() / scale[..., 0]).max()) < 2e-3
+        assert float(((got[..., 1] - want[..., 1]).abs() / want[..., 1]).max()) < 5e-3
+
+
+# (C, N, HW)
+LINATTN_CASES = [(32, 2, 1024), (64, 1, 784), (128, 2, 256), (32, 3, 4096), (64, 5, 1000)]
+
+
+@pytest.mark.parametrize("C_,N,HW", LINATTN_CASES)
+def test_fused_linear_attention_matches_torch(C_, N, HW):
+    """attn(x) + x of LinearAttention (ddpm.py:214-251, 425) through the fused tcgen05 kernels."""
+    lib = _lib.lib()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(C_ + N + HW)
+    x = (torch.randn(N, HW, C_, generator=g) * 1.3).bfloat16().float()
+    wqkv = torch.randn(384, C_, generator=g) / C_ ** 0.5
+    gn = torch.rand(C_, generator=g) + 0.5
+    wout = torch.randn(C_, 128, generator=g) / 128 ** 0.5
+    bout = torch.randn(C_, generator=g) * 0.1
+    g2 = torch.rand(C_, generator=g) + 0.5
+    xd = x.double()
+    xn = F.normalize(xd, dim=-1) * gn.double() * C_ ** 0.5
+    q, k, v = (xn @ wqkv.double().T).view(N, HW, 3, 4, 32).unbind(dim=2)
+    q = q.softmax(dim=-1) * 32 ** -0.5
+    k = k.softmax(dim=1)
+    ctx = torch.einsum("nphd,nphe->nhde", k, v)
+    o = torch.einsum("nhde,nphd->nphe", ctx, q).reshape(N, HW, 128) @ wout.double().T + bout.double()
+    attn = F.normalize(o, dim=-1) * g2.double() * C_ ** 0.5
+    out = torch.empty(N, HW, C_, device=dev)
+    rc = lib.ld_debug_linattn(x.to(dev).data_ptr(), C_, N, HW, wqkv.contiguous().data_ptr(), gn.data_ptr(), wout.contiguous().data_ptr(),
+                              bout.data_ptr(), g2.data_ptr(), out.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc)
+    got = out.cpu().double() - xd   # attention branch (the residual is exact up to the output rounding)
+    assert util.rel_err(got, attn) < 2.5e-2
