@@ -174,6 +174,9 @@ LD_API int ld_debug_conv_fused(const float* x0, int C0, int N, int H, int W, con
  * wqkv [384][C], g [C], wout [C][128], bout [C], g2 [C]: host fp32 in the reference's parameter layout. */
 LD_API int ld_debug_linattn(const float* x, int C, int N, int HW, const float* wqkv, const float* g, const float* wout,
                             const float* bout, const float* g2, float* out, void* stream);
+/* Test hook: tcgen05 flash-style soft-max attention (attend.py:98-113).  qkv: fp32 [N][n][3*heads*32] device
+ * (channel = part*hid + h*32 + d, ddpm.py:276-277); out: fp32 [N][n][heads*32]. */
+LD_API int ld_debug_attention(const float* qkv, int N, int n, int heads, float* out, void* stream);
 /* Average device time (ms, CUDA events on `stream`) of `iters` launches of one convolution kernel on
  * synthetic operands; used by bench.py for the roofline of the dominant kernel. */
 LD_API int ld_debug_conv_time(int kernel, int C0, int C1, int N, int H, int W, int up, int Cout, int ks,

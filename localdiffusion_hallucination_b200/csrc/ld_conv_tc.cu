@@ -424,7 +424,7 @@ size_t smem_bytes(int NT, int nb_stages, int coef_floats) {
          (2 * SA + 2 * SB + 4) * 8 + 16;
 }
 
-struct Cfg { int max_smem = 0; int sms = 0; };
+struct Cfg { int max_smem = 0; int max_smem_sm = 0; int sms = 0; };
 Cfg& cfg() {
   static Cfg c;
   if (!c.sms) {
@@ -432,6 +432,7 @@ Cfg& cfg() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&c.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&c.max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
   }
   return c;
 }
@@ -455,15 +456,13 @@ int configure_nt(int NT) {
 template <int NT, int KS, int KC>
 int launch_one(KParams& p, int ntiles_y, size_t smem, cudaStream_t s) {
   // persistent grid: as many CTAs as can be resident (shared memory, 2*NT TMEM columns of 512 each)
-  static int occ_cache_smem = -1, occ_cache = 1;
-  if (occ_cache_smem != (int)smem) {
-    int occ = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tc_kernel<NT, KS, KC>, kThreads, smem) != cudaSuccess || occ < 1) occ = 1;
-    const int tm = 512 / (2 * NT);
-    occ_cache = occ < tm ? occ : tm;
-    if (occ_cache < 1) occ_cache = 1;
-    occ_cache_smem = (int)smem;
-  }
+  // (registers allow two CTAs per SM, see __launch_bounds__)
+  int occ = (int)((size_t)cfg().max_smem_sm / (smem + 1024));
+  if (occ > 2) occ = 2;
+  const int tm = 512 / (2 * NT);
+  if (occ > tm) occ = tm;
+  if (occ < 1) occ = 1;
+  const int occ_cache = occ;
   int gx = cfg().sms * occ_cache / ntiles_y;
   if (gx < 1) gx = 1;
   if (gx > p.ntiles) gx = p.ntiles;

@@ -20,6 +20,7 @@
 #include "ld_conv_tc.h"
 #include "ld_kernels.h"
 #include "ld_linattn_tc.h"
+#include "ld_attn_tc.h"
 
 namespace ld {
 
@@ -117,7 +118,7 @@ struct Engine {
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   int64_t launches = 0;
-  int64_t opt_micro_batch = 0, opt_use_graph = 1, opt_debug_keep = 0, opt_la_exact = 0;
+  int64_t opt_micro_batch = 0, opt_use_graph = 1, opt_debug_keep = 0, opt_la_exact = 0, opt_attn_simt = 0;
   unsigned int* la_flag = nullptr;        // soft-max underflow counter of the fused LinearAttention
   std::map<std::string, std::unique_ptr<Plan>> plans;
   std::map<std::string, Staged> staged;   // stand-alone entry points (ld_unet_forward / ld_cond_encode)
@@ -379,6 +380,7 @@ static int finalize(Engine& E) {
     E.samp[p + ".3"] = cw;
   }
   if ((rc = pack_res(E, "final_res_block", true, fw, fb))) return rc;
+  if (E.use_tc && attn_tc_configure()) return fail(LD_ERR_CUDA, "attn_tc_configure failed");
   CK(cudaMalloc(&E.la_flag, sizeof(unsigned int)));
   CK(cudaMemset(E.la_flag, 0, sizeof(unsigned int)));
   E.film_total = (int)fb.size();
@@ -578,7 +580,12 @@ struct Builder {
     Ten out;
     if (a.full) {
       Ten ao = act(x.N, x.H, x.W, hid);
-      {
+      if (E.use_tc && !E.opt_attn_simt) {
+        Ten sc = alloc(1, 1, 1, (int)((attn_tc_scratch_bytes(x.N, x.H * x.W, heads) + 255) / 256), 256);
+        Ten q = qkv, o = ao;
+        op([q, o, sc, heads](cudaStream_t s) { return attn_tc_launch(q.p, o.p, sc.p, q.N, q.H * q.W, heads, s); });
+        release(sc);
+      } else {
         Ten q = qkv, o = ao;
         op([q, o, heads, bf](cudaStream_t s) { return launch_attention_simt(q.p, o.p, q.N, q.H * q.W, heads, bf, s); });
       }
@@ -1289,6 +1296,23 @@ int ld_debug_linattn(const float* x, int C, int N, int HW, const float* wqkv, co
   return rc;
 }
 
+// tcgen05 flash attention (test hook).  qkv: fp32 [N][n][3*heads*32] device; out: fp32 [N][n][heads*32].
+int ld_debug_attention(const float* qkv, int N, int n, int heads, float* out, void* stream) {
+  if (ld_device_count() == 0) return fail(LD_ERR_NO_DEVICE, "no sm_100 CUDA device is available (there is no CPU fallback)");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (attn_tc_configure()) return fail(LD_ERR_CUDA, "attn_tc_configure failed");
+  const size_t nq = (size_t)N * n * 3 * heads * 32, no = (size_t)N * n * heads * 32;
+  void *qb = nullptr, *ob = nullptr, *sc = nullptr;
+  CK(cudaMalloc(&qb, nq * 2)); CK(cudaMalloc(&ob, no * 2)); CK(cudaMalloc(&sc, attn_tc_scratch_bytes(N, n, heads)));
+  launch_convert(qkv, false, qb, true, (long long)nq, s);
+  int rc = attn_tc_launch(qb, ob, sc, N, n, heads, s) < 0 ? fail(LD_ERR_INVALID, "attn_tc_launch failed") : 0;
+  launch_convert(ob, true, out, false, (long long)no, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  cudaFree(qb); cudaFree(ob); cudaFree(sc);
+  if (e != cudaSuccess) return fail(LD_ERR_CUDA, "debug attention failed: %s", cudaGetErrorString(e));
+  return rc;
+}
+
 // Time one convolution kernel in isolation with CUDA events on its launch stream (bench.py roofline leg).
 int ld_debug_conv_time(int kernel, int C0, int C1, int N, int H, int W, int up, int Cout, int ks, int iters, float* ms_out,
                        void* stream) {
@@ -1347,6 +1371,7 @@ int ld_set_option(ld_handle* h, const char* name, int64_t value) {
   else if (!strcmp(name, "use_graph")) h->E.opt_use_graph = value;
   else if (!strcmp(name, "debug_keep")) h->E.opt_debug_keep = value;
   else if (!strcmp(name, "la_exact")) h->E.opt_la_exact = value;
+  else if (!strcmp(name, "attn_simt")) h->E.opt_attn_simt = value;
   else if (!strcmp(name, "use_tc")) { if (h->E.finalized) return fail(LD_ERR_STATE, "use_tc must be set before finalize"); h->E.use_tc = value != 0 && h->E.bf; }
   else return fail(LD_ERR_INVALID, "unknown option '%s'", name);
   return 0;

@@ -36,6 +36,11 @@ constexpr int kThreads = 13 * 32;  // warps 0-3 producers, 4 MMA, 5-12 transform
 constexpr int kMmaWarp = 4;
 constexpr int kXfWarp0 = 5;
 constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 struct CtxParams {
   const __nv_bfloat16* x;   // [N][HW][C]
@@ -54,25 +59,29 @@ struct OutParams {
   int HW, slices;
 };
 
-// stage ROWS pixels of x/|x| as a K-major operand: 16-byte chunk (pixel p, channels 8*c8..) at c8*ROWS*16 + p*16
+// Producer side: ROWS pixels of x/|x| staged as a K-major operand (16-byte chunk (pixel p, channels 8*c8..) at
+// c8*ROWS*16 + p*16).  Global loads run `XDEPTH` stages ahead of the shared-memory ring through a register FIFO, so
+// that ~25-50 KB per SM are in flight (what HBM latency x bandwidth asks for) with only four producer warps.
 template <int C, int ROWS>
-__device__ __forceinline__ void stage_xhat(const __nv_bfloat16* __restrict__ ximg, int px0, int HW, uint8_t* stage, int tid) {
-  constexpr int LP = C / 8;                 // lanes per pixel
-  constexpr int ITEMS = ROWS * LP / 128;
-  constexpr int BATCH = ITEMS < 8 ? ITEMS : 8;
-  const int c8 = tid % LP;
-#pragma unroll 1
-  for (int it0 = 0; it0 < ITEMS; it0 += BATCH) {
-    uint4 v[BATCH];
+struct XStage {
+  static constexpr int LP = C / 8;                 // lanes per pixel
+  static constexpr int ITEMS = ROWS * LP / 128;    // 16-byte loads per thread per stage
+  static constexpr int DEPTH = ITEMS >= 16 ? 1 : ((12 / ITEMS) < 2 ? 2 : (12 / ITEMS));
+  uint4 v[ITEMS];
+  __device__ __forceinline__ void load(const __nv_bfloat16* __restrict__ ximg, int px0, int HW, int tid) {
+    const int c8 = tid % LP;
 #pragma unroll
-    for (int k = 0; k < BATCH; ++k) {
-      const int p = ((it0 + k) * 128 + tid) / LP;
+    for (int k = 0; k < ITEMS; ++k) {
+      const int p = (k * 128 + tid) / LP;
       v[k] = make_uint4(0u, 0u, 0u, 0u);
       if (px0 + p < HW) v[k] = __ldg(reinterpret_cast<const uint4*>(ximg + (size_t)(px0 + p) * C + c8 * 8));
     }
+  }
+  __device__ __forceinline__ void store(uint8_t* stage, int tid) const {
+    const int c8 = tid % LP;
 #pragma unroll
-    for (int k = 0; k < BATCH; ++k) {
-      const int p = ((it0 + k) * 128 + tid) / LP;
+    for (int k = 0; k < ITEMS; ++k) {
+      const int p = (k * 128 + tid) / LP;
       const uint32_t in[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
       float f[8];
       float ss = 0.f;
@@ -89,6 +98,32 @@ __device__ __forceinline__ void stage_xhat(const __nv_bfloat16* __restrict__ xim
 #pragma unroll
       for (int j = 0; j < 4; ++j) o4[j] = pack_bf16x2(f[2 * j] * inv, f[2 * j + 1] * inv);
       *reinterpret_cast<uint4*>(stage + (size_t)c8 * (ROWS * 16) + p * 16) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+    }
+  }
+};
+
+// the producer loop shared by both passes: stage i covers pixels [(first + i) * ROWS, +ROWS) of one image
+template <int C, int ROWS, int XS>
+__device__ __forceinline__ void produce_x(const __nv_bfloat16* __restrict__ ximg, int first, int count, int HW, uint8_t* x_s,
+                                          int x_stage_bytes, uint32_t x_full, uint32_t x_empty, int tid, int lane) {
+  using X = XStage<C, ROWS>;
+  X fifo[X::DEPTH];
+#pragma unroll
+  for (int d = 0; d < X::DEPTH; ++d)
+    if (d < count) fifo[d].load(ximg, (first + d) * ROWS, HW, tid);
+  for (int i0 = 0; i0 < count; i0 += X::DEPTH) {
+#pragma unroll
+    for (int d = 0; d < X::DEPTH; ++d) {
+      const int i = i0 + d;
+      if (i < count) {
+        const int s = i % XS;
+        mbar_wait(x_empty + 8 * s, ((i / XS) & 1) ^ 1);
+        fifo[d].store(x_s + (size_t)s * x_stage_bytes, tid);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(x_full + 8 * s);
+        if (i + X::DEPTH < count) fifo[d].load(ximg, (first + i + X::DEPTH) * ROWS, HW, tid);
+      }
     }
   }
 }
@@ -149,14 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) la_ctx_kernel(const CtxParams p) 
   if (warp < 4) {
     // ---------------------------------------------------------------- producers ------------------
     const __nv_bfloat16* ximg = p.x + (size_t)n * p.HW * C;
-    for (int i = 0; i < nh; ++i) {
-      const int s = i % K::XS;
-      mbar_wait(x_empty + 8 * s, ((i / K::XS) & 1) ^ 1);
-      stage_xhat<C, 64>(ximg, (h0 + i) * 64, p.HW, x_s + s * K::X_STAGE, threadIdx.x);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(x_full + 8 * s);
-    }
+    produce_x<C, 64, K::XS>(ximg, h0, nh, p.HW, x_s, K::X_STAGE, x_full, x_empty, threadIdx.x, lane);
   } else if (warp == kMmaWarp) {
     // ---------------------------------------------------------------- MMA issue ------------------
     // the whole warp runs the loop (barrier waits), one elected lane issues tcgen05.mma / commit
@@ -227,14 +255,20 @@ __global__ void __launch_bounds__(kThreads, 1) la_ctx_kernel(const CtxParams p) 
       uint32_t pk[16], pv[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float e0 = exp2f(fmaf(__uint_as_float(kr[2 * j]), kLog2e, -mb));
-        float e1 = exp2f(fmaf(__uint_as_float(kr[2 * j + 1]), kLog2e, -mb));
-        if (2 * j >= nvalid) e0 = 0.f;
-        if (2 * j + 1 >= nvalid) e1 = 0.f;
+        const float e0 = ex2_approx(fmaf(__uint_as_float(kr[2 * j]), kLog2e, -mb));
+        const float e1 = ex2_approx(fmaf(__uint_as_float(kr[2 * j + 1]), kLog2e, -mb));
         pk[j] = pack_bf16x2(e0, e1);
-        const float2 rb = unpack_bf16x2(pk[j]);   // the sum uses the values the tensor core will see
-        ksum += rb.x + rb.y;
+        ksum += e0 + e1;
         pv[j] = pack_bf16x2(__uint_as_float(vr[2 * j]), __uint_as_float(vr[2 * j + 1]));
+      }
+      if (nvalid < 32) {   // ragged last tile of the image: pixels past the end carry no weight
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float2 e = unpack_bf16x2(pk[j]);
+          const float e0 = 2 * j < nvalid ? e.x : 0.f, e1 = 2 * j + 1 < nvalid ? e.y : 0.f;
+          ksum -= (e.x - e0) + (e.y - e1);
+          pk[j] = pack_bf16x2(e0, e1);
+        }
       }
       mbar_wait(pv_empty + 8 * b, ((i >> 1) & 1) ^ 1);
       uint8_t* pbuf = pv_s + (size_t)b * 2 * K::PV_BYTES;
@@ -267,21 +301,30 @@ __global__ void __launch_bounds__(kThreads, 1) la_ctx_kernel(const CtxParams p) 
 // ================================================================================================
 // fold: Mn[n][c][(h,d)] (bf16, K-major UMMA image [16 chunks of 8 (h,d)][C][8])
 // ================================================================================================
-__global__ void la_fold_kernel(const float* __restrict__ ctx, const float* __restrict__ ksum, const float* __restrict__ wout,
-                               __nv_bfloat16* __restrict__ Mn, int C, unsigned int* __restrict__ flag) {
-  const int n = blockIdx.y;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 128 * C) return;
-  const int c = idx / 128, j = idx % 128;
-  const int h = j >> 5;
-  const float* cx = ctx + ((size_t)n * 128 + j) * 32;
-  float a = 0.f;
+// grid (4 heads, N), 256 threads
+__global__ void __launch_bounds__(256) la_fold_kernel(const float* __restrict__ ctx, const float* __restrict__ ksum,
+                                                      const float* __restrict__ wout, __nv_bfloat16* __restrict__ Mn, int C,
+                                                      unsigned int* __restrict__ flag) {
+  __shared__ float cx[32][33];       // ctx[d][e] / ksum[d] * 32^-0.5
+  extern __shared__ float wo[];      // [32 e][C]
+  const int h = blockIdx.x, n = blockIdx.y;
+  for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+    const int d = i >> 5, e = i & 31;
+    const float ks = ksum[(size_t)n * 128 + h * 32 + d];
+    if (e == 0 && !(ks > 1e-30f) && flag) atomicAdd(flag, 1u);
+    cx[d][e] = ctx[((size_t)n * 128 + h * 32 + d) * 32 + e] * 0.17677669529663687f / ks;
+  }
+  for (int i = threadIdx.x; i < 32 * C; i += 256) wo[i] = wout[(size_t)h * 32 * C + i];
+  __syncthreads();
+  __nv_bfloat16* dst = Mn + (size_t)n * 128 * C;
+  for (int i = threadIdx.x; i < 32 * C; i += 256) {
+    const int d = i & 31, c = i >> 5;
+    float a = 0.f;
 #pragma unroll 8
-  for (int e = 0; e < 32; ++e) a = fmaf(wout[(size_t)(h * 32 + e) * C + c], cx[e], a);
-  const float ks = ksum[(size_t)n * 128 + j];
-  if (!(ks > 1e-30f) && c == 0 && flag) atomicAdd(flag, 1u);
-  const float v = a * 0.17677669529663687f / ks;
-  Mn[(size_t)n * 128 * C + (size_t)(j >> 3) * (C * 8) + c * 8 + (j & 7)] = __float2bfloat16_rn(v);
+    for (int e = 0; e < 32; ++e) a = fmaf(wo[e * C + c], cx[d][e], a);
+    const int j = h * 32 + d;
+    dst[(size_t)(j >> 3) * (C * 8) + c * 8 + (j & 7)] = __float2bfloat16_rn(a);
+  }
 }
 
 // ================================================================================================
@@ -343,14 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
 
   if (warp < 4) {
     // ---------------------------------------------------------------- producers ------------------
-    for (int i = 0; i < nt; ++i) {
-      const int s = i % K::XS;
-      mbar_wait(x_empty + 8 * s, ((i / K::XS) & 1) ^ 1);
-      stage_xhat<C, 128>(ximg, (t0 + i) * 128, p.HW, x_s + s * K::X_STAGE, threadIdx.x);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(x_full + 8 * s);
-    }
+    produce_x<C, 128, K::XS>(ximg, t0, nt, p.HW, x_s, K::X_STAGE, x_full, x_empty, threadIdx.x, lane);
   } else if (warp == kMmaWarp) {
     // ---------------------------------------------------------------- MMA issue ------------------
     if (lane == 0) {
@@ -422,7 +458,7 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
         const float mxl = mx * kLog2e;
         float e[32], su = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { e[j] = exp2f(fmaf(__uint_as_float(qr[j]), kLog2e, -mxl)); su += e[j]; }
+        for (int j = 0; j < 32; ++j) { e[j] = ex2_approx(fmaf(__uint_as_float(qr[j]), kLog2e, -mxl)); su += e[j]; }
         const float sc = 1.0f / su;   // softmax(dim=-2) (ddpm.py:242); the dim_head^-0.5 of ddpm.py:245 is folded into Mn
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -496,13 +532,14 @@ int configure_c() {
 
 template <int C>
 int launch_c(const LinAttnTcW& w, const LinAttnTcArgs& a, cudaStream_t s) {
-  // slices per image: fill the machine (one CTA per SM) but keep at least 4 half tiles per CTA
+  // slices per image: ONE wave of CTAs (each owns all 512 TMEM columns of its SM), at least 4 half tiles per CTA
   const int HT = (a.HW + 63) / 64, NTL = (a.HW + 127) / 128;
-  int slA = (sms() + a.N - 1) / a.N; if (slA > HT / 4) slA = HT / 4; if (slA < 1) slA = 1;
-  int slB = (sms() + a.N - 1) / a.N; if (slB > NTL / 2) slB = NTL / 2; if (slB < 1) slB = 1;
+  int sl = sms() / a.N; if (sl < 1) sl = 1;
+  int slA = sl; if (slA > HT / 4) slA = HT / 4; if (slA < 1) slA = 1;
+  int slB = sl; if (slB > NTL / 2) slB = NTL / 2; if (slB < 1) slB = 1;
   CtxParams cp{(const __nv_bfloat16*)a.x, (const __nv_bfloat16*)w.wkv, w.kb2, a.ctx, a.ksum, a.HW, slA};
   la_ctx_kernel<C><<<dim3(slA, a.N), kThreads, CtxCfg<C>::SMEM, s>>>(cp);
-  la_fold_kernel<<<dim3((128 * C + 255) / 256, a.N), 256, 0, s>>>(a.ctx, a.ksum, w.wout, (__nv_bfloat16*)a.Mn, C, a.flag);
+  la_fold_kernel<<<dim3(4, a.N), 256, 32 * C * sizeof(float), s>>>(a.ctx, a.ksum, w.wout, (__nv_bfloat16*)a.Mn, C, a.flag);
   OutParams op{(const __nv_bfloat16*)a.x, (const __nv_bfloat16*)w.wq, (const __nv_bfloat16*)a.Mn, w.bout, w.g2,
                (__nv_bfloat16*)a.out, a.HW, slB};
   la_out_kernel<C><<<dim3(slB, a.N), kThreads, OutCfg<C>::SMEM, s>>>(op);

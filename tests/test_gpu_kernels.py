@@ -158,3 +158,23 @@ def test_fused_linear_attention_matches_torch(C_, N, HW):
     _lib.check(rc)
     got = out.cpu().double() - xd   # attention branch (the residual is exact up to the output rounding)
     assert util.rel_err(got, attn) < 2.5e-2
+
+
+# (N, n tokens, heads)
+ATTN_CASES = [(2, 1024, 4), (1, 64, 4), (3, 49, 4), (1, 300, 8), (2, 4096, 4)]
+
+
+@pytest.mark.parametrize("N,n,heads", ATTN_CASES)
+def test_flash_attention_matches_torch(N, n, heads):
+    """softmax(q k^T d^-0.5) v of attend.py:98-113 through the tcgen05 kernel (no [n x n] matrix)."""
+    lib = _lib.lib()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(N + n + heads)
+    qkv = (torch.randn(N, n, 3 * heads * 32, generator=g) * 1.5).bfloat16().float()
+    q, k, v = qkv.double().view(N, n, 3, heads, 32).unbind(dim=2)
+    sim = torch.einsum("nihd,njhd->nhij", q, k) * 32 ** -0.5
+    ref = torch.einsum("nhij,njhd->nihd", sim.softmax(dim=-1), v).reshape(N, n, heads * 32)
+    out = torch.empty(N, n, heads * 32, device=dev)
+    rc = lib.ld_debug_attention(qkv.to(dev).data_ptr(), N, n, heads, out.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc)
+    assert util.rel_err(out, ref) < 1e-2
