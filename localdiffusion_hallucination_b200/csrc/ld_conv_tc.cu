@@ -1,4 +1,4 @@
-// tcgen05 / TMEM implicit-GEMM convolution for sm_100a: persistent, warp-specialised, with the
+// tcgen05 / TMEM implicit-GEMM convolution for sm_100a: persistent, warp-specialised, TMA-fed, with the
 // GroupNorm that surrounds every convolution of the denoiser fused into it.
 //
 //   D[128 pixels, NT couts] (fp32, TMEM)  +=  A[128 pixels, 16 cin] (bf16, smem) * B[NT couts, 16 cin] (bf16, smem)
@@ -10,22 +10,28 @@
 //     moving by one pixel is a 16-byte move of the descriptor start address and the 8-row core-matrix groups of
 //     the tile sit at a constant stride (SBO = halo pitch * 16 B).  Activations are read once, not nine times.
 //   * 1x1 convs: a tile is 128 consecutive pixels of the flattened [N*H*W] axis, no halo.
-//   * warp roles (14 warps): warps 0-7 are two producer teams that alternate pipeline stages (global -> registers
-//     -> [GroupNorm affine + FiLM + SiLU/ReLU of the PREVIOUS layer, "normalise on load"] -> shared memory; direct
-//     loads make zero padding, the virtual channel concat of two sources (torch.cat, ddpm.py:435-448) and the
-//     nearest x2 up-sampling (ddpm.py:116) free); warps 8-11 run the epilogue (TMEM -> registers -> bias /
-//     residual / GroupNorm statistics of THIS layer's output -> bf16 -> global); warp 12 issues the MMAs from one
-//     lane; warp 13 drives the weight pipeline.  The accumulator is double-buffered in TMEM so the epilogue of
-//     tile i overlaps the MMAs of tile i+1, and the activation ring is 3 deep.
+//   * activations arrive by TMA (cp.async.bulk.tensor, one elected thread): the NHWC tensor is described to the
+//     TMA unit as the 5-D view (8 ch, W, H, C/8, N), so one box copy of (8, 10, 18, KC/8, 1) lands the halo patch
+//     directly in the UMMA operand layout, with hardware zero fill outside the image (conv padding) -- no staging
+//     warps, no address arithmetic, several stages in flight.  Two cases keep a register staging path through two
+//     producer teams (warps 0-7): the nearest x2 up-sampling read (ddpm.py:116) and the "normalise on load"
+//     prologue, where GroupNorm affine + FiLM + SiLU/ReLU of the PREVIOUS layer is applied on the way to smem.
+//   * warps 8-11 run the epilogue (TMEM -> registers -> bias / residual / GroupNorm statistics of THIS layer's
+//     output -> bf16); for NT <= 64 the tile is written swizzled to shared memory and leaves by one TMA tensor
+//     store (full-sector writes, hardware clipping at the image border), else by direct 16-byte stores.
+//     Warp 12 issues the MMAs from one lane; warp 13 drives the weight pipeline.  The accumulator is
+//     double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   * weights are pre-packed on the host into the exact shared-memory image of every (chunk, tap) stage and
-//     copied with the TMA bulk-copy engine (cp.async.bulk -> UBLKCP): once per CTA when the whole filter fits in
-//     shared memory (all high-resolution layers), else streamed through a 4-deep mbarrier ring per tile.
+//     copied with the bulk-copy engine (cp.async.bulk): once per CTA when the whole filter fits in shared memory
+//     (all high-resolution layers), else streamed through a 4-deep mbarrier ring per tile.
 //
 // Reference call sites this kernel serves: nn.Conv2d at ddpm.py:117,173,198,227,230,268,269,372,391 and
 // unet_model.py:20,24,30 (every conv with Cin >= 32 and Cout >= 32); nn.GroupNorm + scale/shift + SiLU of
 // Block.forward (ddpm.py:174-185) and GroupNorm + ReLU of BasicBlock (unet_model.py:21-25) as prologue/epilogue.
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -42,28 +48,33 @@ constexpr int kTeamThreads = 128;      // one producer team = 4 warps
 constexpr int kTeams = 2;
 constexpr int kEpiWarp0 = 8;           // warps 8..11 (warp % 4 == TMEM lane quarter)
 constexpr int kMmaWarp = 12;
-constexpr int kWWarp = 13;
-constexpr int kThreads = 14 * 32;
-constexpr int SA = 3;                  // activation stages
+constexpr int kThreads = 14 * 32;      // warp 13: weight pipeline
+constexpr int SA_MAX = 6;              // activation stages (runtime: 3..6)
 constexpr int SB = 4;                  // weight stages (streaming mode)
-constexpr int kBatch = 6;              // 16-byte loads in flight per producer thread
+constexpr int kBatch = 3;              // 16-byte loads in flight per producer thread (register staging path)
 
-struct KParams {
+struct alignas(64) KParams {
+  CUtensorMap map_a0, map_a1, map_out;   // TMA views of the two sources and of the output (see map_in_* / map_out)
   const __nv_bfloat16* src0; const __nv_bfloat16* src1;
   int C0, C1;
   int N, H, W, Hin, Win, up;
   int tiles_x, tiles_y, ntiles;
+  int step_img, step_ty, step_tx;   // gridDim.x = step_img * tiles_x * tiles_y + step_ty * tiles_x + step_tx
   int nchunks;
   const __nv_bfloat16* w; const float* bias;
   int Cout;
   __nv_bfloat16* dst; const __nv_bfloat16* res;
   long long M;
   int resident, nb_stages, coef_floats;
+  int tma_in, tma_out, sa;           // TMA activation loads / TMA output store / number of activation stages
+  int a_stage, lbo16;                // activation stage pitch (bytes) and chunk stride (16-byte units)
+  int off_a, off_b, off_coef;        // shared memory carve-up (bytes)
   // normalise-on-load prologue (GroupNorm affine [+ FiLM] + activation of the source tensor)
   const double* pro_stats; const float* pro_gamma; const float* pro_beta; const float* pro_film;
   int pro_film_stride, pro_G, pro_act; float pro_eps;
   // GroupNorm statistics of the output
   double* stats; int stats_G;
+  int dbg;   // development aid (env LD_CONV_DBG): 1 no activation loads, 2 no MMAs, 4 no output stores
 };
 
 template <int KS, int KC>
@@ -73,10 +84,38 @@ struct Geo {
   static constexpr int PITCH = TW + KS - 1;
   static constexpr int HPIX = (TH + KS - 1) * PITCH;                   // staged pixels per chunk
   static constexpr int CH = KC / 8;                                    // 16-byte channel groups per pixel
-  static constexpr int LBO = ((HPIX * 16 + 127) / 128) * 128 + 16;     // == 16 (mod 128): conflict-free staging stores
-  static constexpr int A_STAGE = CH * LBO;
+  static constexpr int LBO_REG = ((HPIX * 16 + 127) / 128) * 128 + 16; // register path: == 16 (mod 128), conflict-free stores
+  static constexpr int LBO_TMA = HPIX * 16;                            // TMA path: dense box image
   static constexpr int ITEMS = (HPIX * CH + kTeamThreads - 1) / kTeamThreads;
   static constexpr int SBO = (KS == 3 ? PITCH : 8) * 16;               // stride between 8-pixel core-matrix groups
+};
+
+// walks tile = blockIdx.x + k * gridDim.x and keeps its (image, tile row, tile column) without integer divisions
+struct TileWalk {
+  int tile, img, ty, tx;
+  __device__ __forceinline__ void init(const KParams& p, bool k3) {
+    tile = blockIdx.x; img = 0; ty = 0; tx = 0;
+    if (k3) {
+      const int tpi = p.tiles_x * p.tiles_y;
+      img = tile / tpi;
+      const int r = tile - img * tpi;
+      ty = r / p.tiles_x; tx = r - ty * p.tiles_x;
+    }
+  }
+  __device__ __forceinline__ void next(const KParams& p) {
+    tile += gridDim.x;
+    tx += p.step_tx;
+    if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+    ty += p.step_ty;
+    if (ty >= p.tiles_y) { ty -= p.tiles_y; ++img; }
+    img += p.step_img;
+  }
+};
+
+// ring position: stage index and phase parity, advanced without divisions
+struct Ring {
+  int s = 0; uint32_t ph = 0;
+  __device__ __forceinline__ void advance(int n) { if (++s == n) { s = 0; ph ^= 1; } }
 };
 
 // y = act(a * x + b) on 8 bf16 channels
@@ -110,28 +149,33 @@ __device__ __forceinline__ void stats_chunk(const float (&f)[16], bool valid, fl
 }
 
 template <int NT, int KS, int KC>
-__global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const KParams p) {
+__global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_constant__ KParams p) {
   using G = Geo<KS, KC>;
   constexpr int TAPS = KS * KS;
   constexpr int B_STAGE = NT * KC * 2;
   constexpr uint32_t TM_COLS = 2 * NT;   // two accumulator stages; NT in {32,64,128,256} -> power of two >= 64
-  extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* a_s = smem;
-  uint8_t* b_s = smem + SA * G::A_STAGE;
-  float* coef = reinterpret_cast<float*>(b_s + (size_t)p.nb_stages * B_STAGE);
+  constexpr int O_ROW = NT * 2;          // bytes of one staged output row (TMA store path, NT <= 64)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* o_s = smem;                                // [2][128 rows][O_ROW] swizzled output tiles (TMA store path)
+  uint8_t* a_s = smem + p.off_a;
+  uint8_t* b_s = smem + p.off_b;
+  float* coef = reinterpret_cast<float*>(smem + p.off_coef);
   float* sacc = coef + p.coef_floats;                 // [256] per-tile GroupNorm partial sums
   float* bias_s = sacc + 256;                         // [NT] bias of this CTA's output channels
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + NT);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA + 2 * SB + 4);
-  const uint32_t a_full = smem_u32(bars), a_empty = a_full + 8 * SA, b_full = a_empty + 8 * SA, b_empty = b_full + 8 * SB,
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA_MAX + 2 * SB + 4);
+  const uint32_t a_full = smem_u32(bars), a_empty = a_full + 8 * SA_MAX, b_full = a_empty + 8 * SA_MAX, b_empty = b_full + 8 * SB,
                  acc_full = b_empty + 8 * SB, acc_empty = acc_full + 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int SA = p.sa;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < SA; ++i) { mbar_init(a_full + 8 * i, 4); mbar_init(a_empty + 8 * i, 1); }
+    for (int i = 0; i < SA; ++i) { mbar_init(a_full + 8 * i, p.tma_in ? 1 : 4); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < SB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 128); }
     fence_barrier_init();
+    if (p.tma_in) { tma_prefetch_desc(&p.map_a0); if (p.C1) tma_prefetch_desc(&p.map_a1); }
+    if (p.tma_out) tma_prefetch_desc(&p.map_out);
   }
   for (int i = threadIdx.x; i < 256; i += kThreads) sacc[i] = 0.f;
   for (int i = threadIdx.x; i < NT; i += kThreads) bias_s[i] = p.bias ? p.bias[blockIdx.y * NT + i] : 0.f;
@@ -141,101 +185,132 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const KParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n_tile = blockIdx.y;
-  const int tiles_per_img = p.tiles_x * p.tiles_y;
 
   if (warp < kTeams * 4) {
-    // ================================================================== producers =====================
-    const int team = warp >> 2, tid = threadIdx.x & (kTeamThreads - 1);
-    const int ch = tid % G::CH;                       // constant per thread: 128 % CH == 0
-    float* cA = coef + team * 2 * (p.coef_floats / 4);  // [Cin] scale, then [Cin] shift
-    float* cB = cA + p.coef_floats / 4;
-    int cur_img = -1;
-    int it_tile = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it_tile) {
-      int img = 0, ty0 = 0, tx0 = 0;
-      long long pix0 = 0;
-      if (KS == 3) {
-        img = tile / tiles_per_img;
-        const int r = tile - img * tiles_per_img;
-        const int ty = r / p.tiles_x;
-        ty0 = ty * G::TH; tx0 = (r - ty * p.tiles_x) * G::TW;
-      } else {
-        pix0 = (long long)tile * 128;
-      }
-      if (p.pro_stats && img != cur_img) {
-        // GroupNorm coefficients of the source tensor for this image (ddpm.py:174-185 folded to y = a x + b)
-        named_bar(1 + team, kTeamThreads);            // nobody of this team still reads the old coefficients
-        const int Cin = p.C0, cpg = Cin / p.pro_G;
-        const double cnt = (double)p.Hin * p.Win * cpg;
-        for (int c = tid; c < Cin; c += kTeamThreads) {
-          const int g = c / cpg;
-          const double su = p.pro_stats[((size_t)img * p.pro_G + g) * 2], sq = p.pro_stats[((size_t)img * p.pro_G + g) * 2 + 1];
-          const double mean = su / cnt;
-          double var = sq / cnt - mean * mean;
-          if (var < 0) var = 0;
-          const float rstd = (float)(1.0 / sqrt(var + (double)p.pro_eps));
-          float a = rstd * p.pro_gamma[c], b = p.pro_beta[c] - (float)mean * a;
-          if (p.pro_film) {
-            const float sc = p.pro_film[(size_t)img * p.pro_film_stride + c] + 1.0f;
-            const float sf = p.pro_film[(size_t)img * p.pro_film_stride + Cin + c];
-            a *= sc; b = b * sc + sf;
+    if (p.tma_in) {
+      // ================================================================ TMA producer (one thread) =======
+      if (warp == 0 && lane == 0) {
+        Ring ra;
+        TileWalk tw;
+        tw.init(p, KS == 3);
+        const uint32_t stage_bytes = (uint32_t)(G::CH * G::LBO_TMA);
+        for (; tw.tile < p.ntiles; tw.next(p)) {
+          for (int c = 0; c < p.nchunks; ++c) {
+            mbar_wait(a_empty + 8 * ra.s, ra.ph ^ 1);
+            const int cbase = c * KC;
+            const void* map = cbase < p.C0 ? (const void*)&p.map_a0 : (const void*)&p.map_a1;
+            const int cb8 = (cbase < p.C0 ? cbase : cbase - p.C0) >> 3;
+            const uint32_t dst = smem_u32(a_s + (size_t)ra.s * p.a_stage);
+            mbar_arrive_expect_tx(a_full + 8 * ra.s, stage_bytes);
+            if (!(p.dbg & 1)) {
+              if (KS == 3) tma_load_5d(dst, map, 0, tw.tx * G::TW - 1, tw.ty * G::TH - 1, cb8, tw.img, a_full + 8 * ra.s);
+              else tma_load_3d(dst, map, 0, tw.tile * 128, cb8, a_full + 8 * ra.s);
+            } else {
+              // development aid: complete the transaction without data
+              asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(a_full + 8 * ra.s), "r"(stage_bytes) : "memory");
+            }
+            ra.advance(SA);
           }
-          cA[c] = a; cB[c] = b;
         }
-        named_bar(1 + team, kTeamThreads);
-        cur_img = img;
       }
-      for (int c = 0; c < p.nchunks; ++c) {
-        const int g = it_tile * p.nchunks + c;
-        if ((g & 1) != team) continue;
-        const int sa = g % SA;
-        mbar_wait(a_empty + 8 * sa, ((g / SA) & 1) ^ 1);
-        const int cbase = c * KC;
-        const __nv_bfloat16* src; int cs, cb;
-        if (cbase < p.C0) { src = p.src0; cs = p.C0; cb = cbase; } else { src = p.src1; cs = p.C1; cb = cbase - p.C0; }
-        float pa[8], pb[8];
-        if (p.pro_stats) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { pa[j] = cA[cbase + ch * 8 + j]; pb[j] = cB[cbase + ch * 8 + j]; }
+    } else {
+      // ================================================================ register-staging producers ======
+      const int team = warp >> 2, tid = threadIdx.x & (kTeamThreads - 1);
+      const int ch = tid % G::CH;                       // constant per thread: 128 % CH == 0
+      float* cA = coef + team * 2 * (p.coef_floats / 4);  // [Cin] scale, then [Cin] shift
+      float* cB = cA + p.coef_floats / 4;
+      int cur_img = -1;
+      const int hp0 = tid / G::CH;                      // my first staged pixel; item `it` stages pixel hp0 + it * (128 / CH)
+      constexpr int HSTEP = kTeamThreads / G::CH;
+      Ring ra;                                          // position of global stage g
+      int g = 0;
+      TileWalk tw;
+      tw.init(p, KS == 3);
+      for (; tw.tile < p.ntiles; tw.next(p)) {
+        if (p.nchunks == 1 && (g & 1) != team) { ++g; ra.advance(SA); continue; }
+        const int img = tw.img, ty0 = tw.ty * G::TH, tx0 = tw.tx * G::TW;
+        const long long pix0 = (long long)tw.tile * 128;
+        if (p.pro_stats && img != cur_img) {
+          // GroupNorm coefficients of the source tensor for this image (ddpm.py:174-185 folded to y = a x + b)
+          named_bar(1 + team, kTeamThreads);            // nobody of this team still reads the old coefficients
+          const int Cin = p.C0, cpg = Cin / p.pro_G;
+          const double cnt = (double)p.Hin * p.Win * cpg;
+          for (int c = tid; c < Cin; c += kTeamThreads) {
+            const int gi = c / cpg;
+            const double su = p.pro_stats[((size_t)img * p.pro_G + gi) * 2], sq = p.pro_stats[((size_t)img * p.pro_G + gi) * 2 + 1];
+            const double mean = su / cnt;
+            double var = sq / cnt - mean * mean;
+            if (var < 0) var = 0;
+            const float rstd = (float)(1.0 / sqrt(var + (double)p.pro_eps));
+            float a = rstd * p.pro_gamma[c], b = p.pro_beta[c] - (float)mean * a;
+            if (p.pro_film) {
+              const float sc = p.pro_film[(size_t)img * p.pro_film_stride + c] + 1.0f;
+              const float sf = p.pro_film[(size_t)img * p.pro_film_stride + Cin + c];
+              a *= sc; b = b * sc + sf;
+            }
+            cA[c] = a; cB[c] = b;
+          }
+          named_bar(1 + team, kTeamThreads);
+          cur_img = img;
         }
-        uint8_t* stage = a_s + sa * G::A_STAGE + ch * G::LBO;
+        // the whole halo patch lies inside the image: no bounds checks
+        const bool interior = KS == 3 && ty0 > 0 && tx0 > 0 && ty0 + G::TH < p.H && tx0 + G::TW < p.W && !p.up;
+        const long long tbase = ((long long)img * p.Hin + (ty0 - 1)) * p.Win + (tx0 - 1);   // halo origin (3x3, no up-sampling)
+        for (int c = 0; c < p.nchunks; ++c, ++g, ra.advance(SA)) {
+          if ((g & 1) != team) continue;
+          mbar_wait(a_empty + 8 * ra.s, ra.ph ^ 1);
+          const int cbase = c * KC;
+          const __nv_bfloat16* src; int cs, cb;
+          if (cbase < p.C0) { src = p.src0; cs = p.C0; cb = cbase; } else { src = p.src1; cs = p.C1; cb = cbase - p.C0; }
+          src += cb + ch * 8;
+          float pa[8], pb[8];
+          if (p.pro_stats) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { pa[j] = cA[cbase + ch * 8 + j]; pb[j] = cB[cbase + ch * 8 + j]; }
+          }
+          uint8_t* stage = a_s + (size_t)ra.s * p.a_stage + ch * G::LBO_REG + hp0 * 16;
 #pragma unroll 1
-        for (int it0 = 0; it0 < G::ITEMS; it0 += kBatch) {
-          uint4 v[kBatch];
-          bool ok[kBatch];
+          for (int it0 = 0; it0 < G::ITEMS; it0 += kBatch) {
+            uint4 v[kBatch];
+            bool ok[kBatch];
 #pragma unroll
-          for (int k = 0; k < kBatch; ++k) {
-            const int hp = ((it0 + k) * kTeamThreads + tid) / G::CH;
-            v[k] = make_uint4(0u, 0u, 0u, 0u);
-            ok[k] = false;
-            if (it0 + k < G::ITEMS && hp < G::HPIX) {
-              long long goff = -1;
-              if (KS == 3) {
-                const int hy = hp / G::PITCH, hx = hp - hy * G::PITCH;
-                int gy = ty0 + hy - 1, gx = tx0 + hx - 1;
-                if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
-                  if (p.up) { gy >>= 1; gx >>= 1; }
-                  goff = ((long long)img * p.Hin + gy) * p.Win + gx;
+            for (int k = 0; k < kBatch; ++k) {
+              const int hp = hp0 + (it0 + k) * HSTEP;
+              v[k] = make_uint4(0u, 0u, 0u, 0u);
+              ok[k] = false;
+              if (it0 + k < G::ITEMS && hp < G::HPIX) {
+                long long goff = -1;
+                if (KS == 3) {
+                  const int hy = hp / G::PITCH, hx = hp - hy * G::PITCH;
+                  if (interior) {
+                    goff = tbase + hy * p.Win + hx;
+                  } else {
+                    int gy = ty0 + hy - 1, gx = tx0 + hx - 1;
+                    if ((unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W) {
+                      if (p.up) { gy >>= 1; gx >>= 1; }
+                      goff = ((long long)img * p.Hin + gy) * p.Win + gx;
+                    }
+                  }
+                } else {
+                  const long long gp = pix0 + hp;
+                  if (gp < p.M) goff = gp;
                 }
-              } else {
-                const long long gp = pix0 + hp;
-                if (gp < p.M) goff = gp;
+                if (goff >= 0 && !(p.dbg & 1)) { v[k] = __ldg(reinterpret_cast<const uint4*>(src + goff * cs)); ok[k] = true; }
               }
-              if (goff >= 0) { v[k] = __ldg(reinterpret_cast<const uint4*>(src + goff * cs + cb + ch * 8)); ok[k] = true; }
             }
-          }
 #pragma unroll
-          for (int k = 0; k < kBatch; ++k) {
-            const int hp = ((it0 + k) * kTeamThreads + tid) / G::CH;
-            if (it0 + k < G::ITEMS && hp < G::HPIX) {
-              if (p.pro_stats && ok[k]) v[k] = pro_apply(v[k], pa, pb, p.pro_act);   // padding stays exactly zero
-              *reinterpret_cast<uint4*>(stage + hp * 16) = v[k];
+            for (int k = 0; k < kBatch; ++k) {
+              const int hp = hp0 + (it0 + k) * HSTEP;
+              if (it0 + k < G::ITEMS && hp < G::HPIX) {
+                if (p.pro_stats && ok[k]) v[k] = pro_apply(v[k], pa, pb, p.pro_act);   // padding stays exactly zero
+                *reinterpret_cast<uint4*>(stage + (it0 + k) * (HSTEP * 16)) = v[k];
+              }
             }
           }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_full + 8 * ra.s);
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_full + 8 * sa);
       }
     }
   } else if (warp < kMmaWarp) {
@@ -245,52 +320,59 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const KParams p) {
     const int nbase = n_tile * NT;
     const int cpg = p.stats ? p.Cout / p.stats_G : 1;
     int it_tile = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it_tile) {
+    TileWalk tw;
+    tw.init(p, KS == 3);
+    for (; tw.tile < p.ntiles; tw.next(p), ++it_tile) {
       const int as = it_tile & 1;
-      int img = 0;
+      const int img = tw.img;
       long long opix = -1;
       if (KS == 3) {
-        img = tile / tiles_per_img;
-        const int r = tile - img * tiles_per_img;
-        const int ty = r / p.tiles_x;
-        const int gy = ty * G::TH + (m >> 3), gx = (r - ty * p.tiles_x) * G::TW + (m & 7);
+        const int gy = tw.ty * G::TH + (m >> 3), gx = tw.tx * G::TW + (m & 7);
         if (gy < p.H && gx < p.W) opix = ((long long)img * p.H + gy) * p.W + gx;
       } else {
-        const long long gp = (long long)tile * 128 + m;
+        const long long gp = (long long)tw.tile * 128 + m;
         if (gp < p.M) opix = gp;
       }
       mbar_wait(acc_full + 8 * as, (it_tile >> 1) & 1);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * NT);
+      // TMA store path: the store that read this staging buffer two tiles ago must have finished reading it
+      if (NT <= 64 && p.tma_out) {
+        if (etid == 0) bulk_wait_group_read<1>();
+        named_bar(3, 128);
+      }
+      uint8_t* orow = o_s + (size_t)as * (128 * O_ROW) + (size_t)m * O_ROW;
 #pragma unroll 1
-      for (int j0 = 0; j0 < NT; j0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(trow + j0, r);
+      for (int j1 = 0; j1 < NT; j1 += 32) {
+        uint32_t r32[32];
+        tmem_ld32(trow + j1, r32);
         tmem_ld_wait();
-        if (j0 + 16 == NT) {              // every TMEM read of this thread is complete: hand the stage back
+        if (j1 + 32 == NT) {              // every TMEM read of this thread is complete: hand the stage back
           tc_fence_before();
           mbar_arrive(acc_empty + 8 * as);
         }
-        float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j0 + j);
-          f[j] = __uint_as_float(r[j]) + b4.x; f[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
-          f[j + 2] = __uint_as_float(r[j + 2]) + b4.z; f[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
-        }
-        if (p.stats) {
-          const int grp0 = (nbase + j0) / cpg - nbase / cpg;
-          const bool valid = opix >= 0;
-          switch (cpg) {
-            case 2: stats_chunk<2>(f, valid, sacc, grp0, lane); break;
-            case 4: stats_chunk<4>(f, valid, sacc, grp0, lane); break;
-            case 8: stats_chunk<8>(f, valid, sacc, grp0, lane); break;
-            default: stats_chunk<16>(f, valid, sacc, grp0, lane); break;   // cpg >= 16: chunk inside one group
+        for (int h = 0; h < 2; ++h) {
+          const int j0 = j1 + 16 * h;
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j0 + j);
+            f[j] = __uint_as_float(r32[16 * h + j]) + b4.x; f[j + 1] = __uint_as_float(r32[16 * h + j + 1]) + b4.y;
+            f[j + 2] = __uint_as_float(r32[16 * h + j + 2]) + b4.z; f[j + 3] = __uint_as_float(r32[16 * h + j + 3]) + b4.w;
           }
-        }
-        if (opix >= 0) {
-          const size_t o = (size_t)opix * p.Cout + nbase + j0;
-          if (p.res) {
+          if (p.stats) {
+            const int grp0 = (nbase + j0) / cpg - nbase / cpg;
+            const bool valid = opix >= 0;
+            switch (cpg) {
+              case 2: stats_chunk<2>(f, valid, sacc, grp0, lane); break;
+              case 4: stats_chunk<4>(f, valid, sacc, grp0, lane); break;
+              case 8: stats_chunk<8>(f, valid, sacc, grp0, lane); break;
+              default: stats_chunk<16>(f, valid, sacc, grp0, lane); break;   // cpg >= 16: chunk inside one group
+            }
+          }
+          if (p.res && opix >= 0) {
+            const size_t o = (size_t)opix * p.Cout + nbase + j0;
             const uint4 r0 = *reinterpret_cast<const uint4*>(p.res + o), r1 = *reinterpret_cast<const uint4*>(p.res + o + 8);
             const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
@@ -302,8 +384,29 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const KParams p) {
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-          *reinterpret_cast<uint4*>(p.dst + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(p.dst + o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          if (NT <= 64 && p.tma_out) {
+            // 16-byte chunk index XOR row bits = the TMA 64B / 128B swizzle pattern: conflict-free row-per-thread stores
+            const int c0 = j0 >> 3;
+            const int sw = NT == 32 ? ((m >> 1) & 3) : (m & 7);
+            *reinterpret_cast<uint4*>(orow + ((c0 ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(orow + (((c0 + 1) ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          } else if (opix >= 0 && !(p.dbg & 4)) {
+            const size_t o = (size_t)opix * p.Cout + nbase + j0;
+            *reinterpret_cast<uint4*>(p.dst + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(p.dst + o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+      }
+      if (NT <= 64 && p.tma_out) {
+        fence_proxy_async();               // my generic-proxy writes are visible to the TMA unit
+        named_bar(3, 128);
+        if (etid == 0) {
+          if (!(p.dbg & 4)) {
+            const uint32_t src = smem_u32(o_s + (size_t)as * (128 * O_ROW));
+            if (KS == 3) tma_store_4d(&p.map_out, nbase, tw.tx * G::TW, tw.ty * G::TH, img, src);
+            else tma_store_2d(&p.map_out, nbase, tw.tile * 128, src);
+            bulk_commit_group();
+          }
         }
       }
       if (p.stats) {
@@ -313,22 +416,25 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const KParams p) {
         if (etid < ng2) {
           const float v = sacc[etid];
           sacc[etid] = 0.f;
-          const int g = nbase / cpg + (etid >> 1);
-          atomicAdd(p.stats + ((size_t)img * p.stats_G + g) * 2 + (etid & 1), (double)v);
+          const int gi = nbase / cpg + (etid >> 1);
+          atomicAdd(p.stats + ((size_t)img * p.stats_G + gi) * 2 + (etid & 1), (double)v);
         }
         named_bar(3, 128);
       }
     }
+    if (NT <= 64 && p.tma_out && etid == 0) bulk_wait_group<0>();
   } else if (warp == kMmaWarp) {
     // ================================================================== MMA issue =====================
-    // One thread issues every tcgen05.mma of the CTA, so its instruction stream is kept minimal: the descriptors
-    // are (lo, hi) register pairs and every tap / k-step only adds a compile-time constant to `lo`.
+    // The whole warp runs the loop (barrier waits); one elected lane issues tcgen05.mma / commit.  Descriptors
+    // are (lo, hi) register pairs and every tap / k-step only adds a small constant to `lo`.
     {
       constexpr uint32_t idesc = make_idesc(128, NT);
       const uint32_t a_hi = desc_hi(G::SBO), b_hi = desc_hi(128);
-      const uint32_t a_lo0 = desc_lo(smem_u32(a_s), G::LBO), b_lo0 = desc_lo(smem_u32(b_s), NT * 16);
-      int sb = 0; uint32_t pb = 0;
-      int g = 0, it_tile = 0;
+      const uint32_t lbo16 = (uint32_t)p.lbo16;
+      const uint32_t a_lo0 = desc_lo(smem_u32(a_s), lbo16 << 4), b_lo0 = desc_lo(smem_u32(b_s), NT * 16);
+      const uint32_t a_stage16 = (uint32_t)p.a_stage >> 4;
+      Ring ra, rb;
+      int it_tile = 0;
       if (p.resident) { mbar_wait(b_full, 0); tc_fence_after(); }
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it_tile) {
         const int as = it_tile & 1;
@@ -336,25 +442,26 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const KParams p) {
         tc_fence_after();
         const uint32_t dcol = tmem_base + (uint32_t)(as * NT);
         uint32_t acc = 0;
-        for (int c = 0; c < p.nchunks; ++c, ++g) {
-          const int sa = g % SA;
-          mbar_wait(a_full + 8 * sa, (g / SA) & 1);
+        for (int c = 0; c < p.nchunks; ++c) {
+          mbar_wait(a_full + 8 * ra.s, ra.ph);
           tc_fence_after();
-          const uint32_t a_lo = a_lo0 + (uint32_t)(sa * (G::A_STAGE >> 4));
+          const uint32_t a_lo = a_lo0 + (uint32_t)ra.s * a_stage16;
           if (p.resident) {
             const uint32_t b_lo = b_lo0 + (uint32_t)(c * TAPS * (B_STAGE >> 4));
             if (elect_one()) {
+              if (!(p.dbg & 2)) {
 #pragma unroll
-              for (int tap = 0; tap < TAPS; ++tap) {
-                const int ky = tap / KS, kx = tap - ky * KS;
+                for (int tap = 0; tap < TAPS; ++tap) {
+                  const int ky = tap / KS, kx = tap - ky * KS;
 #pragma unroll
-                for (int k = 0; k < KC / 16; ++k) {
-                  umma_bf16_lh(dcol, a_lo + (uint32_t)(ky * G::PITCH + kx + 2 * k * (G::LBO >> 4)), a_hi,
-                               b_lo + (uint32_t)(tap * (B_STAGE >> 4) + 2 * k * NT), b_hi, idesc, acc);
-                  acc = 1;
+                  for (int k = 0; k < KC / 16; ++k) {
+                    umma_bf16_lh(dcol, a_lo + (uint32_t)(ky * G::PITCH + kx) + (uint32_t)(2 * k) * lbo16, a_hi,
+                                 b_lo + (uint32_t)(tap * (B_STAGE >> 4) + 2 * k * NT), b_hi, idesc, acc);
+                    acc = 1;
+                  }
                 }
               }
-              umma_commit(a_empty + 8 * sa);
+              umma_commit(a_empty + 8 * ra.s);
               if (c == p.nchunks - 1) umma_commit(acc_full + 8 * as);
             }
             acc = 1;
@@ -362,28 +469,29 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const KParams p) {
           } else {
 #pragma unroll 1
             for (int tap = 0; tap < TAPS; ++tap) {
-              mbar_wait(b_full + 8 * sb, pb);
+              mbar_wait(b_full + 8 * rb.s, rb.ph);
               tc_fence_after();
-              const uint32_t b_lo = b_lo0 + (uint32_t)(sb * (B_STAGE >> 4));
+              const uint32_t b_lo = b_lo0 + (uint32_t)(rb.s * (B_STAGE >> 4));
               const int ky = tap / KS, kx = tap - ky * KS;
               const uint32_t a_t = a_lo + (uint32_t)(ky * G::PITCH + kx);
               if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < KC / 16; ++k) {
-                  umma_bf16_lh(dcol, a_t + (uint32_t)(2 * k * (G::LBO >> 4)), a_hi, b_lo + (uint32_t)(2 * k * NT), b_hi, idesc, acc);
+                  umma_bf16_lh(dcol, a_t + (uint32_t)(2 * k) * lbo16, a_hi, b_lo + (uint32_t)(2 * k * NT), b_hi, idesc, acc);
                   acc = 1;
                 }
-                umma_commit(b_empty + 8 * sb);
+                umma_commit(b_empty + 8 * rb.s);
                 if (tap == TAPS - 1) {
-                  umma_commit(a_empty + 8 * sa);
+                  umma_commit(a_empty + 8 * ra.s);
                   if (c == p.nchunks - 1) umma_commit(acc_full + 8 * as);
                 }
               }
               acc = 1;
               __syncwarp();
-              if (++sb == SB) { sb = 0; pb ^= 1; }
+              rb.advance(SB);
             }
           }
+          ra.advance(SA);
         }
       }
     }
@@ -393,18 +501,16 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const KParams p) {
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)n_tile * p.nchunks * TAPS * B_STAGE;
       const int total = p.nchunks * TAPS;
       if (p.resident) {
-        if (blockIdx.x < p.ntiles) {
-          mbar_arrive_expect_tx(b_full, (uint32_t)total * B_STAGE);
-          for (int i = 0; i < total; ++i) bulk_g2s(smem_u32(b_s + (size_t)i * B_STAGE), wsrc + (size_t)i * B_STAGE, B_STAGE, b_full);
-        }
+        mbar_arrive_expect_tx(b_full, (uint32_t)total * B_STAGE);
+        for (int i = 0; i < total; ++i) bulk_g2s(smem_u32(b_s + (size_t)i * B_STAGE), wsrc + (size_t)i * B_STAGE, B_STAGE, b_full);
       } else {
-        int sb = 0; uint32_t pb = 0;
+        Ring rb;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
           for (int i = 0; i < total; ++i) {
-            mbar_wait(b_empty + 8 * sb, pb ^ 1);
-            mbar_arrive_expect_tx(b_full + 8 * sb, B_STAGE);
-            bulk_g2s(smem_u32(b_s + sb * B_STAGE), wsrc + (size_t)i * B_STAGE, B_STAGE, b_full + 8 * sb);
-            if (++sb == SB) { sb = 0; pb ^= 1; }
+            mbar_wait(b_empty + 8 * rb.s, rb.ph ^ 1);
+            mbar_arrive_expect_tx(b_full + 8 * rb.s, B_STAGE);
+            bulk_g2s(smem_u32(b_s + rb.s * B_STAGE), wsrc + (size_t)i * B_STAGE, B_STAGE, b_full + 8 * rb.s);
+            rb.advance(SB);
           }
         }
       }
@@ -416,13 +522,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const KParams p) {
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, TM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
 constexpr size_t kResidentBudget = 200 * 1024;
-
-template <int KS, int KC>
-size_t smem_bytes(int NT, int nb_stages, int coef_floats) {
-  return (size_t)SA * Geo<KS, KC>::A_STAGE + (size_t)nb_stages * NT * KC * 2 + (size_t)(coef_floats + 256 + NT) * 4 +
-         (2 * SA + 2 * SB + 4) * 8 + 16;
-}
 
 struct Cfg { int max_smem = 0; int max_smem_sm = 0; int sms = 0; };
 Cfg& cfg() {
@@ -435,6 +538,66 @@ Cfg& cfg() {
     cudaDeviceGetAttribute(&c.max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
   }
   return c;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    if (getenv("LD_CONV_NO_TMA")) return nullptr;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+  }
+  return fn;
+}
+
+// NHWC bf16 activation [N][H][W][C] as the view (8 ch, W, H, C/8, N): a box of (8, PITCH, ROWS, KC/8, 1) is the
+// UMMA K-major operand image [KC/8 chunks][ROWS*PITCH pixels][16 B] of a halo patch, zero filled outside the image.
+bool map_in_3x3(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int kc, int pitch, int rows) {
+  EncodeTiledFn f = encode_fn();
+  if (!f) return false;
+  const cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C / 8), (cuuint64_t)N};
+  const cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, 16, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[5] = {8, (cuuint32_t)pitch, (cuuint32_t)rows, (cuuint32_t)(kc / 8), 1};
+  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  return f(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// flattened pixels [M][C] as (8 ch, M, C/8): box (8, 128, KC/8)
+bool map_in_1x1(CUtensorMap* m, const void* ptr, long long M, int C, int kc) {
+  EncodeTiledFn f = encode_fn();
+  if (!f) return false;
+  const cuuint64_t dims[3] = {8, (cuuint64_t)M, (cuuint64_t)(C / 8)};
+  const cuuint64_t strides[2] = {(cuuint64_t)C * 2, 16};
+  const cuuint32_t box[3] = {8, 128, (cuuint32_t)(kc / 8)};
+  const cuuint32_t es[3] = {1, 1, 1};
+  return f(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// output [N][H][W][Cout]: box (NT, 8, 16, 1) (3x3) or [M][Cout]: box (NT, 128) (1x1), 64B / 128B swizzle for NT = 32 / 64
+bool map_out(CUtensorMap* m, void* ptr, int N, int H, int W, int Cout, int nt, int ks) {
+  EncodeTiledFn f = encode_fn();
+  if (!f || (nt != 32 && nt != 64)) return false;
+  const CUtensorMapSwizzle sw = nt == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  if (ks == 3) {
+    const cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)nt, 8, 16, 1};
+    return f(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)Cout, (cuuint64_t)N * H * W};
+  const cuuint64_t strides[1] = {(cuuint64_t)Cout * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)nt, 128};
+  return f(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // opt in to the maximum dynamic shared memory once per instantiation (done at pack time, outside any graph capture)
@@ -453,38 +616,63 @@ int configure_nt(int NT) {
   return -1;
 }
 
+// shared memory carve-up; returns total bytes
 template <int NT, int KS, int KC>
-int launch_one(KParams& p, int ntiles_y, size_t smem, cudaStream_t s) {
-  // persistent grid: as many CTAs as can be resident (shared memory, 2*NT TMEM columns of 512 each)
-  // (registers allow two CTAs per SM, see __launch_bounds__)
+size_t layout(KParams& p, int sa, int nb_stages) {
+  using G = Geo<KS, KC>;
+  size_t off = 0;
+  if (p.tma_out) off += 2 * 128 * NT * 2;                      // output staging (1024-byte aligned, first)
+  p.off_a = (int)off;
+  p.a_stage = p.tma_in ? G::CH * G::LBO_TMA : G::CH * G::LBO_REG;
+  p.a_stage = (p.a_stage + 127) & ~127;
+  p.lbo16 = (p.tma_in ? G::LBO_TMA : G::LBO_REG) >> 4;
+  off += (size_t)sa * p.a_stage;
+  off = (off + 127) & ~(size_t)127;
+  p.off_b = (int)off;
+  off += (size_t)nb_stages * NT * KC * 2;
+  p.off_coef = (int)off;
+  off += (size_t)(p.coef_floats + 256 + NT) * 4 + (2 * SA_MAX + 2 * SB + 4) * 8 + 16;
+  return off;
+}
+
+template <int NT, int KS, int KC>
+int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
+  const int total = p.nchunks * KS * KS;
+  const size_t limit = (size_t)cfg().max_smem < kResidentBudget ? (size_t)cfg().max_smem : kResidentBudget;
+  // weights resident in shared memory when everything fits; more activation stages when fed by TMA
+  int sa = p.tma_in ? 4 : 3;
+  p.resident = layout<NT, KS, KC>(p, sa, total) <= limit ? 1 : 0;
+  p.nb_stages = p.resident ? total : SB;
+  size_t smem = layout<NT, KS, KC>(p, sa, p.nb_stages);
+  if (smem > (size_t)cfg().max_smem) { sa = 3; smem = layout<NT, KS, KC>(p, sa, p.nb_stages); }
+  if (smem > (size_t)cfg().max_smem) return -1;
+  p.sa = sa;
+  // persistent grid: as many CTAs as are co-resident (registers allow two per SM; 2*NT of 512 TMEM columns each)
   int occ = (int)((size_t)cfg().max_smem_sm / (smem + 1024));
   if (occ > 2) occ = 2;
   const int tm = 512 / (2 * NT);
   if (occ > tm) occ = tm;
   if (occ < 1) occ = 1;
-  const int occ_cache = occ;
-  int gx = cfg().sms * occ_cache / ntiles_y;
+  int gx = cfg().sms * occ / ntiles_y;
   if (gx < 1) gx = 1;
   if (gx > p.ntiles) gx = p.ntiles;
+  {
+    const int tpi = p.tiles_x * p.tiles_y;
+    p.step_img = gx / tpi;
+    const int r = gx - p.step_img * tpi;
+    p.step_ty = r / p.tiles_x; p.step_tx = r - p.step_ty * p.tiles_x;
+  }
   conv_tc_kernel<NT, KS, KC><<<dim3((unsigned)gx, (unsigned)ntiles_y), kThreads, smem, s>>>(p);
   return 1;
 }
 
 template <int KS, int KC>
 int launch_nt(int NT, KParams& p, int ntiles_y, cudaStream_t s) {
-  // weights resident in shared memory when everything fits
-  const int total = p.nchunks * KS * KS;
-  const size_t res_bytes = smem_bytes<KS, KC>(NT, total, p.coef_floats);
-  const size_t limit = (size_t)cfg().max_smem < kResidentBudget ? (size_t)cfg().max_smem : kResidentBudget;
-  p.resident = res_bytes <= limit ? 1 : 0;
-  p.nb_stages = p.resident ? total : SB;
-  const size_t smem = smem_bytes<KS, KC>(NT, p.nb_stages, p.coef_floats);
-  if (smem > (size_t)cfg().max_smem) return -1;
   switch (NT) {
-    case 32: return launch_one<32, KS, KC>(p, ntiles_y, smem, s);
-    case 64: return launch_one<64, KS, KC>(p, ntiles_y, smem, s);
-    case 128: return launch_one<128, KS, KC>(p, ntiles_y, smem, s);
-    case 256: return launch_one<256, KS, KC>(p, ntiles_y, smem, s);
+    case 32: return launch_one<32, KS, KC>(p, ntiles_y, s);
+    case 64: return launch_one<64, KS, KC>(p, ntiles_y, s);
+    case 128: return launch_one<128, KS, KC>(p, ntiles_y, s);
+    case 256: return launch_one<256, KS, KC>(p, ntiles_y, s);
   }
   return -1;
 }
@@ -551,13 +739,16 @@ bool conv_tc_supports(const ConvTcW& w, const ConvTcArgs& a) {
   return true;
 }
 
+long long* conv_tc_trace() { return nullptr; }
+
 int conv_tc_launch(const ConvTcW& w, const ConvTcArgs& a, cudaStream_t s) {
   if (!conv_tc_supports(w, a)) return -1;
   const bool k64 = w.w && a.C0 % 64 == 0 && a.C1 % 64 == 0;
+  const int kc = k64 ? 64 : 32;
   KParams p{};
   p.src0 = (const __nv_bfloat16*)a.src0; p.src1 = (const __nv_bfloat16*)a.src1; p.C0 = a.C0; p.C1 = a.C1;
   p.N = a.N; p.H = a.H; p.W = a.W; p.Hin = a.Hin; p.Win = a.Win; p.up = a.up;
-  p.nchunks = w.Cin / (k64 ? 64 : 32);
+  p.nchunks = w.Cin / kc;
   p.w = (const __nv_bfloat16*)(k64 ? w.w : w.w32); p.bias = w.bias; p.Cout = w.Cout;
   p.dst = (__nv_bfloat16*)a.dst; p.res = (const __nv_bfloat16*)a.res;
   p.M = (long long)a.N * a.H * a.W;
@@ -565,6 +756,16 @@ int conv_tc_launch(const ConvTcW& w, const ConvTcArgs& a, cudaStream_t s) {
   p.pro_film_stride = a.pro_film_stride; p.pro_G = a.pro_G; p.pro_act = a.pro_act; p.pro_eps = a.pro_eps;
   p.coef_floats = a.pro_stats ? 4 * a.C0 : 0;   // two teams x (scale, shift)
   p.stats = a.stats; p.stats_G = a.stats_G;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("LD_CONV_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
+  // TMA activation loads whenever the source is read as stored (no up-sampling, no normalise-on-load)
+  p.tma_in = 0;
+  if (!a.up && !a.pro_stats) {
+    bool ok = w.ks == 3 ? map_in_3x3(&p.map_a0, a.src0, a.N, a.Hin, a.Win, a.C0, kc, 10, 18) : map_in_1x1(&p.map_a0, a.src0, p.M, a.C0, kc);
+    if (ok && a.src1)
+      ok = w.ks == 3 ? map_in_3x3(&p.map_a1, a.src1, a.N, a.Hin, a.Win, a.C1, kc, 10, 18) : map_in_1x1(&p.map_a1, a.src1, p.M, a.C1, kc);
+    p.tma_in = ok ? 1 : 0;
+  }
+  p.tma_out = map_out(&p.map_out, a.dst, a.N, a.H, a.W, w.Cout, w.ntile, w.ks) ? 1 : 0;
   const int ny = w.Cout / w.ntile;
   if (w.ks == 3) {
     p.tiles_x = (a.W + 7) / 8; p.tiles_y = (a.H + 15) / 16;

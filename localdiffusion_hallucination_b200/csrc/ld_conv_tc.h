@@ -40,4 +40,7 @@ bool conv_tc_supports(const ConvTcW& w, const ConvTcArgs& a);
 // returns number of kernels launched, < 0 on error
 int conv_tc_launch(const ConvTcW& w, const ConvTcArgs& a, cudaStream_t s);
 
+// development aid: device buffer of per-role clock stamps (null unless env LD_CONV_TRACE is set)
+long long* conv_tc_trace();
+
 }  // namespace ld

@@ -1352,6 +1352,18 @@ int ld_debug_conv_time(int kernel, int C0, int C1, int N, int H, int W, int up, 
     *ms_out = ms / (float)iters;
     if (e != cudaSuccess) rc = fail(LD_ERR_CUDA, "conv timing failed: %s", cudaGetErrorString(e));
   }
+  if (conv_tc_trace()) {   // development aid: dump the hand-shake timeline of CTA 0 (last launch)
+    std::vector<long long> tr(4 * 64 * 4);
+    cudaMemcpy(tr.data(), conv_tc_trace(), tr.size() * 8, cudaMemcpyDeviceToHost);
+    long long t0 = 0;
+    for (auto v : tr) if (v && (!t0 || v < t0)) t0 = v;
+    const char* names[4] = {"prod0", "prod1", "mma", "epi"};
+    for (int t = 0; t < 24; ++t)
+      for (int r = 0; r < 4; ++r) {
+        const long long* e = &tr[(r * 64 + t) * 4];
+        if (e[0]) printf("tile %2d %-5s  %8lld %8lld %8lld %8lld\n", t, names[r], e[0] - t0, e[1] ? e[1] - t0 : -1, e[2] ? e[2] - t0 : -1, e[3] ? e[3] - t0 : -1);
+      }
+  }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaFree(tw.w); cudaFree(tw.w32); cudaFree(tw.bias);
   cudaFree(dw); cudaFree(db); cudaFree(a0); cudaFree(a1); cudaFree(ao);
