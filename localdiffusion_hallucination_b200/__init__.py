@@ -2,7 +2,8 @@
 
 Public surface mirrors the reference's `ddpm.py`: `Unet`, `GaussianDiffusion`.
 """
+from .checkpoint import extract_state_dict, load_reference_checkpoint
 from .diffusion import GaussianDiffusion
 from .unet import Unet
 
-__all__ = ["Unet", "GaussianDiffusion"]
+__all__ = ["Unet", "GaussianDiffusion", "load_reference_checkpoint", "extract_state_dict"]

@@ -33,6 +33,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "ld_conv_tc.h"
@@ -741,11 +743,12 @@ bool conv_tc_supports(const ConvTcW& w, const ConvTcArgs& a) {
 
 long long* conv_tc_trace() { return nullptr; }
 
-int conv_tc_launch(const ConvTcW& w, const ConvTcArgs& a, cudaStream_t s) {
-  if (!conv_tc_supports(w, a)) return -1;
+// Kernel parameters (incl. the three encoded tensor maps) are cached per distinct (weights, arguments): plans replay
+// the same launches every timestep and cuTensorMapEncodeTiled is a host-side driver call.
+static bool build_params(const ConvTcW& w, const ConvTcArgs& a, KParams& p) {
   const bool k64 = w.w && a.C0 % 64 == 0 && a.C1 % 64 == 0;
   const int kc = k64 ? 64 : 32;
-  KParams p{};
+  p = KParams{};
   p.src0 = (const __nv_bfloat16*)a.src0; p.src1 = (const __nv_bfloat16*)a.src1; p.C0 = a.C0; p.C1 = a.C1;
   p.N = a.N; p.H = a.H; p.W = a.W; p.Hin = a.Hin; p.Win = a.Win; p.up = a.up;
   p.nchunks = w.Cin / kc;
@@ -766,14 +769,34 @@ int conv_tc_launch(const ConvTcW& w, const ConvTcArgs& a, cudaStream_t s) {
     p.tma_in = ok ? 1 : 0;
   }
   p.tma_out = map_out(&p.map_out, a.dst, a.N, a.H, a.W, w.Cout, w.ntile, w.ks) ? 1 : 0;
-  const int ny = w.Cout / w.ntile;
   if (w.ks == 3) {
     p.tiles_x = (a.W + 7) / 8; p.tiles_y = (a.H + 15) / 16;
     p.ntiles = a.N * p.tiles_x * p.tiles_y;
-    return k64 ? launch_nt<3, 64>(w.ntile, p, ny, s) : launch_nt<3, 32>(w.ntile, p, ny, s);
+  } else {
+    p.tiles_x = 1; p.tiles_y = 1;
+    p.ntiles = (int)((p.M + 127) / 128);
   }
-  p.tiles_x = 1; p.tiles_y = 1;
-  p.ntiles = (int)((p.M + 127) / 128);
+  return k64;
+}
+
+int conv_tc_launch(const ConvTcW& w, const ConvTcArgs& a, cudaStream_t s) {
+  if (!conv_tc_supports(w, a)) return -1;
+  struct Cached { KParams p; bool k64; };
+  static std::unordered_map<std::string, Cached> cache;
+  std::string key(reinterpret_cast<const char*>(&a), sizeof(ConvTcArgs));
+  const void* wk[3] = {w.w, w.w32, w.bias};
+  key.append(reinterpret_cast<const char*>(wk), sizeof wk);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    if (cache.size() > 4096) cache.clear();
+    Cached c;
+    c.k64 = build_params(w, a, c.p);
+    it = cache.emplace(std::move(key), c).first;
+  }
+  KParams p = it->second.p;
+  const bool k64 = it->second.k64;
+  const int ny = w.Cout / w.ntile;
+  if (w.ks == 3) return k64 ? launch_nt<3, 64>(w.ntile, p, ny, s) : launch_nt<3, 32>(w.ntile, p, ny, s);
   return k64 ? launch_nt<1, 64>(w.ntile, p, ny, s) : launch_nt<1, 32>(w.ntile, p, ny, s);
 }
 
