@@ -177,6 +177,10 @@ LD_API int ld_debug_linattn(const float* x, int C, int N, int HW, const float* w
 /* Test hook: tcgen05 flash-style soft-max attention (attend.py:98-113).  qkv: fp32 [N][n][3*heads*32] device
  * (channel = part*hid + h*32 + d, ddpm.py:276-277); out: fp32 [N][n][heads*32]. */
 LD_API int ld_debug_attention(const float* qkv, int N, int n, int heads, float* out, void* stream);
+/* Test hook: tcgen05 7x7 convolution of a single fp32 channel (init_conv, ddpm.py:319).  x: fp32 [N][H][W] device;
+ * w_host [Cout][1][7][7], bias_host [Cout]: host; out: fp32 [N][H][W][Cout] device. */
+LD_API int ld_debug_conv7(const float* x, int N, int H, int W, const float* w_host, const float* bias_host, int Cout,
+                          float* out, void* stream);
 /* Average device time (ms, CUDA events on `stream`) of `iters` launches of one convolution kernel on
  * synthetic operands; used by bench.py for the roofline of the dominant kernel. */
 LD_API int ld_debug_conv_time(int kernel, int C0, int C1, int N, int H, int W, int up, int Cout, int ks,

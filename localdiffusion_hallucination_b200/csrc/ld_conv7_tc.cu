@@ -1,0 +1,225 @@
+// init_conv (ddpm.py:319): 7x7, pad 3, ONE fp32 input channel -> 32..64 bf16 channels, on tcgen05 for sm_100a.
+//
+// The sampler state x_t is fp32 and stays fp32 in HBM; the im2col operand is built on the fly in shared memory:
+//   builders (4 warps, thread = output pixel of a 16 x 8 tile) read the 22 x 14 halo patch of x from a shared
+//   staging buffer, split every tap into bf16 hi + bf16 lo (x = hi + lo to ~2^-17, so the fp32 state is not
+//   rounded to 8 bits on its way into the network) and write their row of the K-major A operand
+//   [K = 64 (49 hi taps + pad) | 64 (49 lo taps + pad)];
+//   one lane issues 8 tcgen05.mma (M = 128 pixels, N = Cout, K = 16) against the resident weights [w | w];
+//   4 epilogue warps add the bias and store bf16 NHWC.  Persistent CTAs, 2 A stages, 2 TMEM accumulators.
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "ld_conv7_tc.h"
+#include "ld_tc_common.cuh"
+
+namespace ld {
+
+using namespace tc;
+
+namespace {
+
+constexpr int kThreads = 9 * 32;     // warps 0-3 builders, 4-7 epilogue, 8 MMA
+constexpr int kMmaWarp = 8;
+constexpr int PH = 22, PW = 14;      // halo patch of a 16 x 8 tile
+constexpr int A_STAGE = 16 * 2048;   // [16 chunks of 8 K][128 rows][16 B]
+
+struct Params {
+  const float* x; const __nv_bfloat16* w; const float* bias; __nv_bfloat16* out;
+  int N, H, W, tiles_x, tiles_y, ntiles;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(kThreads, 2) conv7_tc_kernel(const Params p) {
+  constexpr int W_BYTES = 16 * NT * 16;               // [16 chunks][NT rows][16 B]
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* a_s = smem;                                // 2 stages
+  uint8_t* w_s = a_s + 2 * A_STAGE;
+  float* patch = reinterpret_cast<float*>(w_s + W_BYTES);   // [2][PH*PW] (+ pad)
+  float* bias_s = patch + 2 * 320;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + NT);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  const uint32_t w_full = smem_u32(bars), a_full = w_full + 8, a_empty = a_full + 16, acc_full = a_empty + 16, acc_empty = acc_full + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(a_full + 8 * i, 4); mbar_init(a_empty + 8 * i, 1);
+      mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 128);
+    }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < NT; i += kThreads) bias_s[i] = p.bias ? p.bias[i] : 0.f;
+  if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), 2 * NT);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tpi = p.tiles_x * p.tiles_y;
+
+  if (warp < 4) {
+    // ---------------------------------------------------------------- builders -------------------
+    const int m = threadIdx.x;                         // output pixel of the tile: (m >> 3, m & 7)
+    const int py = m >> 3, px = m & 7;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      const int img = tile / tpi, r = tile - img * tpi;
+      const int ty0 = (r / p.tiles_x) * 16, tx0 = (r % p.tiles_x) * 8;
+      float* pb = patch + s * 320;
+      // stage the halo patch (zero outside the image = the conv's zero padding)
+      const float* ximg = p.x + (size_t)img * p.H * p.W;
+      for (int i = m; i < PH * PW; i += 128) {
+        const int hy = i / PW, hx = i - hy * PW;
+        const int gy = ty0 + hy - 3, gx = tx0 + hx - 3;
+        pb[i] = ((unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W) ? __ldg(ximg + (size_t)gy * p.W + gx) : 0.f;
+      }
+      named_bar(1, 128);                               // patch complete (and the previous tile's readers are done: 2 patch buffers)
+      mbar_wait(a_empty + 8 * s, ((it >> 1) & 1) ^ 1);
+      uint8_t* row = a_s + s * A_STAGE + m * 16;
+      const float* src = pb + py * PW + px;
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {                 // 8 taps per 16-byte chunk; taps 49..63 are zero
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float v[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int tap = c8 * 8 + 2 * j + e;
+            v[e] = tap < 49 ? src[(tap / 7) * PW + (tap % 7)] : 0.f;
+          }
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[0], v[1]);
+          const float2 hf = __bfloat1622float2(h2);
+          hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
+          lo[j] = pack_bf16x2(v[0] - hf.x, v[1] - hf.y);
+        }
+        if (c8 < 7) {                                  // chunk 7 (taps 56..63) is all padding: written once below
+          *reinterpret_cast<uint4*>(row + c8 * 2048) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(row + (8 + c8) * 2048) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      if (it < 2) {                                    // the padding chunks of a stage never change
+        *reinterpret_cast<uint4*>(row + 7 * 2048) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(row + 15 * 2048) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full + 8 * s);
+    }
+  } else if (warp < kMmaWarp) {
+    // ---------------------------------------------------------------- epilogue -------------------
+    const int ew = warp - 4, m = ew * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const int img = tile / tpi, r = tile - img * tpi;
+      const int gy = (r / p.tiles_x) * 16 + (m >> 3), gx = (r % p.tiles_x) * 8 + (m & 7);
+      const bool ok = gy < p.H && gx < p.W;
+      mbar_wait(acc_full + 8 * as, (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * NT);
+      __nv_bfloat16* dst = p.out + (((size_t)img * p.H + gy) * p.W + gx) * NT;
+#pragma unroll
+      for (int j0 = 0; j0 < NT; j0 += 32) {
+        uint32_t rr[32];
+        tmem_ld32(trow + j0, rr);
+        tmem_ld_wait();
+        if (j0 + 32 == NT) { tc_fence_before(); mbar_arrive(acc_empty + 8 * as); }
+        if (ok) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              o[j] = pack_bf16x2(__uint_as_float(rr[8 * c + 2 * j]) + bias_s[j0 + 8 * c + 2 * j],
+                                 __uint_as_float(rr[8 * c + 2 * j + 1]) + bias_s[j0 + 8 * c + 2 * j + 1]);
+            *reinterpret_cast<uint4*>(dst + j0 + 8 * c) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- MMA issue ------------------
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, W_BYTES);
+      bulk_g2s(smem_u32(w_s), p.w, W_BYTES, w_full);
+    }
+    __syncwarp();
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc = make_idesc(128, NT);
+    const uint32_t hi128 = desc_hi(128);
+    const uint32_t a_lo0 = desc_lo(smem_u32(a_s), 2048), b_lo = desc_lo(smem_u32(w_s), NT * 16);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      mbar_wait(acc_empty + 8 * s, ((it >> 1) & 1) ^ 1);
+      mbar_wait(a_full + 8 * s, (it >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_lo = a_lo0 + (uint32_t)(s * (A_STAGE >> 4));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // K = 128 = 8 x 16
+          umma_bf16_lh(tmem_base + (uint32_t)(s * NT), a_lo + (uint32_t)(2 * k * 128), hi128, b_lo + (uint32_t)(2 * k * NT), hi128, idesc,
+                       k > 0 ? 1u : 0u);
+        umma_commit(a_empty + 8 * s);
+        umma_commit(acc_full + 8 * s);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 2 * NT);
+}
+
+template <int NT>
+constexpr int smem_bytes() { return 2 * A_STAGE + 16 * NT * 16 + (2 * 320 + NT) * 4 + 9 * 8 + 16; }
+
+int g_sms = 0;
+
+}  // namespace
+
+int conv7_tc_pack(const float* w_tap_cout, const float* bias, int Cout, Conv7TcW* out) {
+  out->ready = false;
+  if (Cout != 32 && Cout != 64) return 0;
+  // B operand [Cout rows][K = 128]: K index k < 64 -> tap k (hi part), k >= 64 -> tap k - 64 (lo part); same weights
+  std::vector<__nv_bfloat16> pk((size_t)16 * Cout * 8);
+  for (int c8 = 0; c8 < 16; ++c8)
+    for (int n = 0; n < Cout; ++n)
+      for (int e = 0; e < 8; ++e) {
+        const int tap = (c8 & 7) * 8 + e;
+        pk[((size_t)c8 * Cout + n) * 8 + e] = __float2bfloat16_rn(tap < 49 ? w_tap_cout[(size_t)tap * Cout + n] : 0.f);
+      }
+  if (cudaMalloc(&out->w, pk.size() * 2) != cudaSuccess) return -1;
+  if (cudaMemcpy(out->w, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+  out->bias = nullptr;
+  if (bias) {
+    if (cudaMalloc(&out->bias, Cout * 4) != cudaSuccess) return -1;
+    if (cudaMemcpy(out->bias, bias, Cout * 4, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+  }
+  out->Cout = Cout;
+  if (Cout == 32) { if (cudaFuncSetAttribute(conv7_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<32>()) != cudaSuccess) return -1; }
+  else { if (cudaFuncSetAttribute(conv7_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<64>()) != cudaSuccess) return -1; }
+  out->ready = true;
+  return 0;
+}
+
+void conv7_tc_free(Conv7TcW* w) { cudaFree(w->w); cudaFree(w->bias); *w = Conv7TcW(); }
+
+int conv7_tc_launch(const Conv7TcW& w, const float* x, void* out, int N, int H, int W, cudaStream_t s) {
+  if (!w.ready) return -1;
+  if (!g_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev); }
+  Params p{x, (const __nv_bfloat16*)w.w, w.bias, (__nv_bfloat16*)out, N, H, W, (W + 7) / 8, (H + 15) / 16, 0};
+  p.ntiles = N * p.tiles_x * p.tiles_y;
+  int grid = 2 * g_sms;
+  if (grid > p.ntiles) grid = p.ntiles;
+  if (w.Cout == 32) conv7_tc_kernel<32><<<grid, kThreads, smem_bytes<32>(), s>>>(p);
+  else conv7_tc_kernel<64><<<grid, kThreads, smem_bytes<64>(), s>>>(p);
+  return 1;
+}
+
+}  // namespace ld

@@ -21,6 +21,7 @@
 #include "ld_kernels.h"
 #include "ld_linattn_tc.h"
 #include "ld_attn_tc.h"
+#include "ld_conv7_tc.h"
 
 namespace ld {
 
@@ -103,6 +104,7 @@ struct Engine {
   // model
   std::vector<int> dims;
   ConvW init_conv, final_conv;
+  Conv7TcW init_tc;
   float *tw1, *tb1, *tw2, *tb2, *film_w, *film_b;
   int film_total = 0;
   std::vector<ResW> res;                  // all resnet blocks by name index
@@ -142,6 +144,7 @@ struct Engine {
     staged.clear();
     for (void* p : dev_allocs) cudaFree(p);
     for (auto& kv : attn) linattn_tc_free(&kv.second.la);
+    conv7_tc_free(&init_tc);
     if (la_flag) cudaFree(la_flag);
     if (coef1) cudaFree(coef1);
     if (coef2) cudaFree(coef2);
@@ -349,6 +352,14 @@ static int finalize(Engine& E) {
   if (E.d.cond_mode == LD_COND_MRI) { if ((rc = pack_cond(E, "cond_model.mid_conv.0"))) return rc; E.cond_C = 256; E.cond_div = 8; }
   else { E.cond_C = 128; E.cond_div = 4; }
   if ((rc = pack_conv(E, "init_conv", true, false, &E.init_conv))) return rc;
+  if (E.use_tc && E.d.channels == 1) {   // 7x7 init conv on tensor cores: weights [Cout][1][7][7] -> [tap][Cout]
+    const WSpec& w = W(E, "init_conv.weight");
+    const int co = (int)w.shape[0];
+    std::vector<float> wt((size_t)49 * co);
+    for (int o = 0; o < co; ++o)
+      for (int t = 0; t < 49; ++t) wt[(size_t)t * co + o] = w.host[(size_t)o * 49 + t];
+    if (conv7_tc_pack(wt.data(), W(E, "init_conv.bias").host.data(), co, &E.init_tc)) return fail(LD_ERR_CUDA, "conv7_tc_pack failed");
+  }
   if ((rc = pack_conv(E, "final_conv", true, false, &E.final_conv))) return rc;
   if ((rc = upload_key(E, "time_mlp.1.weight", &E.tw1))) return rc;
   if ((rc = upload_key(E, "time_mlp.1.bias", &E.tb1))) return rc;
@@ -695,7 +706,9 @@ static int build_unet_plan(Engine& E, Plan& P, int N, int H, int W, const float*
   Ten h = B.act(N, H, W, E.d.init_dim);
   {
     const ConvW* c = &E.init_conv; Ten hh = h;
-    B.op([=](cudaStream_t s) { return launch_conv_c1(x, c->w, c->bias, hh.p, N, H, W, c->Cout, 7, bf, s); });
+    const Conv7TcW* c7 = &E.init_tc;
+    if (E.use_tc && c7->ready) B.op([=](cudaStream_t s) { return conv7_tc_launch(*c7, x, hh.p, N, H, W, s); });
+    else B.op([=](cudaStream_t s) { return launch_conv_c1(x, c->w, c->bias, hh.p, N, H, W, c->Cout, 7, bf, s); });
   }
   B.tag("init_conv", h);
   Ten r = h;  // ddpm.py:414 (clone not needed: h is never written again)
@@ -1310,6 +1323,27 @@ int ld_debug_attention(const float* qkv, int N, int n, int heads, float* out, vo
   cudaError_t e = cudaStreamSynchronize(s);
   cudaFree(qb); cudaFree(ob); cudaFree(sc);
   if (e != cudaSuccess) return fail(LD_ERR_CUDA, "debug attention failed: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+// tcgen05 7x7 single-channel convolution (init_conv) test hook.  x: fp32 [N][H][W] device; w_host [Cout][1][7][7]; out fp32 NHWC.
+int ld_debug_conv7(const float* x, int N, int H, int W, const float* w_host, const float* bias_host, int Cout, float* out, void* stream) {
+  if (ld_device_count() == 0) return fail(LD_ERR_NO_DEVICE, "no sm_100 CUDA device is available (there is no CPU fallback)");
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<float> wt((size_t)49 * Cout);
+  for (int o = 0; o < Cout; ++o)
+    for (int t = 0; t < 49; ++t) wt[(size_t)t * Cout + o] = w_host[(size_t)o * 49 + t];
+  Conv7TcW w;
+  if (conv7_tc_pack(wt.data(), bias_host, Cout, &w) || !w.ready) return fail(LD_ERR_INVALID, "conv7_tc_pack: unsupported width");
+  const size_t n = (size_t)N * H * W * Cout;
+  void* ob = nullptr;
+  CK(cudaMalloc(&ob, n * 2));
+  int rc = conv7_tc_launch(w, x, ob, N, H, W, s) < 0 ? fail(LD_ERR_INVALID, "conv7_tc_launch failed") : 0;
+  launch_convert(ob, true, out, false, (long long)n, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  cudaFree(ob);
+  conv7_tc_free(&w);
+  if (e != cudaSuccess) return fail(LD_ERR_CUDA, "debug conv7 failed: %s", cudaGetErrorString(e));
   return rc;
 }
 

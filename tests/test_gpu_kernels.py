@@ -178,3 +178,20 @@ def test_flash_attention_matches_torch(N, n, heads):
     rc = lib.ld_debug_attention(qkv.to(dev).data_ptr(), N, n, heads, out.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
     _lib.check(rc)
     assert util.rel_err(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("N,H,W,Cout", [(2, 32, 32, 32), (1, 20, 28, 32), (3, 64, 64, 64), (1, 256, 256, 32)])
+def test_init_conv7_matches_torch(N, H, W, Cout):
+    """7x7 single-channel init_conv (ddpm.py:319) on tcgen05: the fp32 state enters as bf16 hi + lo, weights as bf16."""
+    lib = _lib.lib()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(N + H + W + Cout)
+    x = torch.randn(N, H, W, generator=g) * 2.0
+    w = torch.randn(Cout, 1, 7, 7, generator=g) / 7.0
+    b = torch.randn(Cout, generator=g)
+    out = torch.empty(N, H, W, Cout, device=dev)
+    rc = lib.ld_debug_conv7(x.to(dev).data_ptr(), N, H, W, w.contiguous().data_ptr(), b.data_ptr(), Cout, out.data_ptr(),
+                            C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc)
+    ref = F.conv2d(x[:, None].double(), w.bfloat16().double(), b.double(), padding=3).permute(0, 2, 3, 1)
+    assert util.rel_err(out, ref) < 4e-3   # only the bf16 output rounding (+ 2^-17 of the hi/lo split) remains
