@@ -569,12 +569,12 @@ struct Builder {
       Ten mn = alloc(x.N, 1, 1, 128 * x.C, 2);
       LinAttnTcArgs la;
       la.x = x.p; la.out = out.p; la.N = x.N; la.HW = x.H * x.W; la.Mn = mn.p; la.flag = E.la_flag;
-      const size_t ctx_off = (size_t)zalloc((size_t)x.N * 128 * 32 * 4), ks_off = (size_t)zalloc((size_t)x.N * 128 * 4);
+      const size_t ctx_off = (size_t)zalloc((size_t)x.N * 128 * x.C * 4), ks_off = (size_t)zalloc((size_t)x.N * 128 * 4);
       const LinAttnTcW* w = &a.la;
       Plan* pp = &P;
       op([pp, la, w, ctx_off, ks_off](cudaStream_t s) {
         LinAttnTcArgs q = la;
-        q.ctx = (float*)((char*)pp->zero_arena + ctx_off);
+        q.Z = (float*)((char*)pp->zero_arena + ctx_off);
         q.ksum = (float*)((char*)pp->zero_arena + ks_off);
         return linattn_tc_launch(*w, q, s);
       });
@@ -1293,10 +1293,10 @@ int ld_debug_linattn(const float* x, int C, int N, int HW, const float* wqkv, co
   const size_t n = (size_t)N * HW * C;
   void *xb = nullptr, *ob = nullptr, *mn = nullptr; float *ctx = nullptr, *ks = nullptr; unsigned int* flag = nullptr;
   CK(cudaMalloc(&xb, n * 2)); CK(cudaMalloc(&ob, n * 2)); CK(cudaMalloc(&mn, (size_t)N * 128 * C * 2));
-  CK(cudaMalloc(&ctx, (size_t)N * 128 * 32 * 4)); CK(cudaMalloc(&ks, (size_t)N * 128 * 4)); CK(cudaMalloc(&flag, 4));
-  CK(cudaMemsetAsync(ctx, 0, (size_t)N * 128 * 32 * 4, s)); CK(cudaMemsetAsync(ks, 0, (size_t)N * 128 * 4, s)); CK(cudaMemsetAsync(flag, 0, 4, s));
+  CK(cudaMalloc(&ctx, (size_t)N * 128 * C * 4)); CK(cudaMalloc(&ks, (size_t)N * 128 * 4)); CK(cudaMalloc(&flag, 4));
+  CK(cudaMemsetAsync(ctx, 0, (size_t)N * 128 * C * 4, s)); CK(cudaMemsetAsync(ks, 0, (size_t)N * 128 * 4, s)); CK(cudaMemsetAsync(flag, 0, 4, s));
   launch_convert(x, false, xb, true, (long long)n, s);
-  LinAttnTcArgs a; a.x = xb; a.out = ob; a.N = N; a.HW = HW; a.ctx = ctx; a.ksum = ks; a.Mn = mn; a.flag = flag;
+  LinAttnTcArgs a; a.x = xb; a.out = ob; a.N = N; a.HW = HW; a.Z = ctx; a.ksum = ks; a.Mn = mn; a.flag = flag;
   int rc = linattn_tc_launch(w, a, s) < 0 ? fail(LD_ERR_INVALID, "linattn_tc_launch failed") : 0;
   launch_convert(ob, true, out, false, (long long)n, s);
   unsigned int under = 0;

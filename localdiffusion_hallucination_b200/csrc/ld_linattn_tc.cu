@@ -3,15 +3,18 @@
 // The reference materialises qkv = to_qkv(RMSNorm(x)) ([384, H*W] per image, 768 B per pixel in bf16), two
 // soft-maxes and two einsums.  Here x is read twice and the result written once; qkv never leaves the SM:
 //
-//   pass A  `la_ctx_kernel`   per 64-pixel half tile:
-//        producers   x -> x/|x| (RMSNorm, g*sqrt(C) folded into the weights) -> bf16 -> smem  [64 px][C]
-//        MMA1        K^T[128 (h,d)][64 px], V^T[128 (h,e)][64 px] = W'_{k,v} . xhat^T      (tcgen05, TMEM)
-//        transform   thread = row: ek = exp(k - bound_d) -> bf16 -> smem P[(h,d)][px];  v -> bf16 -> smem V[(h,e)][px]
-//        MMA2        CTX[128 (h,d)][128 (h',e)] += P . V^T  accumulated in TMEM over all tiles of the CTA
-//        end         diagonal (h == h') blocks and the row sums of ek are added to ctx[n], ksum[n]
-//      soft-max over the pixel axis is shift invariant; instead of a separate max pass the shift is the
+//   pass A  `la_ctx_kernel`   per 64-pixel half tile (two transform warp-groups ping-pong on alternate half tiles):
+//        producers   x -> x/|x| (RMSNorm, g*sqrt(C) folded into the weights) -> bf16 -> smem, as [64 px][C] AND [C][64 px]
+//        MMA1        K^T[128 (h,d)][64 px] = W'_k . xhat^T                                   (tcgen05, TMEM)
+//        transform   thread = row (h,d): ek = exp(k - bound_d) -> bf16 -> smem P[(h,d)][px], row sums in registers
+//        MMA2        Z[128 (h,d)][C] += P . xhat     accumulated in TMEM over all tiles of the CTA
+//        end         Z and the row sums of ek are added to Z[n], ksum[n]
+//      v = W'_v xhat is linear, so context[d][e] = sum_p ek[p,d] v[p,e] = sum_c W'_v[e,c] Z[d][c]: v is never formed
+//      per pixel (half the TMEM read-out, a 4x smaller second MMA), W'_v moves into the per-image fold.
+//      Soft-max over the pixel axis is shift invariant; instead of a separate max pass the shift is the
 //      analytic bound |k_d| <= |W'_k[d,:]| (|xhat| = 1).  `la_fold_kernel` raises a flag if a row sum underflowed.
-//   fold   `la_fold_kernel`   Mn[n][c][(h,d)] = 32^-0.5 * sum_e Wout[c][(h,e)] ctx[n][h][d][e] / ksum[n][(h,d)]  (bf16, UMMA layout)
+//   fold   `la_fold_kernel`   Mn[n][c'][(h,d)] = 32^-0.5 / ksum[n][(h,d)] * sum_c U[h][c'][c] Z[n][(h,d)][c],
+//                             U[h] = Wout[:, h] . W'_v[h] (C x C, constant)                  (bf16, UMMA layout)
 //   pass B  `la_out_kernel`   per 128-pixel tile (two transform warp-groups ping-pong on alternate tiles):
 //        MMA1        Q[128 px][128 (h,d)] = xhat . W'_q^T
 //        transform   thread = pixel: per-head soft-max over d -> bf16 -> smem P[px][(h,d)]
@@ -44,9 +47,9 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 struct CtxParams {
   const __nv_bfloat16* x;   // [N][HW][C]
-  const __nv_bfloat16* wkv; // packed [2][C/8][128][8]
+  const __nv_bfloat16* wk;  // packed [C/8][128][8]
   const float* kb2;         // [128] log2(e) * bound of |k_d|
-  float* ctx;               // [N][4][32][32]
+  float* Z;                 // [N][128 (h,d)][C]
   float* ksum;              // [N][128]
   int HW, slices;
 };
@@ -77,6 +80,9 @@ struct XStage {
       if (px0 + p < HW) v[k] = __ldg(reinterpret_cast<const uint4*>(ximg + (size_t)(px0 + p) * C + c8 * 8));
     }
   }
+  // WITH_T: also write the transposed image [C rows][ROWS pixels] (K-major over pixels: 8-pixel chunk kc at
+  // kc*C*16 + c*16 + (p%8)*2) right behind the first one -- the B operand of Z += P . xhat
+  template <bool WITH_T>
   __device__ __forceinline__ void store(uint8_t* stage, int tid) const {
     const int c8 = tid % LP;
 #pragma unroll
@@ -98,12 +104,17 @@ struct XStage {
 #pragma unroll
       for (int j = 0; j < 4; ++j) o4[j] = pack_bf16x2(f[2 * j] * inv, f[2 * j + 1] * inv);
       *reinterpret_cast<uint4*>(stage + (size_t)c8 * (ROWS * 16) + p * 16) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+      if (WITH_T) {
+        uint8_t* t = stage + ROWS * C * 2 + (size_t)(p >> 3) * (C * 16) + (size_t)(c8 * 8) * 16 + (p & 7) * 2;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) *reinterpret_cast<uint16_t*>(t + e * 16) = (uint16_t)(o4[e >> 1] >> (16 * (e & 1)));
+      }
     }
   }
 };
 
 // the producer loop shared by both passes: stage i covers pixels [(first + i) * ROWS, +ROWS) of one image
-template <int C, int ROWS, int XS>
+template <int C, int ROWS, int XS, bool WITH_T>
 __device__ __forceinline__ void produce_x(const __nv_bfloat16* __restrict__ ximg, int first, int count, int HW, uint8_t* x_s,
                                           int x_stage_bytes, uint32_t x_full, uint32_t x_empty, int tid, int lane) {
   using X = XStage<C, ROWS>;
@@ -118,7 +129,7 @@ __device__ __forceinline__ void produce_x(const __nv_bfloat16* __restrict__ ximg
       if (i < count) {
         const int s = i % XS;
         mbar_wait(x_empty + 8 * s, ((i / XS) & 1) ^ 1);
-        fifo[d].store(x_s + (size_t)s * x_stage_bytes, tid);
+        fifo[d].template store<WITH_T>(x_s + (size_t)s * x_stage_bytes, tid);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(x_full + 8 * s);
@@ -128,17 +139,74 @@ __device__ __forceinline__ void produce_x(const __nv_bfloat16* __restrict__ ximg
   }
 }
 
+// Same producer fed by the bulk-copy engine: a stage of x is ROWS*C*2 contiguous bytes in global memory, so one lane
+// issues cp.async.bulk copies RS stages ahead into a raw ring (no registers, no scoreboards tied up: the register
+// FIFO above cannot keep more than ~6 load batches in flight per warp), and the four warps normalise smem -> smem.
+template <int C, int ROWS, int XS, int RS>
+__device__ __forceinline__ void produce_x_raw(const __nv_bfloat16* __restrict__ ximg, int first, int count, int HW, uint8_t* x_s,
+                                              int x_stage_bytes, uint32_t x_full, uint32_t x_empty, uint8_t* raw_s, uint32_t raw_full,
+                                              uint32_t raw_empty, int tid, int lane) {
+  constexpr int LP = C / 8, ITEMS = ROWS * LP / 128, RAWB = ROWS * C * 2;
+  const int c8 = tid % LP;
+  auto issue = [&](int j) {
+    const int slot = j % RS;
+    mbar_wait(raw_empty + 8 * slot, ((j / RS) & 1) ^ 1);
+    const int px0 = (first + j) * ROWS;
+    const int valid = HW - px0 < ROWS ? HW - px0 : ROWS;
+    const uint32_t bytes = (uint32_t)valid * C * 2;
+    mbar_arrive_expect_tx(raw_full + 8 * slot, bytes);
+    bulk_g2s(smem_u32(raw_s + (size_t)slot * RAWB), ximg + (size_t)px0 * C, bytes, raw_full + 8 * slot);
+  };
+  if (tid == 0)
+    for (int j = 0; j < RS - 1 && j < count; ++j) issue(j);
+  for (int i = 0; i < count; ++i) {
+    if (tid == 0 && i + RS - 1 < count) issue(i + RS - 1);
+    const int slot = i % RS, s = i % XS;
+    const int valid = HW - (first + i) * ROWS;               // pixels of this stage that exist (may exceed ROWS)
+    mbar_wait(raw_full + 8 * slot, (i / RS) & 1);
+    mbar_wait(x_empty + 8 * s, ((i / XS) & 1) ^ 1);
+    const uint8_t* raw = raw_s + (size_t)slot * RAWB;
+    uint8_t* stage = x_s + (size_t)s * x_stage_bytes;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+      const int p = (k * 128 + tid) / LP;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (p < valid) v = *reinterpret_cast<const uint4*>(raw + (size_t)p * (C * 2) + c8 * 16);
+      const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+      float f[8];
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = unpack_bf16x2(in[j]);
+        f[2 * j] = t.x; f[2 * j + 1] = t.y;
+        ss = fmaf(t.x, t.x, ss); ss = fmaf(t.y, t.y, ss);
+      }
+#pragma unroll
+      for (int o = 1; o < LP; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float inv = rsqrtf(fmaxf(ss, 1e-24f));           // 1 / max(|x|, 1e-12): F.normalize(x, dim=1) (ddpm.py:132)
+      uint32_t o4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o4[j] = pack_bf16x2(f[2 * j] * inv, f[2 * j + 1] * inv);
+      *reinterpret_cast<uint4*>(stage + (size_t)c8 * (ROWS * 16) + p * 16) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) { mbar_arrive(x_full + 8 * s); mbar_arrive(raw_empty + 8 * slot); }
+  }
+}
+
 // ================================================================================================
 // pass A: context
 // ================================================================================================
 template <int C>
 struct CtxCfg {
-  static constexpr int XS = 3;
-  static constexpr int X_STAGE = 64 * C * 2;
-  static constexpr int W_BYTES = 2 * 128 * C * 2;
-  static constexpr int PV_BYTES = 128 * 64 * 2;       // one P or V buffer
-  static constexpr int SMEM_MIN = W_BYTES + XS * X_STAGE + 4 * PV_BYTES + 128 * 4 + 16 * 8 + 16;
-  static constexpr int SMEM = SMEM_MIN > 117 * 1024 ? SMEM_MIN : 117 * 1024;   // one CTA per SM: it owns all 512 TMEM columns
+  static constexpr int XS = C >= 128 ? 6 : 8;         // xhat stages: released only after MMA2, ~4 half tiles after MMA1
+  static constexpr int X_STAGE = 64 * C * 2;          // xhat [C/8][64 px][16 B]: K-major for MMA1, MN-major for MMA2
+  static constexpr int W_BYTES = 128 * C * 2;
+  static constexpr int P_BYTES = 128 * 64 * 2;        // one P buffer
+  static constexpr int NB = 4;                        // K^T (TMEM) and P (smem) buffers: two per transform warp-group
+  static constexpr int RS = C >= 128 ? 0 : 4;         // raw x ring fed by cp.async.bulk (C = 128: register FIFO, smem is full)
+  static constexpr int SMEM = W_BYTES + XS * X_STAGE + NB * P_BYTES + RS * X_STAGE + 128 * 4 + 48 * 8 + 16;
 };
 
 template <int C>
@@ -147,12 +215,14 @@ __global__ void __launch_bounds__(kThreads, 1) la_ctx_kernel(const CtxParams p) 
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* w_s = smem;
   uint8_t* x_s = w_s + K::W_BYTES;
-  uint8_t* pv_s = x_s + K::XS * K::X_STAGE;           // [buf][P | V]
-  float* kb_s = reinterpret_cast<float*>(pv_s + 4 * K::PV_BYTES);
+  uint8_t* p_s = x_s + K::XS * K::X_STAGE;            // [buffer][128 rows (h,d)][64 px]
+  uint8_t* raw_s = p_s + K::NB * K::P_BYTES;
+  float* kb_s = reinterpret_cast<float*>(raw_s + K::RS * K::X_STAGE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(kb_s + 128);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-  const uint32_t w_full = smem_u32(bars), x_full = w_full + 8, x_empty = x_full + 8 * K::XS, d1_full = x_empty + 8 * K::XS,
-                 d1_empty = d1_full + 16, pv_full = d1_empty + 16, pv_empty = pv_full + 16, d2_full = pv_empty + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 48);
+  const uint32_t w_full = smem_u32(bars), x_full = w_full + 8, x_empty = x_full + 64, d1_full = x_empty + 64,
+                 d1_empty = d1_full + 32, p_full = d1_empty + 32, p_empty = p_full + 32, z_full = p_empty + 32,
+                 raw_full = z_full + 8, raw_empty = raw_full + 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.y;
   const int HT = (p.HW + 63) / 64;
@@ -162,11 +232,12 @@ __global__ void __launch_bounds__(kThreads, 1) la_ctx_kernel(const CtxParams p) 
   if (threadIdx.x == 0) {
     mbar_init(w_full, 1);
     for (int i = 0; i < K::XS; ++i) { mbar_init(x_full + 8 * i, 4); mbar_init(x_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(d1_full + 8 * i, 1); mbar_init(d1_empty + 8 * i, 256);
-      mbar_init(pv_full + 8 * i, 256); mbar_init(pv_empty + 8 * i, 1);
+    for (int i = 0; i < K::NB; ++i) {
+      mbar_init(d1_full + 8 * i, 1); mbar_init(d1_empty + 8 * i, 128);
+      mbar_init(p_full + 8 * i, 128); mbar_init(p_empty + 8 * i, 1);
     }
-    mbar_init(d2_full, 1);
+    mbar_init(z_full, 1);
+    for (int i = 0; i < K::RS; ++i) { mbar_init(raw_full + 8 * i, 1); mbar_init(raw_empty + 8 * i, 4); }
     fence_barrier_init();
   }
   if (threadIdx.x < 128) kb_s[threadIdx.x] = p.kb2[threadIdx.x];
@@ -175,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) la_ctx_kernel(const CtxParams p) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: D1 buffer b: K^T at b*128, V^T at b*128 + 64;  CTX at 256..383
+  // TMEM columns: K^T buffer b at b*64 (64 pixels each);  Z at 256 .. 256+C
   if (nh <= 0) {
     if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
     return;
@@ -184,113 +255,115 @@ __global__ void __launch_bounds__(kThreads, 1) la_ctx_kernel(const CtxParams p) 
   if (warp < 4) {
     // ---------------------------------------------------------------- producers ------------------
     const __nv_bfloat16* ximg = p.x + (size_t)n * p.HW * C;
-    produce_x<C, 64, K::XS>(ximg, h0, nh, p.HW, x_s, K::X_STAGE, x_full, x_empty, threadIdx.x, lane);
+    if constexpr (K::RS > 0)
+      produce_x_raw<C, 64, K::XS, (K::RS > 0 ? K::RS : 1)>(ximg, h0, nh, p.HW, x_s, K::X_STAGE, x_full, x_empty, raw_s, raw_full, raw_empty,
+                                                          threadIdx.x, lane);
+    else
+      produce_x<C, 64, K::XS, false>(ximg, h0, nh, p.HW, x_s, K::X_STAGE, x_full, x_empty, threadIdx.x, lane);
   } else if (warp == kMmaWarp) {
     // ---------------------------------------------------------------- MMA issue ------------------
-    // the whole warp runs the loop (barrier waits), one elected lane issues tcgen05.mma / commit
+    // The whole warp runs the loop (barrier waits), one elected lane issues tcgen05.mma / commit.  MMA1 runs NB
+    // half tiles ahead of MMA2, so a transform warp-group always finds its next K^T tile ready.
     if (lane == 0) {
       mbar_arrive_expect_tx(w_full, K::W_BYTES);
-      bulk_g2s(smem_u32(w_s), p.wkv, K::W_BYTES, w_full);
+      bulk_g2s(smem_u32(w_s), p.wk, K::W_BYTES, w_full);
     }
     __syncwarp();
     mbar_wait(w_full, 0);
     tc_fence_after();
-    constexpr uint32_t idesc1 = make_idesc(128, 64), idesc2 = make_idesc(128, 128);
-    const uint32_t hi128 = desc_hi(128);
-    const uint32_t w_lo = desc_lo(smem_u32(w_s), 2048), x_lo0 = desc_lo(smem_u32(x_s), 1024), pv_lo0 = desc_lo(smem_u32(pv_s), 2048);
-    auto mma2 = [&](int j) {
-      const int b = j & 1;
-      mbar_wait(pv_full + 8 * b, (j >> 1) & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t p_lo = pv_lo0 + (uint32_t)(b * 2 * (K::PV_BYTES >> 4)), v_lo = p_lo + (K::PV_BYTES >> 4);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)   // K = 64 pixels = 4 x 16
-          umma_bf16_lh(tmem_base + 256, p_lo + (uint32_t)(2 * k * 128), hi128, v_lo + (uint32_t)(2 * k * 128), hi128, idesc2,
-                       (j > 0 || k > 0) ? 1u : 0u);
-        umma_commit(pv_empty + 8 * b);
-      }
-      __syncwarp();
-    };
-    for (int i = 0; i < nh; ++i) {
-      const int s = i % K::XS, b = i & 1;
+    // MMA2 reads xhat as an MN-major B operand (N = channels contiguous in 16-byte groups, K = pixels at 16 B stride):
+    // the same shared-memory image MMA1 reads K-major, no transposed copy.  idesc bit 16 = B is MN-major.
+    constexpr uint32_t idesc1 = make_idesc(128, 64), idesc2 = make_idesc(128, C) | (1u << 16);
+    const uint32_t hi128 = desc_hi(128), hi_xt = desc_hi(64 * 16);
+    const uint32_t w_lo = desc_lo(smem_u32(w_s), 2048), x_lo0 = desc_lo(smem_u32(x_s), 1024), xt_lo0 = desc_lo(smem_u32(x_s), 128),
+                   p_lo0 = desc_lo(smem_u32(p_s), 2048);
+    auto mma1 = [&](int i) {            // K^T(i) = W'_k . xhat(i)^T
+      const int s = i % K::XS, b = i & (K::NB - 1);
       mbar_wait(x_full + 8 * s, (i / K::XS) & 1);
-      mbar_wait(d1_empty + 8 * b, ((i >> 1) & 1) ^ 1);
+      mbar_wait(d1_empty + 8 * b, ((i >> 2) & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t x_lo = x_lo0 + (uint32_t)(s * (K::X_STAGE >> 4));
 #pragma unroll
-        for (int half = 0; half < 2; ++half)          // K^T rows, then V^T rows
-#pragma unroll
-          for (int k = 0; k < C / 16; ++k)
-            umma_bf16_lh(tmem_base + (uint32_t)(b * 128 + half * 64), w_lo + (uint32_t)(half * (C * 16) + 2 * k * 128), hi128,
-                         x_lo + (uint32_t)(2 * k * 64), hi128, idesc1, k > 0 ? 1u : 0u);
-        umma_commit(x_empty + 8 * s);
+        for (int k = 0; k < C / 16; ++k)
+          umma_bf16_lh(tmem_base + (uint32_t)(b * 64), w_lo + (uint32_t)(2 * k * 128), hi128, x_lo + (uint32_t)(2 * k * 64), hi128, idesc1,
+                       k > 0 ? 1u : 0u);
         umma_commit(d1_full + 8 * b);
       }
       __syncwarp();
-      if (i >= 1) mma2(i - 1);
+    };
+    for (int i = 0; i < K::NB && i < nh; ++i) mma1(i);
+    for (int j = 0; j < nh; ++j) {      // Z += P(j) . xhat(j)
+      const int b = j & (K::NB - 1), sj = j % K::XS;
+      mbar_wait(p_full + 8 * b, (j >> 2) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t p_lo = p_lo0 + (uint32_t)(b * (K::P_BYTES >> 4)), xt_lo = xt_lo0 + (uint32_t)(sj * (K::X_STAGE >> 4));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // K = 64 pixels = 4 x 16
+          umma_bf16_lh(tmem_base + 256u, p_lo + (uint32_t)(2 * k * 128), hi128, xt_lo + (uint32_t)(k * 16), hi_xt, idesc2,
+                       (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(p_empty + 8 * b);
+        umma_commit(x_empty + 8 * sj);
+      }
+      __syncwarp();
+      if (j + K::NB < nh) mma1(j + K::NB);
     }
-    mma2(nh - 1);
-    if (elect_one()) umma_commit(d2_full);
+    if (elect_one()) umma_commit(z_full);
     __syncwarp();
   } else {
     // ---------------------------------------------------------------- transform ------------------
-    const int q = warp & 3, hsel = (warp - kXfWarp0) >> 2;   // TMEM lane quarter, pixel-column half
-    const int r = q * 32 + lane;                             // row: (h,d) for K^T, (h,e) for V^T
+    const int q = warp & 3, g = (warp - kXfWarp0) >> 2;      // TMEM lane quarter, warp-group (alternate half tiles)
+    const int r = q * 32 + lane;                             // row (h,d)
     const float mb = kb_s[r];
     float ksum = 0.f;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int i = 0; i < nh; ++i) {
-      const int b = i & 1;
-      const int nvalid = p.HW - (h0 + i) * 64 - hsel * 32;   // valid pixel columns of my 32
-      mbar_wait(d1_full + 8 * b, (i >> 1) & 1);
+    for (int i = g; i < nh; i += 2) {
+      const int b = i & (K::NB - 1);
+      const uint32_t par = (uint32_t)(i >> 2) & 1u;
+      const int nvalid = p.HW - (h0 + i) * 64;               // valid pixel columns of this half tile
+      uint8_t* pbuf = p_s + (size_t)b * K::P_BYTES + r * 16;
+      mbar_wait(d1_full + 8 * b, par);
       tc_fence_after();
-      uint32_t kr[32], vr[32];
-      tmem_ld32(lane_base + (uint32_t)(b * 128 + hsel * 32), kr);
-      tmem_ld32(lane_base + (uint32_t)(b * 128 + 64 + hsel * 32), vr);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(d1_empty + 8 * b);
-      uint32_t pk[16], pv[16];
+      mbar_wait(p_empty + 8 * b, par ^ 1);                   // MMA2 of half tile i - 4 has consumed this P buffer
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float e0 = ex2_approx(fmaf(__uint_as_float(kr[2 * j]), kLog2e, -mb));
-        const float e1 = ex2_approx(fmaf(__uint_as_float(kr[2 * j + 1]), kLog2e, -mb));
-        pk[j] = pack_bf16x2(e0, e1);
-        ksum += e0 + e1;
-        pv[j] = pack_bf16x2(__uint_as_float(vr[2 * j]), __uint_as_float(vr[2 * j + 1]));
-      }
-      if (nvalid < 32) {   // ragged last tile of the image: pixels past the end carry no weight
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t kr[32];
+        tmem_ld32(lane_base + (uint32_t)(b * 64 + c0), kr);
+        tmem_ld_wait();
+        if (c0 == 32) { tc_fence_before(); mbar_arrive(d1_empty + 8 * b); }
+        uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float2 e = unpack_bf16x2(pk[j]);
-          const float e0 = 2 * j < nvalid ? e.x : 0.f, e1 = 2 * j + 1 < nvalid ? e.y : 0.f;
-          ksum -= (e.x - e0) + (e.y - e1);
+          float e0 = ex2_approx(fmaf(__uint_as_float(kr[2 * j]), kLog2e, -mb));
+          float e1 = ex2_approx(fmaf(__uint_as_float(kr[2 * j + 1]), kLog2e, -mb));
+          if (nvalid < 64) {     // ragged last tile of the image: pixels past the end carry no weight
+            if (c0 + 2 * j >= nvalid) e0 = 0.f;
+            if (c0 + 2 * j + 1 >= nvalid) e1 = 0.f;
+          }
           pk[j] = pack_bf16x2(e0, e1);
+          ksum += e0 + e1;
         }
-      }
-      mbar_wait(pv_empty + 8 * b, ((i >> 1) & 1) ^ 1);
-      uint8_t* pbuf = pv_s + (size_t)b * 2 * K::PV_BYTES;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {   // 4 chunks of 8 pixels; chunk index along K = hsel*4 + c
-        const size_t off = (size_t)(hsel * 4 + c) * 2048 + r * 16;
-        *reinterpret_cast<uint4*>(pbuf + off) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-        *reinterpret_cast<uint4*>(pbuf + K::PV_BYTES + off) = make_uint4(pv[4 * c], pv[4 * c + 1], pv[4 * c + 2], pv[4 * c + 3]);
+        for (int c = 0; c < 4; ++c)   // chunks of 8 pixels along K
+          *reinterpret_cast<uint4*>(pbuf + (size_t)(c0 / 8 + c) * 2048) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
       }
       fence_proxy_async();
-      mbar_arrive(pv_full + 8 * b);
+      mbar_arrive(p_full + 8 * b);
     }
     atomicAdd(p.ksum + (size_t)n * 128 + r, ksum);
-    if (hsel == 0) {
-      mbar_wait(d2_full, 0);
+    if (g == 0) {
+      mbar_wait(z_full, 0);
       tc_fence_after();
-      uint32_t cr[32];
-      tmem_ld32(lane_base + 256u + (uint32_t)(q * 32), cr);   // diagonal block: columns of my own head
-      tmem_ld_wait();
-      float* dst = p.ctx + ((size_t)n * 128 + r) * 32;
+      float* dst = p.Z + ((size_t)n * 128 + r) * C;
+#pragma unroll 1
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        uint32_t zr[32];
+        tmem_ld32(lane_base + 256u + (uint32_t)c0, zr);
+        tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 32; ++e) atomicAdd(dst + e, __uint_as_float(cr[e]));
+        for (int e = 0; e < 32; ++e) atomicAdd(dst + c0 + e, __uint_as_float(zr[e]));
+      }
     }
   }
   tc_fence_before();
@@ -299,31 +372,40 @@ __global__ void __launch_bounds__(kThreads, 1) la_ctx_kernel(const CtxParams p) 
 }
 
 // ================================================================================================
-// fold: Mn[n][c][(h,d)] (bf16, K-major UMMA image [16 chunks of 8 (h,d)][C][8])
+// fold: Mn[n][c'][(h,d)] = 32^-0.5 / ksum[n][(h,d)] * sum_c U[h][c'][c] * Z[n][(h,d)][c]
+//       (bf16, K-major UMMA image [16 chunks of 8 (h,d)][C][8]);  Ut is U transposed: [h][c][c']
 // ================================================================================================
-// grid (4 heads, N), 256 threads
-__global__ void __launch_bounds__(256) la_fold_kernel(const float* __restrict__ ctx, const float* __restrict__ ksum,
-                                                      const float* __restrict__ wout, __nv_bfloat16* __restrict__ Mn, int C,
+// grid (4 heads, N), 256 threads, dynamic smem 32 * C floats
+__global__ void __launch_bounds__(256) la_fold_kernel(const float* __restrict__ Z, const float* __restrict__ ksum,
+                                                      const float* __restrict__ Ut, __nv_bfloat16* __restrict__ Mn, int C,
                                                       unsigned int* __restrict__ flag) {
-  __shared__ float cx[32][33];       // ctx[d][e] / ksum[d] * 32^-0.5
-  extern __shared__ float wo[];      // [32 e][C]
+  extern __shared__ float zs[];      // [32 d][C]: Z[(h,d)][c] * 32^-0.5 / ksum[(h,d)]
   const int h = blockIdx.x, n = blockIdx.y;
-  for (int i = threadIdx.x; i < 32 * 32; i += 256) {
-    const int d = i >> 5, e = i & 31;
-    const float ks = ksum[(size_t)n * 128 + h * 32 + d];
-    if (e == 0 && !(ks > 1e-30f) && flag) atomicAdd(flag, 1u);
-    cx[d][e] = ctx[((size_t)n * 128 + h * 32 + d) * 32 + e] * 0.17677669529663687f / ks;
-  }
-  for (int i = threadIdx.x; i < 32 * C; i += 256) wo[i] = wout[(size_t)h * 32 * C + i];
-  __syncthreads();
-  __nv_bfloat16* dst = Mn + (size_t)n * 128 * C;
   for (int i = threadIdx.x; i < 32 * C; i += 256) {
-    const int d = i & 31, c = i >> 5;
-    float a = 0.f;
-#pragma unroll 8
-    for (int e = 0; e < 32; ++e) a = fmaf(wo[e * C + c], cx[d][e], a);
-    const int j = h * 32 + d;
-    dst[(size_t)(j >> 3) * (C * 8) + c * 8 + (j & 7)] = __float2bfloat16_rn(a);
+    const int d = i / C;
+    const float ks = ksum[(size_t)n * 128 + h * 32 + d];
+    if (i % C == 0 && !(ks > 1e-30f) && flag) atomicAdd(flag, 1u);
+    zs[i] = Z[((size_t)n * 128 + h * 32) * C + i] * 0.17677669529663687f / ks;
+  }
+  __syncthreads();
+  const float* u = Ut + (size_t)h * C * C;
+  __nv_bfloat16* dst = Mn + (size_t)n * 128 * C;
+  // thread -> (c', group of 8 d): consecutive threads take consecutive c' (coalesced rows of Ut)
+  for (int i = threadIdx.x; i < 4 * C; i += 256) {
+    const int cp = i % C, dg = i / C;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float uu = u[(size_t)c * C + cp];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = fmaf(uu, zs[(dg * 8 + k) * C + c], acc[k]);
+    }
+    // (h,d) = j: chunk j>>3 = h*4 + dg, position j&7 = k  -> 16 contiguous bytes
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = pack_bf16x2(acc[2 * k], acc[2 * k + 1]);
+    *reinterpret_cast<uint4*>(dst + (size_t)(h * 4 + dg) * (C * 8) + cp * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -337,7 +419,8 @@ struct OutCfg {
   static constexpr int WQ_BYTES = 128 * C * 2;
   static constexpr int MN_BYTES = 128 * C * 2;
   static constexpr int P_BYTES = 128 * 128 * 2;
-  static constexpr int SMEM_MIN = WQ_BYTES + MN_BYTES + XS * X_STAGE + 2 * P_BYTES + 2 * C * 4 + 20 * 8 + 16;
+  static constexpr int RS = C >= 128 ? 0 : 3;         // raw x ring fed by cp.async.bulk
+  static constexpr int SMEM_MIN = WQ_BYTES + MN_BYTES + XS * X_STAGE + 2 * P_BYTES + RS * X_STAGE + 2 * C * 4 + 28 * 8 + 16;
   static constexpr int SMEM = SMEM_MIN > 117 * 1024 ? SMEM_MIN : 117 * 1024;   // one CTA per SM: it owns all 512 TMEM columns
 };
 
@@ -349,12 +432,13 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
   uint8_t* mn_s = wq_s + K::WQ_BYTES;
   uint8_t* x_s = mn_s + K::MN_BYTES;
   uint8_t* p_s = x_s + K::XS * K::X_STAGE;
-  float* bg_s = reinterpret_cast<float*>(p_s + 2 * K::P_BYTES);   // bias[C], g2*sqrt(C)[C]
+  uint8_t* raw_s = p_s + 2 * K::P_BYTES;
+  float* bg_s = reinterpret_cast<float*>(raw_s + K::RS * K::X_STAGE);   // bias[C], g2*sqrt(C)[C]
   uint64_t* bars = reinterpret_cast<uint64_t*>(bg_s + 2 * C);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
   const uint32_t w_full = smem_u32(bars), x_full = w_full + 8, x_empty = x_full + 8 * 3, d1_full = x_empty + 8 * 3,
                  d1_empty = d1_full + 16, p_full = d1_empty + 16, p_empty = p_full + 16, d2_full = p_empty + 16,
-                 d2_empty = d2_full + 16;
+                 d2_empty = d2_full + 16, raw_full = d2_empty + 16, raw_empty = raw_full + 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.y;
   const int NTL = (p.HW + 127) / 128;
@@ -369,6 +453,7 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
       mbar_init(p_full + 8 * i, 128); mbar_init(p_empty + 8 * i, 1);
       mbar_init(d2_full + 8 * i, 1); mbar_init(d2_empty + 8 * i, 128);
     }
+    for (int i = 0; i < K::RS; ++i) { mbar_init(raw_full + 8 * i, 1); mbar_init(raw_empty + 8 * i, 4); }
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < C; i += kThreads) { bg_s[i] = p.bout[i]; bg_s[C + i] = p.g2[i] * sqrtf((float)C); }
@@ -386,7 +471,11 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
 
   if (warp < 4) {
     // ---------------------------------------------------------------- producers ------------------
-    produce_x<C, 128, K::XS>(ximg, t0, nt, p.HW, x_s, K::X_STAGE, x_full, x_empty, threadIdx.x, lane);
+    if constexpr (K::RS > 0)
+      produce_x_raw<C, 128, K::XS, (K::RS > 0 ? K::RS : 1)>(ximg, t0, nt, p.HW, x_s, K::X_STAGE, x_full, x_empty, raw_s, raw_full, raw_empty,
+                                                           threadIdx.x, lane);
+    else
+      produce_x<C, 128, K::XS, false>(ximg, t0, nt, p.HW, x_s, K::X_STAGE, x_full, x_empty, threadIdx.x, lane);
   } else if (warp == kMmaWarp) {
     // ---------------------------------------------------------------- MMA issue ------------------
     if (lane == 0) {
@@ -537,9 +626,9 @@ int launch_c(const LinAttnTcW& w, const LinAttnTcArgs& a, cudaStream_t s) {
   int sl = sms() / a.N; if (sl < 1) sl = 1;
   int slA = sl; if (slA > HT / 4) slA = HT / 4; if (slA < 1) slA = 1;
   int slB = sl; if (slB > NTL / 2) slB = NTL / 2; if (slB < 1) slB = 1;
-  CtxParams cp{(const __nv_bfloat16*)a.x, (const __nv_bfloat16*)w.wkv, w.kb2, a.ctx, a.ksum, a.HW, slA};
+  CtxParams cp{(const __nv_bfloat16*)a.x, (const __nv_bfloat16*)w.wk, w.kb2, a.Z, a.ksum, a.HW, slA};
   la_ctx_kernel<C><<<dim3(slA, a.N), kThreads, CtxCfg<C>::SMEM, s>>>(cp);
-  la_fold_kernel<<<dim3(4, a.N), 256, 32 * C * sizeof(float), s>>>(a.ctx, a.ksum, w.wout, (__nv_bfloat16*)a.Mn, C, a.flag);
+  la_fold_kernel<<<dim3(4, a.N), 256, 32 * C * sizeof(float), s>>>(a.Z, a.ksum, w.Ut, (__nv_bfloat16*)a.Mn, C, a.flag);
   OutParams op{(const __nv_bfloat16*)a.x, (const __nv_bfloat16*)w.wq, (const __nv_bfloat16*)a.Mn, w.bout, w.g2,
                (__nv_bfloat16*)a.out, a.HW, slB};
   la_out_kernel<C><<<dim3(slB, a.N), kThreads, OutCfg<C>::SMEM, s>>>(op);
@@ -565,25 +654,32 @@ int linattn_tc_pack(const float* wqkv, const float* g, const float* wout, const 
             dst[(((size_t)b * (C / 8) + c8) * 128 + r) * 8 + e] = __float2bfloat16_rn(wqkv[(size_t)(row0 + b * 128 + r) * C + c] * g[c] * sq);
           }
   };
-  std::vector<__nv_bfloat16> q, kv;
+  std::vector<__nv_bfloat16> q, k;
   pack_rows(0, 1, q);
-  pack_rows(128, 2, kv);
+  pack_rows(128, 1, k);
   std::vector<float> kb(128);
   for (int r = 0; r < 128; ++r) {
     double ss = 0;
     for (int c8 = 0; c8 < C / 8; ++c8)
-      for (int e = 0; e < 8; ++e) { const double v = (double)__bfloat162float(kv[((size_t)c8 * 128 + r) * 8 + e]); ss += v * v; }
+      for (int e = 0; e < 8; ++e) { const double v = (double)__bfloat162float(k[((size_t)c8 * 128 + r) * 8 + e]); ss += v * v; }
     kb[r] = (float)(sqrt(ss) * 1.01 * 1.4426950408889634);   // |k_d| <= |W'_k[d,:]| * |xhat|, |xhat| <= 1 + 2^-8
   }
-  std::vector<float> wo((size_t)128 * C);
-  for (int j = 0; j < 128; ++j)
-    for (int c = 0; c < C; ++c) wo[(size_t)j * C + c] = wout[(size_t)c * 128 + j];   // torch [C][128] -> [128][C]
+  // Ut[h][c][c'] = sum_e Wout[c'][(h,e)] * W'_v[(h,e)][c],  W'_v = W_v * g * sqrt(C)   (to_out.0 o v-projection, per head)
+  std::vector<float> ut((size_t)4 * C * C);
+  for (int h = 0; h < 4; ++h)
+    for (int c = 0; c < C; ++c)
+      for (int cp = 0; cp < C; ++cp) {
+        double a = 0;
+        for (int e = 0; e < 32; ++e)
+          a += (double)wout[(size_t)cp * 128 + h * 32 + e] * (double)wqkv[(size_t)(256 + h * 32 + e) * C + c] * (double)g[c] * (double)sq;
+        ut[((size_t)h * C + c) * C + cp] = (float)a;
+      }
   auto up = [](const void* h, size_t bytes, void** d) {
     if (cudaMalloc(d, bytes) != cudaSuccess) return -1;
     return cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : -1;
   };
-  if (up(q.data(), q.size() * 2, &out->wq) || up(kv.data(), kv.size() * 2, &out->wkv) || up(kb.data(), 128 * 4, (void**)&out->kb2) ||
-      up(wo.data(), wo.size() * 4, (void**)&out->wout) || up(bout, C * 4, (void**)&out->bout) || up(g2, C * 4, (void**)&out->g2))
+  if (up(q.data(), q.size() * 2, &out->wq) || up(k.data(), k.size() * 2, &out->wk) || up(kb.data(), 128 * 4, (void**)&out->kb2) ||
+      up(ut.data(), ut.size() * 4, (void**)&out->Ut) || up(bout, C * 4, (void**)&out->bout) || up(g2, C * 4, (void**)&out->g2))
     return -1;
   int rc = C == 32 ? configure_c<32>() : C == 64 ? configure_c<64>() : configure_c<128>();
   if (rc) return -1;
@@ -592,7 +688,7 @@ int linattn_tc_pack(const float* wqkv, const float* g, const float* wout, const 
 }
 
 void linattn_tc_free(LinAttnTcW* w) {
-  cudaFree(w->wq); cudaFree(w->wkv); cudaFree(w->kb2); cudaFree(w->wout); cudaFree(w->bout); cudaFree(w->g2);
+  cudaFree(w->wq); cudaFree(w->wk); cudaFree(w->kb2); cudaFree(w->Ut); cudaFree(w->bout); cudaFree(w->g2);
   *w = LinAttnTcW();
 }
 

@@ -9,9 +9,9 @@ struct LinAttnTcW {
   bool ready = false;
   int C = 0;
   void* wq = nullptr;    // bf16 [C/8][128][8]: to_qkv rows 0..127 (q), RMSNorm g*sqrt(C) folded in
-  void* wkv = nullptr;   // bf16 [2][C/8][128][8]: rows 128..255 (k) and 256..383 (v)
+  void* wk = nullptr;    // bf16 [C/8][128][8]: rows 128..255 (k)
   float* kb2 = nullptr;  // [128] log2(e) * upper bound of |k_d| (soft-max shift)
-  float* wout = nullptr; // fp32 [128][C] to_out.0 weight, transposed
+  float* Ut = nullptr;   // fp32 [4 heads][C][C]: (to_out.0 o v-projection) per head, transposed
   float* bout = nullptr; // fp32 [C]
   float* g2 = nullptr;   // fp32 [C] to_out.1.g
 };
@@ -20,7 +20,7 @@ struct LinAttnTcArgs {
   const void* x = nullptr;   // bf16 [N][HW][C] (input of the attention block AND its residual)
   void* out = nullptr;       // bf16 [N][HW][C]
   int N = 0, HW = 0;
-  float* ctx = nullptr;      // [N][128][32] fp32, zeroed by the caller
+  float* Z = nullptr;        // [N][128][C] fp32, zeroed by the caller: sum_p exp(k[p,(h,d)]) * xhat[p,c]
   float* ksum = nullptr;     // [N][128] fp32, zeroed by the caller
   void* Mn = nullptr;        // [N][128*C] bf16 scratch
   unsigned int* flag = nullptr;  // optional: incremented when a soft-max row sum underflowed
