@@ -92,7 +92,7 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 # CPU leg: the reference's algorithm (oracle port, torch CPU fp32) on the host cores, bounded sample
 # ------------------------------------------------------------------------------------------------
-def cpu_sample_rate(args, cores, sample_batch=2):
+def cpu_sample_rate(args, cores, sample_batch=8):
     """img/s of the reference's CPU algorithm for the bench workload, extrapolated from one branched
     step + one fused-phase step at `sample_batch` images (a full run is hours)."""
     import torch
@@ -280,9 +280,14 @@ def dominant_kernel_roofline(lib, dev, B, S, hbm, src):
         return None
     byts = N * S * S * (32 + 32) * 2 + 9 * 32 * 32 * 2
     ach = byts / (ms.value / 1000.0) / 1e9
-    return {"kernel": "conv_tc_kernel<32,3,32> (3x3, 32->32 ch, %dx%dx%d)" % (N, S, S), "bound": "hbm", "achieved": ach, "peak": hbm,
-            "unit": "GB/s", "frac": ach / hbm, "traffic": None, "ms_per_launch": ms.value, "peak_source": src,
-            "algorithmic_bytes_per_launch": byts}
+    traffic, tsrc = None, None
+    tp = os.path.join(ROOT, "profiles", "r1h_conv32_traffic.json")
+    if N == 32 and S == 256 and os.path.isfile(tp):  # the ncu capture was taken on exactly this launch shape
+        t = json.load(open(tp))
+        traffic, tsrc = t["traffic_bytes_per_launch"], t["source"]
+    return {"kernel": "conv_tc_kernel<32,3,32> (3x3, 32->32 ch, %dx%dx%d; TMA in, tcgen05, TMA out)" % (N, S, S), "bound": "hbm",
+            "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic, "traffic_source": tsrc,
+            "ms_per_launch": ms.value, "peak_source": src, "algorithmic_bytes_per_launch": byts}
 
 
 if __name__ == "__main__":
