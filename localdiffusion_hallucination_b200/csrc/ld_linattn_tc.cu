@@ -60,6 +60,7 @@ struct OutParams {
   const float* bout; const float* g2;
   __nv_bfloat16* out;
   int HW, slices;
+  int use_max;              // 0: |q| is provably small, soft-max over d needs no max subtraction
 };
 
 // Producer side: ROWS pixels of x/|x| staged as a K-major operand (16-byte chunk (pixel p, channels 8*c8..) at
@@ -414,30 +415,32 @@ __global__ void __launch_bounds__(256) la_fold_kernel(const float* __restrict__ 
 // ================================================================================================
 template <int C>
 struct OutCfg {
-  static constexpr int XS = C >= 128 ? 2 : 3;
+  static constexpr int XS = C >= 64 ? 2 : 3;
   static constexpr int X_STAGE = 128 * C * 2;
   static constexpr int WQ_BYTES = 128 * C * 2;
   static constexpr int MN_BYTES = 128 * C * 2;
   static constexpr int P_BYTES = 128 * 128 * 2;
-  static constexpr int RS = C >= 128 ? 0 : 3;         // raw x ring fed by cp.async.bulk
-  static constexpr int SMEM_MIN = WQ_BYTES + MN_BYTES + XS * X_STAGE + 2 * P_BYTES + RS * X_STAGE + 2 * C * 4 + 28 * 8 + 16;
+  static constexpr int NP = C >= 128 ? 2 : 4;         // P buffers: two per transform warp-group (one when smem is full)
+  static constexpr int RS = C >= 128 ? 0 : (C >= 64 ? 2 : 3);   // raw x ring fed by cp.async.bulk
+  static constexpr int SMEM_MIN = WQ_BYTES + MN_BYTES + XS * X_STAGE + NP * P_BYTES + RS * X_STAGE + 2 * C * 4 + 32 * 8 + 16;
   static constexpr int SMEM = SMEM_MIN > 117 * 1024 ? SMEM_MIN : 117 * 1024;   // one CTA per SM: it owns all 512 TMEM columns
 };
 
 template <int C>
 __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) {
   using K = OutCfg<C>;
+  constexpr int PPG = K::NP / 2;                      // P buffers per warp-group
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* wq_s = smem;
   uint8_t* mn_s = wq_s + K::WQ_BYTES;
   uint8_t* x_s = mn_s + K::MN_BYTES;
   uint8_t* p_s = x_s + K::XS * K::X_STAGE;
-  uint8_t* raw_s = p_s + 2 * K::P_BYTES;
+  uint8_t* raw_s = p_s + K::NP * K::P_BYTES;
   float* bg_s = reinterpret_cast<float*>(raw_s + K::RS * K::X_STAGE);   // bias[C], g2*sqrt(C)[C]
   uint64_t* bars = reinterpret_cast<uint64_t*>(bg_s + 2 * C);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
   const uint32_t w_full = smem_u32(bars), x_full = w_full + 8, x_empty = x_full + 8 * 3, d1_full = x_empty + 8 * 3,
-                 d1_empty = d1_full + 16, p_full = d1_empty + 16, p_empty = p_full + 16, d2_full = p_empty + 16,
+                 d1_empty = d1_full + 16, p_full = d1_empty + 16, p_empty = p_full + 32, d2_full = p_empty + 32,
                  d2_empty = d2_full + 16, raw_full = d2_empty + 16, raw_empty = raw_full + 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.y;
@@ -450,9 +453,9 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
     for (int i = 0; i < K::XS; ++i) { mbar_init(x_full + 8 * i, 4); mbar_init(x_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(d1_full + 8 * i, 1); mbar_init(d1_empty + 8 * i, 128);
-      mbar_init(p_full + 8 * i, 128); mbar_init(p_empty + 8 * i, 1);
       mbar_init(d2_full + 8 * i, 1); mbar_init(d2_empty + 8 * i, 128);
     }
+    for (int i = 0; i < K::NP; ++i) { mbar_init(p_full + 8 * i, 128); mbar_init(p_empty + 8 * i, 1); }
     for (int i = 0; i < K::RS; ++i) { mbar_init(raw_full + 8 * i, 1); mbar_init(raw_empty + 8 * i, 4); }
     fence_barrier_init();
   }
@@ -468,6 +471,9 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
     return;
   }
   const __nv_bfloat16* ximg = p.x + (size_t)n * p.HW * C;
+  // P buffer of tile j: warp-group g = j & 1, its (j >> 1) % PPG -th buffer; completion parity of its k-th use
+  auto pidx = [](int j) { return (j & 1) * PPG + ((j >> 1) % PPG); };
+  auto ppar = [](int j) { return (uint32_t)(((j >> 1) / PPG) & 1); };
 
   if (warp < 4) {
     // ---------------------------------------------------------------- producers ------------------
@@ -491,17 +497,17 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
     const uint32_t wq_lo = desc_lo(smem_u32(wq_s), 2048), mn_lo = desc_lo(smem_u32(mn_s), C * 16), x_lo0 = desc_lo(smem_u32(x_s), 2048),
                    p_lo0 = desc_lo(smem_u32(p_s), 2048);
     auto mma2 = [&](int j) {
-      const int g = j & 1, u = j >> 1;
-      mbar_wait(p_full + 8 * g, u & 1);
+      const int g = j & 1, u = j >> 1, pi = pidx(j);
+      mbar_wait(p_full + 8 * pi, ppar(j));
       mbar_wait(d2_empty + 8 * g, (u & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t p_lo = p_lo0 + (uint32_t)(g * (K::P_BYTES >> 4));
+        const uint32_t p_lo = p_lo0 + (uint32_t)(pi * (K::P_BYTES >> 4));
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // K = 128 (h,d) = 8 x 16
           umma_bf16_lh(tmem_base + 256u + (uint32_t)(g * C), p_lo + (uint32_t)(2 * k * 128), hi128, mn_lo + (uint32_t)(2 * k * C), hi128,
                        idesc2, k > 0 ? 1u : 0u);
-        umma_commit(p_empty + 8 * g);
+        umma_commit(p_empty + 8 * pi);
         umma_commit(d2_full + 8 * g);
       }
       __syncwarp();
@@ -526,79 +532,127 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
     mma2(nt - 1);
   } else {
     // ---------------------------------------------------------------- transform + epilogue -------
+    // Warp-group g owns tiles g, g+2, ...  Order: T(i), T(i+2), E(i), T(i+4), E(i+2), ... so that the epilogue of a
+    // tile never waits for its own second MMA (with a single P buffer per group the order is T(i), E(i)).
     const int q = warp & 3, g = (warp - kXfWarp0) >> 2;
     const int m = q * 32 + lane;                    // pixel row inside the tile
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint8_t* pbuf = p_s + (size_t)g * K::P_BYTES;
-    int u = 0;
-    for (int i = g; i < nt; i += 2, ++u) {
+    auto transform = [&](int i) {
+      const int u = i >> 1, pi = pidx(i);
+      uint8_t* pbuf = p_s + (size_t)pi * K::P_BYTES + m * 16;
       mbar_wait(d1_full + 8 * g, u & 1);
       tc_fence_after();
-      mbar_wait(p_empty + 8 * g, (u & 1) ^ 1);      // MMA2 of my previous tile has consumed P
+      mbar_wait(p_empty + 8 * pi, ppar(i) ^ 1);     // the MMA2 that last read this P buffer is complete
 #pragma unroll 1
       for (int h = 0; h < 4; ++h) {
         uint32_t qr[32];
         tmem_ld32(lane_base + (uint32_t)(g * 128 + h * 32), qr);
         tmem_ld_wait();
         if (h == 3) { tc_fence_before(); mbar_arrive(d1_empty + 8 * g); }
-        float mx = __uint_as_float(qr[0]);
+        // q arrives pre-multiplied by log2(e) (folded into W_q): softmax_d(q) = 2^(q' - max) / sum
+        float mx = 0.f;
+        if (p.use_max) {
+          mx = __uint_as_float(qr[0]);
 #pragma unroll
-        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(qr[j]));
-        const float mxl = mx * kLog2e;
+          for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(qr[j]));
+        }
         float e[32], su = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { e[j] = ex2_approx(fmaf(__uint_as_float(qr[j]), kLog2e, -mxl)); su += e[j]; }
+        for (int j = 0; j < 32; ++j) { e[j] = ex2_approx(__uint_as_float(qr[j]) - mx); su += e[j]; }
         const float sc = 1.0f / su;   // softmax(dim=-2) (ddpm.py:242); the dim_head^-0.5 of ddpm.py:245 is folded into Mn
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t o4[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) o4[j] = pack_bf16x2(e[8 * c + 2 * j] * sc, e[8 * c + 2 * j + 1] * sc);
-          *reinterpret_cast<uint4*>(pbuf + (size_t)(h * 4 + c) * 2048 + m * 16) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+          *reinterpret_cast<uint4*>(pbuf + (size_t)(h * 4 + c) * 2048) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
         }
       }
       fence_proxy_async();
-      mbar_arrive(p_full + 8 * g);
-      // epilogue of this tile: two sweeps over the TMEM row (sum of squares, then normalise + store)
+      mbar_arrive(p_full + 8 * pi);
+    };
+    auto epilogue = [&](int i) {
+      const int u = i >> 1;
       mbar_wait(d2_full + 8 * g, u & 1);
       tc_fence_after();
       const int px = (t0 + i) * 128 + m;
-      float ss = 0.f;
-#pragma unroll 1
-      for (int j0 = 0; j0 < C; j0 += 32) {
-        uint32_t rr[32];
-        tmem_ld32(lane_base + 256u + (uint32_t)(g * C + j0), rr);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { const float v = __uint_as_float(rr[j]) + bg_s[j0 + j]; ss = fmaf(v, v, ss); }
-      }
-      const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);       // to_out RMSNorm (ddpm.py:231,251)
       const __nv_bfloat16* xr = ximg + (size_t)px * C;
       __nv_bfloat16* orow = p.out + ((size_t)n * p.HW + px) * C;
-#pragma unroll 1
-      for (int j0 = 0; j0 < C; j0 += 32) {
-        uint32_t rr[32];
-        tmem_ld32(lane_base + 256u + (uint32_t)(g * C + j0), rr);
-        tmem_ld_wait();
-        if (j0 + 32 == C) { tc_fence_before(); mbar_arrive(d2_empty + 8 * g); }
-        if (px < p.HW) {
+      if constexpr (C <= 64) {
+        // one sweep: the whole row stays in registers
+        float o[C];
+        float ss = 0.f;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint4 xv = *reinterpret_cast<const uint4*>(xr + j0 + 8 * c);
+        for (int j0 = 0; j0 < C; j0 += 32) {
+          uint32_t rr[32];
+          tmem_ld32(lane_base + 256u + (uint32_t)(g * C + j0), rr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { o[j0 + j] = __uint_as_float(rr[j]) + bg_s[j0 + j]; ss = fmaf(o[j0 + j], o[j0 + j], ss); }
+        }
+        tc_fence_before();
+        mbar_arrive(d2_empty + 8 * g);
+        if (px < p.HW) {
+          const float inv = rsqrtf(fmaxf(ss, 1e-24f));            // to_out RMSNorm (ddpm.py:231,251)
+#pragma unroll
+          for (int j0 = 0; j0 < C; j0 += 8) {
+            const uint4 xv = *reinterpret_cast<const uint4*>(xr + j0);
             const uint32_t xi[4] = {xv.x, xv.y, xv.z, xv.w};
             uint32_t o4[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const int cc = 8 * c + 2 * j;
               const float2 xf = unpack_bf16x2(xi[j]);
-              const float a = fmaf((__uint_as_float(rr[cc]) + bg_s[j0 + cc]) * inv, bg_s[C + j0 + cc], xf.x);
-              const float b = fmaf((__uint_as_float(rr[cc + 1]) + bg_s[j0 + cc + 1]) * inv, bg_s[C + j0 + cc + 1], xf.y);
-              o4[j] = pack_bf16x2(a, b);
+              o4[j] = pack_bf16x2(fmaf(o[j0 + 2 * j] * inv, bg_s[C + j0 + 2 * j], xf.x), fmaf(o[j0 + 2 * j + 1] * inv, bg_s[C + j0 + 2 * j + 1], xf.y));
             }
-            *reinterpret_cast<uint4*>(orow + j0 + 8 * c) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+            *reinterpret_cast<uint4*>(orow + j0) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+          }
+        }
+      } else {
+        // two sweeps over the TMEM row (sum of squares, then normalise + store)
+        float ss = 0.f;
+#pragma unroll 1
+        for (int j0 = 0; j0 < C; j0 += 32) {
+          uint32_t rr[32];
+          tmem_ld32(lane_base + 256u + (uint32_t)(g * C + j0), rr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { const float v = __uint_as_float(rr[j]) + bg_s[j0 + j]; ss = fmaf(v, v, ss); }
+        }
+        const float inv = rsqrtf(fmaxf(ss, 1e-24f));              // to_out RMSNorm (ddpm.py:231,251)
+#pragma unroll 1
+        for (int j0 = 0; j0 < C; j0 += 32) {
+          uint32_t rr[32];
+          tmem_ld32(lane_base + 256u + (uint32_t)(g * C + j0), rr);
+          tmem_ld_wait();
+          if (j0 + 32 == C) { tc_fence_before(); mbar_arrive(d2_empty + 8 * g); }
+          if (px < p.HW) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint4 xv = *reinterpret_cast<const uint4*>(xr + j0 + 8 * c);
+              const uint32_t xi[4] = {xv.x, xv.y, xv.z, xv.w};
+              uint32_t o4[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int cc = 8 * c + 2 * j;
+                const float2 xf = unpack_bf16x2(xi[j]);
+                const float a = fmaf((__uint_as_float(rr[cc]) + bg_s[j0 + cc]) * inv, bg_s[C + j0 + cc], xf.x);
+                const float b = fmaf((__uint_as_float(rr[cc + 1]) + bg_s[j0 + cc + 1]) * inv, bg_s[C + j0 + cc + 1], xf.y);
+                o4[j] = pack_bf16x2(a, b);
+              }
+              *reinterpret_cast<uint4*>(orow + j0 + 8 * c) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+            }
           }
         }
       }
+    };
+    if constexpr (PPG == 2) {
+      if (g < nt) transform(g);
+      for (int i = g; i < nt; i += 2) {
+        if (i + 2 < nt) transform(i + 2);
+        epilogue(i);
+      }
+    } else {
+      for (int i = g; i < nt; i += 2) { transform(i); epilogue(i); }
     }
   }
   tc_fence_before();
@@ -630,7 +684,7 @@ int launch_c(const LinAttnTcW& w, const LinAttnTcArgs& a, cudaStream_t s) {
   la_ctx_kernel<C><<<dim3(slA, a.N), kThreads, CtxCfg<C>::SMEM, s>>>(cp);
   la_fold_kernel<<<dim3(4, a.N), 256, 32 * C * sizeof(float), s>>>(a.Z, a.ksum, w.Ut, (__nv_bfloat16*)a.Mn, C, a.flag);
   OutParams op{(const __nv_bfloat16*)a.x, (const __nv_bfloat16*)w.wq, (const __nv_bfloat16*)a.Mn, w.bout, w.g2,
-               (__nv_bfloat16*)a.out, a.HW, slB};
+               (__nv_bfloat16*)a.out, a.HW, slB, w.q_use_max};
   la_out_kernel<C><<<dim3(slB, a.N), kThreads, OutCfg<C>::SMEM, s>>>(op);
   return 3;
 }
@@ -644,18 +698,18 @@ int linattn_tc_pack(const float* wqkv, const float* g, const float* wout, const 
   out->C = C;
   const float sq = sqrtf((float)C);
   // fold RMSNorm's g * sqrt(C) (ddpm.py:131-132) into the 1x1 to_qkv weights (ddpm.py:227); rows: q 0..127, k 128..255, v 256..383
-  auto pack_rows = [&](int row0, int nblocks, std::vector<__nv_bfloat16>& dst) {
+  auto pack_rows = [&](int row0, int nblocks, std::vector<__nv_bfloat16>& dst, float extra = 1.0f) {
     dst.resize((size_t)nblocks * 128 * C);
     for (int b = 0; b < nblocks; ++b)
       for (int c8 = 0; c8 < C / 8; ++c8)
         for (int r = 0; r < 128; ++r)
           for (int e = 0; e < 8; ++e) {
             const int c = c8 * 8 + e;
-            dst[(((size_t)b * (C / 8) + c8) * 128 + r) * 8 + e] = __float2bfloat16_rn(wqkv[(size_t)(row0 + b * 128 + r) * C + c] * g[c] * sq);
+            dst[(((size_t)b * (C / 8) + c8) * 128 + r) * 8 + e] = __float2bfloat16_rn(wqkv[(size_t)(row0 + b * 128 + r) * C + c] * g[c] * sq * extra);
           }
   };
   std::vector<__nv_bfloat16> q, k;
-  pack_rows(0, 1, q);
+  pack_rows(0, 1, q, 1.4426950408889634f);   // q rows carry log2(e): the soft-max over d uses ex2 directly
   pack_rows(128, 1, k);
   std::vector<float> kb(128);
   for (int r = 0; r < 128; ++r) {
@@ -664,6 +718,15 @@ int linattn_tc_pack(const float* wqkv, const float* g, const float* wout, const 
       for (int e = 0; e < 8; ++e) { const double v = (double)__bfloat162float(k[((size_t)c8 * 128 + r) * 8 + e]); ss += v * v; }
     kb[r] = (float)(sqrt(ss) * 1.01 * 1.4426950408889634);   // |k_d| <= |W'_k[d,:]| * |xhat|, |xhat| <= 1 + 2^-8
   }
+  // |q'_d| <= |W'_q[d,:]|: when every bound is small the soft-max over d needs no max subtraction (2^q' cannot overflow)
+  double qb = 0;
+  for (int r = 0; r < 128; ++r) {
+    double ss = 0;
+    for (int c8 = 0; c8 < C / 8; ++c8)
+      for (int e = 0; e < 8; ++e) { const double v = (double)__bfloat162float(q[((size_t)c8 * 128 + r) * 8 + e]); ss += v * v; }
+    if (sqrt(ss) > qb) qb = sqrt(ss);
+  }
+  out->q_use_max = qb * 1.01 > 60.0 ? 1 : 0;
   // Ut[h][c][c'] = sum_e Wout[c'][(h,e)] * W'_v[(h,e)][c],  W'_v = W_v * g * sqrt(C)   (to_out.0 o v-projection, per head)
   std::vector<float> ut((size_t)4 * C * C);
   for (int h = 0; h < 4; ++h)

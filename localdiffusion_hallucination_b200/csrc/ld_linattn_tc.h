@@ -14,6 +14,7 @@ struct LinAttnTcW {
   float* Ut = nullptr;   // fp32 [4 heads][C][C]: (to_out.0 o v-projection) per head, transposed
   float* bout = nullptr; // fp32 [C]
   float* g2 = nullptr;   // fp32 [C] to_out.1.g
+  int q_use_max = 1;     // 0 when |q * log2 e| is provably < 60 for every (h,d): no max pass in the soft-max over d
 };
 
 struct LinAttnTcArgs {
