@@ -48,9 +48,17 @@ namespace {
 
 constexpr int kTeamThreads = 128;      // one producer team = 4 warps
 constexpr int kTeams = 2;
-constexpr int kEpiWarp0 = 8;           // warps 8..11 (warp % 4 == TMEM lane quarter)
-constexpr int kMmaWarp = 12;
-constexpr int kThreads = 14 * 32;      // warp 13: weight pipeline
+// Warp roles.  Full kernel (register-staging producers): warps 0-7 producers, 8-11 epilogue, 12 MMA, 13 weights.
+// Lean kernel (TMA activation loads only): warp 0 TMA, 1 MMA, 2 weights, 4-7 epilogue -- 8 warps, so three CTAs
+// fit an SM and overlap each other's per-tile hand-shake chains.
+template <bool LEAN> struct Roles {
+  static constexpr int kProdWarps = LEAN ? 1 : 8;
+  static constexpr int kEpiWarp0 = LEAN ? 4 : 8;       // four warps, warp % 4 == TMEM lane quarter
+  static constexpr int kMmaWarp = LEAN ? 1 : 12;
+  static constexpr int kWWarp = LEAN ? 2 : 13;
+  static constexpr int kThreads = LEAN ? 8 * 32 : 14 * 32;
+  static constexpr int kMinCtas = LEAN ? 3 : 2;
+};
 constexpr int SA_MAX = 6;              // activation stages (runtime: 3..6)
 constexpr int SB = 4;                  // weight stages (streaming mode)
 constexpr int kBatch = 3;              // 16-byte loads in flight per producer thread (register staging path)
@@ -150,9 +158,11 @@ __device__ __forceinline__ void stats_chunk(const float (&f)[16], bool valid, fl
   }
 }
 
-template <int NT, int KS, int KC>
-__global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_constant__ KParams p) {
+template <int NT, int KS, int KC, bool LEAN>
+__global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) conv_tc_kernel(const __grid_constant__ KParams p) {
   using G = Geo<KS, KC>;
+  using R = Roles<LEAN>;
+  constexpr int kThreads = R::kThreads, kEpiWarp0 = R::kEpiWarp0, kMmaWarp = R::kMmaWarp, kWWarp = R::kWWarp;
   constexpr int TAPS = KS * KS;
   constexpr int B_STAGE = NT * KC * 2;
   constexpr uint32_t TM_COLS = 2 * NT;   // two accumulator stages; NT in {32,64,128,256} -> power of two >= 64
@@ -188,8 +198,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   const int n_tile = blockIdx.y;
 
-  if (warp < kTeams * 4) {
-    if (p.tma_in) {
+  if (warp < R::kProdWarps) {
+    if (LEAN || p.tma_in) {
       // ================================================================ TMA producer (one thread) =======
       if (warp == 0 && lane == 0) {
         Ring ra;
@@ -215,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
           }
         }
       }
-    } else {
+    } else if constexpr (!LEAN) {
       // ================================================================ register-staging producers ======
       const int team = warp >> 2, tid = threadIdx.x & (kTeamThreads - 1);
       const int ch = tid % G::CH;                       // constant per thread: 128 % CH == 0
@@ -315,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
         }
       }
     }
-  } else if (warp < kMmaWarp) {
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
     // ================================================================== epilogue ======================
     const int ew = warp - kEpiWarp0, etid = threadIdx.x - kEpiWarp0 * 32;
     const int m = ew * 32 + lane;
@@ -497,7 +507,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const __grid_const
         }
       }
     }
-  } else {
+  } else if (warp == kWWarp) {
     // ================================================================== weight pipeline ===============
     if (lane == 0) {
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)n_tile * p.nchunks * TAPS * B_STAGE;
@@ -605,7 +615,8 @@ bool map_out(CUtensorMap* m, void* ptr, int N, int H, int W, int Cout, int nt, i
 // opt in to the maximum dynamic shared memory once per instantiation (done at pack time, outside any graph capture)
 template <int NT, int KS, int KC>
 int configure_one() {
-  return cudaFuncSetAttribute(conv_tc_kernel<NT, KS, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg().max_smem) == cudaSuccess ? 0 : -1;
+  if (cudaFuncSetAttribute(conv_tc_kernel<NT, KS, KC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg().max_smem) != cudaSuccess) return -1;
+  return cudaFuncSetAttribute(conv_tc_kernel<NT, KS, KC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg().max_smem) == cudaSuccess ? 0 : -1;
 }
 template <int KS, int KC>
 int configure_nt(int NT) {
@@ -648,10 +659,16 @@ int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
   size_t smem = layout<NT, KS, KC>(p, sa, p.nb_stages);
   if (smem > (size_t)cfg().max_smem) { sa = 3; smem = layout<NT, KS, KC>(p, sa, p.nb_stages); }
   if (smem > (size_t)cfg().max_smem) return -1;
+  if (p.tma_in && sa == 4) {   // a third co-resident CTA is worth more than a fourth activation stage
+    const size_t smem3 = layout<NT, KS, KC>(p, 3, p.nb_stages);
+    if ((size_t)cfg().max_smem_sm / (smem3 + 1024) >= 3 && (size_t)cfg().max_smem_sm / (smem + 1024) < 3 && 512 / (2 * NT) >= 3) { sa = 3; smem = smem3; }
+    else layout<NT, KS, KC>(p, sa, p.nb_stages);
+  }
   p.sa = sa;
   // persistent grid: as many CTAs as are co-resident (registers allow two per SM; 2*NT of 512 TMEM columns each)
+  const bool lean = p.tma_in != 0;
   int occ = (int)((size_t)cfg().max_smem_sm / (smem + 1024));
-  if (occ > 2) occ = 2;
+  if (occ > (lean ? 3 : 2)) occ = lean ? 3 : 2;
   const int tm = 512 / (2 * NT);
   if (occ > tm) occ = tm;
   if (occ < 1) occ = 1;
@@ -664,7 +681,8 @@ int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
     const int r = gx - p.step_img * tpi;
     p.step_ty = r / p.tiles_x; p.step_tx = r - p.step_ty * p.tiles_x;
   }
-  conv_tc_kernel<NT, KS, KC><<<dim3((unsigned)gx, (unsigned)ntiles_y), kThreads, smem, s>>>(p);
+  if (lean) conv_tc_kernel<NT, KS, KC, true><<<dim3((unsigned)gx, (unsigned)ntiles_y), Roles<true>::kThreads, smem, s>>>(p);
+  else conv_tc_kernel<NT, KS, KC, false><<<dim3((unsigned)gx, (unsigned)ntiles_y), Roles<false>::kThreads, smem, s>>>(p);
   return 1;
 }
 
