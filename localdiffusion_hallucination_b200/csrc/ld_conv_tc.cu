@@ -77,6 +77,7 @@ struct alignas(64) KParams {
   long long M;
   int resident, nb_stages, coef_floats;
   int tma_in, tma_out, sa;           // TMA activation loads / TMA output store / number of activation stages
+  int ds, ds_cs;                     // 2x2 stride-2 (pixel-unshuffle) conv run as a 1x1 over four strided TMA gathers; ds_cs = source channels
   int a_stage, lbo16;                // activation stage pitch (bytes) and chunk stride (16-byte units)
   int off_a, off_b, off_coef;        // shared memory carve-up (bytes)
   // normalise-on-load prologue (GroupNorm affine [+ FiLM] + activation of the source tensor)
@@ -204,19 +205,24 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
       if (warp == 0 && lane == 0) {
         Ring ra;
         TileWalk tw;
-        tw.init(p, KS == 3);
+        tw.init(p, KS == 3 || p.ds);
         const uint32_t stage_bytes = (uint32_t)(G::CH * G::LBO_TMA);
         for (; tw.tile < p.ntiles; tw.next(p)) {
           for (int c = 0; c < p.nchunks; ++c) {
             mbar_wait(a_empty + 8 * ra.s, ra.ph ^ 1);
             const int cbase = c * KC;
-            const void* map = cbase < p.C0 ? (const void*)&p.map_a0 : (const void*)&p.map_a1;
+            const void* map = (p.ds || cbase < p.C0) ? (const void*)&p.map_a0 : (const void*)&p.map_a1;
             const int cb8 = (cbase < p.C0 ? cbase : cbase - p.C0) >> 3;
             const uint32_t dst = smem_u32(a_s + (size_t)ra.s * p.a_stage);
             mbar_arrive_expect_tx(a_full + 8 * ra.s, stage_bytes);
             if (!(p.dbg & 1)) {
               if (KS == 3) tma_load_5d(dst, map, 0, tw.tx * G::TW - 1, tw.ty * G::TH - 1, cb8, tw.img, a_full + 8 * ra.s);
-              else tma_load_3d(dst, map, 0, tw.tile * 128, cb8, a_full + 8 * ra.s);
+              else if (p.ds) {
+                // chunk c covers channels [cbase % Cs, +KC) of unshuffle tap q = cbase / Cs = (p1, p2): every other pixel
+                // of the source starting at (2 ty + p1, 2 tx + p2) -- one strided TMA gather of 16 x 8 pixels
+                const int q = cbase / p.ds_cs, cq = cbase - q * p.ds_cs;
+                tma_load_5d(dst, map, 0, 2 * (tw.tx * 8) + (q & 1), 2 * (tw.ty * 16) + (q >> 1), cq >> 3, tw.img, a_full + 8 * ra.s);
+              } else tma_load_3d(dst, map, 0, tw.tile * 128, cb8, a_full + 8 * ra.s);
             } else {
               // development aid: complete the transaction without data
               asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(a_full + 8 * ra.s), "r"(stage_bytes) : "memory");
@@ -333,13 +339,14 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
     const int cpg = p.stats ? p.Cout / p.stats_G : 1;
     int it_tile = 0;
     TileWalk tw;
-    tw.init(p, KS == 3);
+    const bool tile2d = KS == 3 || p.ds;
+    tw.init(p, tile2d);
     for (; tw.tile < p.ntiles; tw.next(p), ++it_tile) {
       const int as = it_tile & 1;
       const int img = tw.img;
       long long opix = -1;
-      if (KS == 3) {
-        const int gy = tw.ty * G::TH + (m >> 3), gx = tw.tx * G::TW + (m & 7);
+      if (tile2d) {
+        const int gy = tw.ty * 16 + (m >> 3), gx = tw.tx * 8 + (m & 7);
         if (gy < p.H && gx < p.W) opix = ((long long)img * p.H + gy) * p.W + gx;
       } else {
         const long long gp = (long long)tw.tile * 128 + m;
@@ -415,7 +422,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
         if (etid == 0) {
           if (!(p.dbg & 4)) {
             const uint32_t src = smem_u32(o_s + (size_t)as * (128 * O_ROW));
-            if (KS == 3) tma_store_4d(&p.map_out, nbase, tw.tx * G::TW, tw.ty * G::TH, img, src);
+            if (tile2d) tma_store_4d(&p.map_out, nbase, tw.tx * 8, tw.ty * 16, img, src);
             else tma_store_2d(&p.map_out, nbase, tw.tile * 128, src);
             bulk_commit_group();
           }
@@ -578,6 +585,17 @@ bool map_in_3x3(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int
   const cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, 16, (cuuint64_t)H * W * C * 2};
   const cuuint32_t box[5] = {8, (cuuint32_t)pitch, (cuuint32_t)rows, (cuuint32_t)(kc / 8), 1};
   const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  return f(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// pixel-unshuffle gather: every other pixel of [N][H][W][C] in both directions -> 16 x 8 pixels per box
+bool map_in_ds(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int kc) {
+  EncodeTiledFn f = encode_fn();
+  if (!f) return false;
+  const cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(C / 8), (cuuint64_t)N};
+  const cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, 16, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[5] = {8, 16, 32, (cuuint32_t)(kc / 8), 1};   // traversal stride 2: ceil(16/2) x ceil(32/2) pixels are loaded
+  const cuuint32_t es[5] = {1, 2, 2, 1, 1};
   return f(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -747,6 +765,8 @@ int conv_tc_pack(const float* w, const float* bias, int Cin, int Cout, int ks, i
 
 bool conv_tc_supports(const ConvTcW& w, const ConvTcArgs& a) {
   if (!w.ready) return false;
+  if (a.ds) return w.ks == 1 && w.Cin == 4 * a.C0 && a.C0 % 32 == 0 && !a.src1 && !a.up && !a.pro_stats && !a.stats && !a.res &&
+                  a.Hin == 2 * a.H && a.Win == 2 * a.W && encode_fn() != nullptr;
   if (a.C0 + a.C1 != w.Cin || a.C0 % 32 || a.C1 % 32) return false;
   if (a.up && (w.ks != 3 || a.src1)) return false;
   if (a.pro_stats && (w.ks != 3 || a.src1 || a.up || a.pro_G < 1 || a.C0 % a.pro_G)) return false;
@@ -767,6 +787,7 @@ static bool build_params(const ConvTcW& w, const ConvTcArgs& a, KParams& p) {
   const bool k64 = w.w && a.C0 % 64 == 0 && a.C1 % 64 == 0;
   const int kc = k64 ? 64 : 32;
   p = KParams{};
+  p.ds = a.ds; p.ds_cs = a.C0;
   p.src0 = (const __nv_bfloat16*)a.src0; p.src1 = (const __nv_bfloat16*)a.src1; p.C0 = a.C0; p.C1 = a.C1;
   p.N = a.N; p.H = a.H; p.W = a.W; p.Hin = a.Hin; p.Win = a.Win; p.up = a.up;
   p.nchunks = w.Cin / kc;
@@ -780,14 +801,16 @@ static bool build_params(const ConvTcW& w, const ConvTcArgs& a, KParams& p) {
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("LD_CONV_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   // TMA activation loads whenever the source is read as stored (no up-sampling, no normalise-on-load)
   p.tma_in = 0;
-  if (!a.up && !a.pro_stats) {
+  if (a.ds) {
+    p.tma_in = map_in_ds(&p.map_a0, a.src0, a.N, a.Hin, a.Win, a.C0, kc) ? 1 : 0;
+  } else if (!a.up && !a.pro_stats) {
     bool ok = w.ks == 3 ? map_in_3x3(&p.map_a0, a.src0, a.N, a.Hin, a.Win, a.C0, kc, 10, 18) : map_in_1x1(&p.map_a0, a.src0, p.M, a.C0, kc);
     if (ok && a.src1)
       ok = w.ks == 3 ? map_in_3x3(&p.map_a1, a.src1, a.N, a.Hin, a.Win, a.C1, kc, 10, 18) : map_in_1x1(&p.map_a1, a.src1, p.M, a.C1, kc);
     p.tma_in = ok ? 1 : 0;
   }
-  p.tma_out = map_out(&p.map_out, a.dst, a.N, a.H, a.W, w.Cout, w.ntile, w.ks) ? 1 : 0;
-  if (w.ks == 3) {
+  p.tma_out = map_out(&p.map_out, a.dst, a.N, a.H, a.W, w.Cout, w.ntile, a.ds ? 3 : w.ks) ? 1 : 0;
+  if (w.ks == 3 || a.ds) {
     p.tiles_x = (a.W + 7) / 8; p.tiles_y = (a.H + 15) / 16;
     p.ntiles = a.N * p.tiles_x * p.tiles_y;
   } else {
@@ -813,6 +836,7 @@ int conv_tc_launch(const ConvTcW& w, const ConvTcArgs& a, cudaStream_t s) {
   }
   KParams p = it->second.p;
   const bool k64 = it->second.k64;
+  if (a.ds && !p.tma_in) return -1;
   const int ny = w.Cout / w.ntile;
   if (w.ks == 3) return k64 ? launch_nt<3, 64>(w.ntile, p, ny, s) : launch_nt<3, 32>(w.ntile, p, ny, s);
   return k64 ? launch_nt<1, 64>(w.ntile, p, ny, s) : launch_nt<1, 32>(w.ntile, p, ny, s);

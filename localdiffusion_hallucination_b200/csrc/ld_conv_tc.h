@@ -21,6 +21,7 @@ struct ConvTcArgs {
   int N = 0, H = 0, W = 0;     // output extent
   int Hin = 0, Win = 0;        // stored source extent
   int up = 0;                  // read src0 through a nearest x2 up-sampling
+  int ds = 0;                  // pixel-unshuffle down-sampling (ddpm.py:122): weights packed as a 1x1 over (p1, p2, c); Hin = 2H
   void* dst = nullptr;         // bf16 [N,H,W,Cout]
   const void* res = nullptr;   // optional bf16 residual added in the epilogue
   // fused "normalise on load" prologue on src0 (3x3, single source, no up-sampling):

@@ -272,7 +272,9 @@ static int pack_conv(Engine& E, const std::string& p, bool bias, bool unshuffle,
   if (E.use_tc && cw->Cin >= 32 && cw->Cout >= 32) {
     std::vector<float> bh;
     if (bias) bh = W(E, p + ".bias").host;
-    r = conv_tc_pack(pk.data(), bias ? bh.data() : nullptr, cw->Cin, cw->Cout, cw->ks, cw->stride, cw->pad, &cw->tc);
+    // the 2x2/stride-2 (pixel-unshuffle) conv is a 1x1 conv over the (p1, p2, c) gather: same [tap][Cin][Cout] memory
+    if (unshuffle) r = conv_tc_pack(pk.data(), bias ? bh.data() : nullptr, 4 * cw->Cin, cw->Cout, 1, 1, 0, &cw->tc);
+    else r = conv_tc_pack(pk.data(), bias ? bh.data() : nullptr, cw->Cin, cw->Cout, cw->ks, cw->stride, cw->pad, &cw->tc);
     if (r) return fail(LD_ERR_CUDA, "conv_tc_pack(%s) failed", p.c_str());
   }
   return 0;
@@ -455,6 +457,7 @@ struct Builder {
       ta.src0 = a.p; ta.C0 = a.C; ta.src1 = b ? b->p : nullptr; ta.C1 = b ? b->C : 0;
       ta.N = a.N; ta.H = outH; ta.W = outW; ta.Hin = a.H; ta.Win = a.W; ta.up = up ? 1 : 0;
       ta.res = resid ? resid->p : nullptr;
+      ta.ds = cw.ks == 2 ? 1 : 0;
       use_tc = conv_tc_supports(cw.tc, ta);
     }
     bool pro_fused = false, stats_fused = false;
