@@ -81,8 +81,8 @@ struct alignas(64) KParams {
   int a_stage, lbo16;                // activation stage pitch (bytes) and chunk stride (16-byte units)
   int off_a, off_b, off_coef;        // shared memory carve-up (bytes)
   // normalise-on-load prologue (GroupNorm affine [+ FiLM] + activation of the source tensor)
-  const double* pro_stats; const float* pro_gamma; const float* pro_beta; const float* pro_film;
-  int pro_film_stride, pro_G, pro_act; float pro_eps;
+  const float* pro_ab;   // [N][2][C0]: scale then shift (gn_coef_kernel), or null
+  int pro_act;
   // GroupNorm statistics of the output
   double* stats; int stats_G;
   int dbg;   // development aid (env LD_CONV_DBG): 1 no activation loads, 2 no MMAs, 4 no output stores
@@ -235,9 +235,6 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
       // ================================================================ register-staging producers ======
       const int team = warp >> 2, tid = threadIdx.x & (kTeamThreads - 1);
       const int ch = tid % G::CH;                       // constant per thread: 128 % CH == 0
-      float* cA = coef + team * 2 * (p.coef_floats / 4);  // [Cin] scale, then [Cin] shift
-      float* cB = cA + p.coef_floats / 4;
-      int cur_img = -1;
       const int hp0 = tid / G::CH;                      // my first staged pixel; item `it` stages pixel hp0 + it * (128 / CH)
       constexpr int HSTEP = kTeamThreads / G::CH;
       Ring ra;                                          // position of global stage g
@@ -248,29 +245,6 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
         if (p.nchunks == 1 && (g & 1) != team) { ++g; ra.advance(SA); continue; }
         const int img = tw.img, ty0 = tw.ty * G::TH, tx0 = tw.tx * G::TW;
         const long long pix0 = (long long)tw.tile * 128;
-        if (p.pro_stats && img != cur_img) {
-          // GroupNorm coefficients of the source tensor for this image (ddpm.py:174-185 folded to y = a x + b)
-          named_bar(1 + team, kTeamThreads);            // nobody of this team still reads the old coefficients
-          const int Cin = p.C0, cpg = Cin / p.pro_G;
-          const double cnt = (double)p.Hin * p.Win * cpg;
-          for (int c = tid; c < Cin; c += kTeamThreads) {
-            const int gi = c / cpg;
-            const double su = p.pro_stats[((size_t)img * p.pro_G + gi) * 2], sq = p.pro_stats[((size_t)img * p.pro_G + gi) * 2 + 1];
-            const double mean = su / cnt;
-            double var = sq / cnt - mean * mean;
-            if (var < 0) var = 0;
-            const float rstd = (float)(1.0 / sqrt(var + (double)p.pro_eps));
-            float a = rstd * p.pro_gamma[c], b = p.pro_beta[c] - (float)mean * a;
-            if (p.pro_film) {
-              const float sc = p.pro_film[(size_t)img * p.pro_film_stride + c] + 1.0f;
-              const float sf = p.pro_film[(size_t)img * p.pro_film_stride + Cin + c];
-              a *= sc; b = b * sc + sf;
-            }
-            cA[c] = a; cB[c] = b;
-          }
-          named_bar(1 + team, kTeamThreads);
-          cur_img = img;
-        }
         // the whole halo patch lies inside the image: no bounds checks
         const bool interior = KS == 3 && ty0 > 0 && tx0 > 0 && ty0 + G::TH < p.H && tx0 + G::TW < p.W && !p.up;
         const long long tbase = ((long long)img * p.Hin + (ty0 - 1)) * p.Win + (tx0 - 1);   // halo origin (3x3, no up-sampling)
@@ -282,9 +256,13 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
           if (cbase < p.C0) { src = p.src0; cs = p.C0; cb = cbase; } else { src = p.src1; cs = p.C1; cb = cbase - p.C0; }
           src += cb + ch * 8;
           float pa[8], pb[8];
-          if (p.pro_stats) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { pa[j] = cA[cbase + ch * 8 + j]; pb[j] = cB[cbase + ch * 8 + j]; }
+          if (p.pro_ab) {   // y = a x + b per (image, channel), precomputed by gn_coef_kernel
+            const float4* ab = reinterpret_cast<const float4*>(p.pro_ab + ((size_t)img * 2) * p.C0 + cbase + ch * 8);
+            const float4 a0 = __ldg(ab), a1 = __ldg(ab + 1);
+            const float4* bb = reinterpret_cast<const float4*>(p.pro_ab + ((size_t)img * 2 + 1) * p.C0 + cbase + ch * 8);
+            const float4 b0 = __ldg(bb), b1 = __ldg(bb + 1);
+            pa[0] = a0.x; pa[1] = a0.y; pa[2] = a0.z; pa[3] = a0.w; pa[4] = a1.x; pa[5] = a1.y; pa[6] = a1.z; pa[7] = a1.w;
+            pb[0] = b0.x; pb[1] = b0.y; pb[2] = b0.z; pb[3] = b0.w; pb[4] = b1.x; pb[5] = b1.y; pb[6] = b1.z; pb[7] = b1.w;
           }
           uint8_t* stage = a_s + (size_t)ra.s * p.a_stage + ch * G::LBO_REG + hp0 * 16;
 #pragma unroll 1
@@ -320,7 +298,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
             for (int k = 0; k < kBatch; ++k) {
               const int hp = hp0 + (it0 + k) * HSTEP;
               if (it0 + k < G::ITEMS && hp < G::HPIX) {
-                if (p.pro_stats && ok[k]) v[k] = pro_apply(v[k], pa, pb, p.pro_act);   // padding stays exactly zero
+                if (p.pro_ab && ok[k]) v[k] = pro_apply(v[k], pa, pb, p.pro_act);   // padding stays exactly zero
                 *reinterpret_cast<uint4*>(stage + (it0 + k) * (HSTEP * 16)) = v[k];
               }
             }
@@ -717,6 +695,35 @@ int launch_nt(int NT, KParams& p, int ntiles_y, cudaStream_t s) {
 
 }  // namespace
 
+namespace {
+// GroupNorm (+FiLM) folded to y = a x + b per (image, channel) (ddpm.py:174-185): ab[n][0][c] = a, ab[n][1][c] = b
+__global__ void gn_coef_kernel(const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ film, int film_stride, int G, int C, double cnt, float eps, float* __restrict__ ab) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / (C / G);
+    const double su = stats[((size_t)n * G + g) * 2], sq = stats[((size_t)n * G + g) * 2 + 1];
+    const double mean = su / cnt;
+    double var = sq / cnt - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    float a = rstd * gamma[c], b = beta[c] - (float)mean * a;
+    if (film) {
+      const float sc = film[(size_t)n * film_stride + c] + 1.0f, sf = film[(size_t)n * film_stride + C + c];
+      a *= sc; b = b * sc + sf;
+    }
+    ab[((size_t)n * 2) * C + c] = a;
+    ab[((size_t)n * 2 + 1) * C + c] = b;
+  }
+}
+}  // namespace
+
+int gn_coef_launch(const double* stats, const float* gamma, const float* beta, const float* film, int film_stride, int G, int C, int N,
+                   long long HW, float eps, float* ab, cudaStream_t s) {
+  gn_coef_kernel<<<N, C < 256 ? C : 256, 0, s>>>(stats, gamma, beta, film, film_stride, G, C, (double)HW * (C / G), eps, ab);
+  return 1;
+}
+
 static int pick_ntile(int Cout) {
   if (Cout <= 256) return (Cout == 32 || Cout == 64 || Cout == 128 || Cout == 256) ? Cout : 0;
   if (Cout % 256 == 0) return 256;
@@ -765,11 +772,11 @@ int conv_tc_pack(const float* w, const float* bias, int Cin, int Cout, int ks, i
 
 bool conv_tc_supports(const ConvTcW& w, const ConvTcArgs& a) {
   if (!w.ready) return false;
-  if (a.ds) return w.ks == 1 && w.Cin == 4 * a.C0 && a.C0 % 32 == 0 && !a.src1 && !a.up && !a.pro_stats && !a.stats && !a.res &&
+  if (a.ds) return w.ks == 1 && w.Cin == 4 * a.C0 && a.C0 % 32 == 0 && !a.src1 && !a.up && !a.pro_ab && !a.stats && !a.res &&
                   a.Hin == 2 * a.H && a.Win == 2 * a.W && encode_fn() != nullptr;
   if (a.C0 + a.C1 != w.Cin || a.C0 % 32 || a.C1 % 32) return false;
   if (a.up && (w.ks != 3 || a.src1)) return false;
-  if (a.pro_stats && (w.ks != 3 || a.src1 || a.up || a.pro_G < 1 || a.C0 % a.pro_G)) return false;
+  if (a.pro_ab && (w.ks != 3 || a.src1 || a.up)) return false;
   if (a.stats) {
     if (w.ks != 3 || a.stats_G < 1 || w.Cout % a.stats_G) return false;
     const int cpg = w.Cout / a.stats_G;
@@ -794,16 +801,15 @@ static bool build_params(const ConvTcW& w, const ConvTcArgs& a, KParams& p) {
   p.w = (const __nv_bfloat16*)(k64 ? w.w : w.w32); p.bias = w.bias; p.Cout = w.Cout;
   p.dst = (__nv_bfloat16*)a.dst; p.res = (const __nv_bfloat16*)a.res;
   p.M = (long long)a.N * a.H * a.W;
-  p.pro_stats = a.pro_stats; p.pro_gamma = a.pro_gamma; p.pro_beta = a.pro_beta; p.pro_film = a.pro_film;
-  p.pro_film_stride = a.pro_film_stride; p.pro_G = a.pro_G; p.pro_act = a.pro_act; p.pro_eps = a.pro_eps;
-  p.coef_floats = a.pro_stats ? 4 * a.C0 : 0;   // two teams x (scale, shift)
+  p.pro_ab = a.pro_ab; p.pro_act = a.pro_act;
+  p.coef_floats = 0;
   p.stats = a.stats; p.stats_G = a.stats_G;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("LD_CONV_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   // TMA activation loads whenever the source is read as stored (no up-sampling, no normalise-on-load)
   p.tma_in = 0;
   if (a.ds) {
     p.tma_in = map_in_ds(&p.map_a0, a.src0, a.N, a.Hin, a.Win, a.C0, kc) ? 1 : 0;
-  } else if (!a.up && !a.pro_stats) {
+  } else if (!a.up && !a.pro_ab) {
     bool ok = w.ks == 3 ? map_in_3x3(&p.map_a0, a.src0, a.N, a.Hin, a.Win, a.C0, kc, 10, 18) : map_in_1x1(&p.map_a0, a.src0, p.M, a.C0, kc);
     if (ok && a.src1)
       ok = w.ks == 3 ? map_in_3x3(&p.map_a1, a.src1, a.N, a.Hin, a.Win, a.C1, kc, 10, 18) : map_in_1x1(&p.map_a1, a.src1, p.M, a.C1, kc);

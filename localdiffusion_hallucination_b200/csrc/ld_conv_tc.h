@@ -25,12 +25,9 @@ struct ConvTcArgs {
   void* dst = nullptr;         // bf16 [N,H,W,Cout]
   const void* res = nullptr;   // optional bf16 residual added in the epilogue
   // fused "normalise on load" prologue on src0 (3x3, single source, no up-sampling):
-  //   x' = act(GroupNorm(x; pro_stats, gamma, beta) * (scale + 1) + shift)   (ddpm.py:174-185, unet_model.py:21-22)
-  const double* pro_stats = nullptr;   // [N][pro_G][2] {sum, sumsq} of src0 (as written by `stats` of its producer)
-  const float* pro_gamma = nullptr; const float* pro_beta = nullptr;   // [C0]
-  const float* pro_film = nullptr; int pro_film_stride = 0;            // per image [2*C0] (scale, shift) or null
-  int pro_G = 0, pro_act = 0;          // act: 0 none, 1 SiLU, 2 ReLU
-  float pro_eps = 1e-5f;
+  //   x' = act(a[n,c] * x + b[n,c]) with the GroupNorm (+FiLM) coefficients of gn_coef_launch  (ddpm.py:174-185, unet_model.py:21-22)
+  const float* pro_ab = nullptr;       // [N][2][C0] (scale, shift) or null
+  int pro_act = 0;                     // 0 none, 1 SiLU, 2 ReLU
   // fused GroupNorm statistics of the output (3x3 only): stats[n][stats_G][2] += {sum, sumsq}; zeroed by the caller
   double* stats = nullptr; int stats_G = 0;
 };
@@ -38,6 +35,9 @@ struct ConvTcArgs {
 // host: pack fp32 [taps][Cin][Cout] weights; leaves `ready == false` for unsupported shapes
 int conv_tc_pack(const float* w_tap_cin_cout, const float* bias, int Cin, int Cout, int ks, int stride, int pad, ConvTcW* out);
 bool conv_tc_supports(const ConvTcW& w, const ConvTcArgs& a);
+// GroupNorm statistics {sum, sumsq}[N][G][2] (+ optional per-image FiLM [2C] scale, shift) -> coefficient table [N][2][C]
+int gn_coef_launch(const double* stats, const float* gamma, const float* beta, const float* film, int film_stride, int G, int C, int N,
+                   long long HW, float eps, float* ab, cudaStream_t s);
 // returns number of kernels launched, < 0 on error
 int conv_tc_launch(const ConvTcW& w, const ConvTcArgs& a, cudaStream_t s);
 

@@ -463,7 +463,7 @@ struct Builder {
     bool pro_fused = false, stats_fused = false;
     if (use_tc && pro) {
       ConvTcArgs t2 = ta;
-      t2.pro_stats = (const double*)8; t2.pro_G = pro->G; t2.pro_act = pro->act;
+      t2.pro_ab = (const float*)8; t2.pro_act = pro->act;
       pro_fused = conv_tc_supports(cw.tc, t2);
     }
     if (use_tc && stats_off) {
@@ -482,17 +482,24 @@ struct Builder {
       ta.dst = o.p;
       const ConvTcW* w = &cw.tc;
       const size_t pro_off = pro_fused ? (size_t)pro->st : 0, st_off = stats_fused ? (size_t)stats_off : 0;
-      if (pro_fused) {
-        ta.pro_gamma = pro->g; ta.pro_beta = pro->b; ta.pro_G = pro->G; ta.pro_act = pro->act; ta.pro_eps = 1e-5f;
-        ta.pro_film = pro->film_off >= 0 ? film + pro->film_off : nullptr; ta.pro_film_stride = E.film_total;
+      Ten abt;
+      if (pro_fused) {   // y = a x + b table of the source tensor's GroupNorm (+FiLM), one tiny kernel
+        abt = alloc(a.N, 1, 1, 2 * a.C, 4);
+        const float* g = pro->g; const float* bb = pro->b; const int G = pro->G, C = a.C, N = a.N; const long long HW = (long long)a.H * a.W;
+        const float* fl = pro->film_off >= 0 ? film + pro->film_off : nullptr; const int fs = E.film_total;
+        float* ab = (float*)abt.p;
+        op([pp, pro_off, g, bb, fl, fs, G, C, N, HW, ab](cudaStream_t s) {
+          return gn_coef_launch((const double*)((char*)pp->zero_arena + pro_off), g, bb, fl, fs, G, C, N, HW, 1e-5f, ab, s);
+        });
+        ta.pro_ab = ab; ta.pro_act = pro->act;
       }
       if (stats_fused) ta.stats_G = stats_G;
-      op([ta, w, pp, pro_fused, stats_fused, pro_off, st_off](cudaStream_t s) {
+      op([ta, w, pp, stats_fused, st_off](cudaStream_t s) {
         ConvTcArgs q = ta;
-        if (pro_fused) q.pro_stats = (const double*)((char*)pp->zero_arena + pro_off);
         if (stats_fused) q.stats = (double*)((char*)pp->zero_arena + st_off);
         return conv_tc_launch(*w, q, s);
       });
+      if (pro_fused) release(abt);
     } else {
       ConvP p{};
       p.src0 = a.p; p.C0 = a.C; p.src1 = b ? b->p : nullptr; p.C1 = b ? b->C : 0;
@@ -778,10 +785,31 @@ static int build_unet_plan(Engine& E, Plan& P, int N, int H, int W, const float*
 static int run_plan(Engine& E, Plan& P, cudaStream_t s) {
   if (P.zero_arena && cudaMemsetAsync(P.zero_arena, 0, P.zero_bytes, s) != cudaSuccess)
     return fail(LD_ERR_CUDA, "memset of the zero arena failed");
+  // development aid (env LD_PROFILE_OPS=1): per-op device time of this plan, CUDA events on the launch stream
+  static int prof = -1;
+  if (prof < 0) { const char* e = getenv("LD_PROFILE_OPS"); prof = e ? atoi(e) : 0; }
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (prof) cudaStreamIsCapturing(s, &cap);
+  const bool timed = prof && cap == cudaStreamCaptureStatusNone && P.ops.size() >= (size_t)prof;
+  std::vector<cudaEvent_t> evs;
+  std::vector<int> nl;
+  if (timed) { evs.resize(P.ops.size() + 1); for (auto& ev : evs) cudaEventCreate(&ev); cudaEventRecord(evs[0], s); }
+  size_t oi = 0;
   for (auto& f : P.ops) {
     int n = f(s);
     if (n < 0) return fail(LD_ERR_CUDA, "kernel launch failed in plan");
     E.launches += n;
+    if (timed) { cudaEventRecord(evs[++oi], s); nl.push_back(n); }
+  }
+  if (timed) {
+    cudaStreamSynchronize(s);
+    float tot = 0;
+    for (size_t i = 0; i < P.ops.size(); ++i) {
+      float ms = 0; cudaEventElapsedTime(&ms, evs[i], evs[i + 1]); tot += ms;
+      fprintf(stderr, "LDPROF %3zu n=%d %9.1f us\n", i, nl[i], ms * 1000.f);
+    }
+    fprintf(stderr, "LDPROF total %9.1f us over %zu ops (N=%d %dx%d)\n", tot * 1000.f, P.ops.size(), P.N, P.H, P.W);
+    for (auto& ev : evs) cudaEventDestroy(ev);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(LD_ERR_CUDA, "launch error: %s", cudaGetErrorString(e));
@@ -1265,7 +1293,7 @@ int ld_debug_conv_fused(const float* x0, int C0, int N, int H, int W, const floa
     for (int c = 0; c < C0; ++c)
       for (int t = 0; t < taps; ++t) pk[((size_t)t * C0 + c) * Cout + o] = w_host[((size_t)o * C0 + c) * taps + t];
   const size_t npx = (size_t)N * H * W;
-  void *a0 = nullptr, *ao = nullptr;
+  void *a0 = nullptr, *ao = nullptr; float* abd = nullptr;
   CK(cudaMalloc(&a0, npx * C0 * 2)); launch_convert(x0, false, a0, true, (long long)npx * C0, s);
   CK(cudaMalloc(&ao, npx * Cout * 2));
   if (stats_out) CK(cudaMemsetAsync(stats_out, 0, (size_t)N * stats_G * 2 * sizeof(double), s));
@@ -1274,14 +1302,17 @@ int ld_debug_conv_fused(const float* x0, int C0, int N, int H, int W, const floa
   if (conv_tc_pack(pk.data(), bias_host, C0, Cout, 3, 1, 1, &tw) || !tw.ready) rc = fail(LD_ERR_INVALID, "conv_tc_pack: unsupported shape");
   else {
     ConvTcArgs ta; ta.src0 = a0; ta.C0 = C0; ta.N = N; ta.H = H; ta.W = W; ta.Hin = H; ta.Win = W; ta.dst = ao;
-    ta.pro_stats = pro_stats; ta.pro_gamma = pro_gamma; ta.pro_beta = pro_beta; ta.pro_film = pro_film;
-    ta.pro_film_stride = pro_film_stride; ta.pro_G = pro_G; ta.pro_act = pro_act; ta.pro_eps = 1e-5f;
+    if (pro_stats) {
+      CK(cudaMalloc(&abd, (size_t)N * 2 * C0 * 4));
+      gn_coef_launch(pro_stats, pro_gamma, pro_beta, pro_film, pro_film_stride, pro_G, C0, N, (long long)H * W, 1e-5f, abd, s);
+      ta.pro_ab = abd; ta.pro_act = pro_act;
+    }
     ta.stats = stats_out; ta.stats_G = stats_G;
     if (conv_tc_launch(tw, ta, s) < 0) rc = fail(LD_ERR_INVALID, "conv_tc_launch: unsupported arguments");
   }
   launch_convert(ao, true, out, false, (long long)npx * Cout, s);
   cudaError_t e = cudaStreamSynchronize(s);
-  cudaFree(tw.w); cudaFree(tw.w32); cudaFree(tw.bias); cudaFree(a0); cudaFree(ao);
+  cudaFree(tw.w); cudaFree(tw.w32); cudaFree(tw.bias); cudaFree(a0); cudaFree(ao); cudaFree(abd);
   if (e != cudaSuccess) return fail(LD_ERR_CUDA, "debug fused conv failed: %s", cudaGetErrorString(e));
   return rc;
 }
