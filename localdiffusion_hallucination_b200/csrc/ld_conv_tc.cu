@@ -85,6 +85,7 @@ struct alignas(64) KParams {
   int pro_act;
   // GroupNorm statistics of the output
   double* stats; int stats_G;
+  int contig;                        // contiguous tile walk (see TileWalk)
   int dbg;   // development aid (env LD_CONV_DBG): 1 no activation loads, 2 no MMAs, 4 no output stores
 };
 
@@ -103,9 +104,16 @@ struct Geo {
 
 // walks tile = blockIdx.x + k * gridDim.x and keeps its (image, tile row, tile column) without integer divisions
 struct TileWalk {
-  int tile, img, ty, tx;
+  int tile, end, img, ty, tx;
+  // strided walk: tile = blockIdx.x + k * gridDim.x.  Contiguous walk (p.contig): CTA b owns one run of consecutive tiles,
+  // so its tiles stay inside one or two images and per-image partial sums can live in the CTA across tiles.
   __device__ __forceinline__ void init(const KParams& p, bool k3) {
-    tile = blockIdx.x; img = 0; ty = 0; tx = 0;
+    if (p.contig) {
+      const int base = p.ntiles / (int)gridDim.x, rem = p.ntiles - base * (int)gridDim.x, b = (int)blockIdx.x;
+      tile = b * base + (b < rem ? b : rem);
+      end = tile + base + (b < rem ? 1 : 0);
+    } else { tile = blockIdx.x; end = p.ntiles; }
+    img = 0; ty = 0; tx = 0;
     if (k3) {
       const int tpi = p.tiles_x * p.tiles_y;
       img = tile / tpi;
@@ -114,7 +122,7 @@ struct TileWalk {
     }
   }
   __device__ __forceinline__ void next(const KParams& p) {
-    tile += gridDim.x;
+    tile += p.contig ? 1 : (int)gridDim.x;
     tx += p.step_tx;
     if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
     ty += p.step_ty;
@@ -122,6 +130,12 @@ struct TileWalk {
     img += p.step_img;
   }
 };
+// number of tiles this CTA walks
+__device__ __forceinline__ int my_tile_count(const KParams& p) {
+  const int G = (int)gridDim.x, b = (int)blockIdx.x;
+  if (p.contig) { const int base = p.ntiles / G; return base + (b < p.ntiles - base * G ? 1 : 0); }
+  return b < p.ntiles ? (p.ntiles - b + G - 1) / G : 0;
+}
 
 // ring position: stage index and phase parity, advanced without divisions
 struct Ring {
@@ -143,20 +157,37 @@ __device__ __forceinline__ uint4 pro_apply(uint4 v, const float (&a)[8], const f
   return make_uint4(out[0], out[1], out[2], out[3]);
 }
 
-// per-warp partial GroupNorm sums of 16 consecutive channels held by each lane (one pixel per lane)
+// per-warp partial GroupNorm sums of 16 consecutive channels held by each lane (one pixel per lane).  The NV = 2 * groups
+// values of a lane are reduced together: every butterfly step halves the number of live values (a lane keeps the half its
+// lane bit selects and sends the other), so NV values cost NV - 1 + log2(32 / NV) shuffles instead of 5 * NV.
 template <int CPG>
 __device__ __forceinline__ void stats_chunk(const float (&f)[16], bool valid, float* sacc, int grp0, int lane) {
   constexpr int NG = CPG >= 16 ? 1 : 16 / CPG;   // groups touched by this 16-channel chunk
   constexpr int W = CPG >= 16 ? 16 : CPG;
+  constexpr int NV = 2 * NG;                     // 2, 4, 8 or 16 values
+  constexpr int LOG = NV == 2 ? 1 : NV == 4 ? 2 : NV == 8 ? 3 : 4;
+  float v[NV];
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
     float s = 0.f, q = 0.f;
 #pragma unroll
-    for (int j = 0; j < W; ++j) { const float v = valid ? f[g * W + j] : 0.f; s += v; q = fmaf(v, v, q); }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-    if (lane == 0) { atomicAdd(sacc + 2 * (grp0 + g), s); atomicAdd(sacc + 2 * (grp0 + g) + 1, q); }
+    for (int j = 0; j < W; ++j) { const float x = valid ? f[g * W + j] : 0.f; s += x; q = fmaf(x, x, q); }
+    v[2 * g] = s; v[2 * g + 1] = q;
   }
+#pragma unroll
+  for (int st = 0; st < LOG; ++st) {
+    const int off = 16 >> st, half = NV >> (st + 1);
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? v[i] : v[i + half], keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+#pragma unroll
+  for (int off = 16 >> LOG; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+  // lane now holds value index (lane >> (5 - LOG)) = 2 * g + statistic, summed over the warp
+  if ((lane & ((32 >> LOG) - 1)) == 0) atomicAdd(sacc + 2 * grp0 + (lane >> (5 - LOG)), v[0]);
 }
 
 template <int NT, int KS, int KC, bool LEAN>
@@ -207,7 +238,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
         TileWalk tw;
         tw.init(p, KS == 3 || p.ds);
         const uint32_t stage_bytes = (uint32_t)(G::CH * G::LBO_TMA);
-        for (; tw.tile < p.ntiles; tw.next(p)) {
+        for (; tw.tile < tw.end; tw.next(p)) {
           for (int c = 0; c < p.nchunks; ++c) {
             mbar_wait(a_empty + 8 * ra.s, ra.ph ^ 1);
             const int cbase = c * KC;
@@ -241,7 +272,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
       int g = 0;
       TileWalk tw;
       tw.init(p, KS == 3);
-      for (; tw.tile < p.ntiles; tw.next(p)) {
+      for (; tw.tile < tw.end; tw.next(p)) {
         if (p.nchunks == 1 && (g & 1) != team) { ++g; ra.advance(SA); continue; }
         const int img = tw.img, ty0 = tw.ty * G::TH, tx0 = tw.tx * G::TW;
         const long long pix0 = (long long)tw.tile * 128;
@@ -319,9 +350,27 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
     TileWalk tw;
     const bool tile2d = KS == 3 || p.ds;
     tw.init(p, tile2d);
-    for (; tw.tile < p.ntiles; tw.next(p), ++it_tile) {
+    // GroupNorm partial sums of the image being walked live in shared memory (sacc) and go to global memory, one double
+    // atomic per (group, statistic), when the walk leaves the image
+    int stat_img = -1;
+    auto flush_stats = [&](int im) {
+      named_bar(3, 128);
+      const int ng2 = 2 * (NT / cpg > 0 ? NT / cpg : 1);
+      if (etid < ng2) {
+        const float v = sacc[etid];
+        sacc[etid] = 0.f;
+        const int gi = nbase / cpg + (etid >> 1);
+        atomicAdd(p.stats + ((size_t)im * p.stats_G + gi) * 2 + (etid & 1), (double)v);
+      }
+      named_bar(3, 128);
+    };
+    for (; tw.tile < tw.end; tw.next(p), ++it_tile) {
       const int as = it_tile & 1;
       const int img = tw.img;
+      if (p.stats && img != stat_img) {
+        if (stat_img >= 0) flush_stats(stat_img);
+        stat_img = img;
+      }
       long long opix = -1;
       if (tile2d) {
         const int gy = tw.ty * 16 + (m >> 3), gx = tw.tx * 8 + (m & 7);
@@ -406,19 +455,8 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
           }
         }
       }
-      if (p.stats) {
-        // flush the tile's partial sums: one double atomic per (group, statistic)
-        named_bar(3, 128);
-        const int ng2 = 2 * (NT / cpg > 0 ? NT / cpg : 1);
-        if (etid < ng2) {
-          const float v = sacc[etid];
-          sacc[etid] = 0.f;
-          const int gi = nbase / cpg + (etid >> 1);
-          atomicAdd(p.stats + ((size_t)img * p.stats_G + gi) * 2 + (etid & 1), (double)v);
-        }
-        named_bar(3, 128);
-      }
     }
+    if (p.stats && stat_img >= 0) flush_stats(stat_img);
     if (NT <= 64 && p.tma_out && etid == 0) bulk_wait_group<0>();
   } else if (warp == kMmaWarp) {
     // ================================================================== MMA issue =====================
@@ -433,7 +471,8 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
       Ring ra, rb;
       int it_tile = 0;
       if (p.resident) { mbar_wait(b_full, 0); tc_fence_after(); }
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it_tile) {
+      const int my_tiles = my_tile_count(p);
+      for (; it_tile < my_tiles; ++it_tile) {
         const int as = it_tile & 1;
         mbar_wait(acc_empty + 8 * as, ((it_tile >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -502,7 +541,8 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
         for (int i = 0; i < total; ++i) bulk_g2s(smem_u32(b_s + (size_t)i * B_STAGE), wsrc + (size_t)i * B_STAGE, B_STAGE, b_full);
       } else {
         Ring rb;
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int my_tiles = my_tile_count(p);
+        for (int it = 0; it < my_tiles; ++it) {
           for (int i = 0; i < total; ++i) {
             mbar_wait(b_empty + 8 * rb.s, rb.ph ^ 1);
             mbar_arrive_expect_tx(b_full + 8 * rb.s, B_STAGE);
@@ -672,6 +712,12 @@ int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
   if (gx < 1) gx = 1;
   if (gx > p.ntiles) gx = p.ntiles;
   {
+    static int walk = -1;   // env LD_CONV_WALK: 0 strided, 1 contiguous when statistics are fused (default), 2 always contiguous
+    if (walk < 0) { const char* e = getenv("LD_CONV_WALK"); walk = e ? atoi(e) : 1; }
+    p.contig = (walk == 2 || (walk == 1 && p.stats)) ? 1 : 0;
+  }
+  if (p.contig) { p.step_img = 0; p.step_ty = 0; p.step_tx = 1; }
+  else {
     const int tpi = p.tiles_x * p.tiles_y;
     p.step_img = gx / tpi;
     const int r = gx - p.step_img * tpi;

@@ -409,7 +409,8 @@ static int finalize(Engine& E) {
 // -------------------------------------------------------------------------------------------------
 struct Builder {
   Engine& E; Plan& P; int err = 0;
-  float* film = nullptr;  // [N][film_total]
+  float* film = nullptr;  // [N][film_total] (row stride film_stride; 0 when the whole batch shares one timestep)
+  int film_stride = 0;
   Builder(Engine& e, Plan& p) : E(e), P(p) {}
 
   Ten alloc(int N, int H, int W, int C, size_t elem) {
@@ -486,7 +487,7 @@ struct Builder {
       if (pro_fused) {   // y = a x + b table of the source tensor's GroupNorm (+FiLM), one tiny kernel
         abt = alloc(a.N, 1, 1, 2 * a.C, 4);
         const float* g = pro->g; const float* bb = pro->b; const int G = pro->G, C = a.C, N = a.N; const long long HW = (long long)a.H * a.W;
-        const float* fl = pro->film_off >= 0 ? film + pro->film_off : nullptr; const int fs = E.film_total;
+        const float* fl = pro->film_off >= 0 ? film + pro->film_off : nullptr; const int fs = film_stride;
         float* ab = (float*)abt.p;
         op([pp, pro_off, g, bb, fl, fs, G, C, N, HW, ab](cudaStream_t s) {
           return gn_coef_launch((const double*)((char*)pp->zero_arena + pro_off), g, bb, fl, fs, G, C, N, HW, 1e-5f, ab, s);
@@ -532,7 +533,7 @@ struct Builder {
     GnApplyP p{};
     p.xa = xa.p; p.statsA = stA; p.gA = gA; p.bA = bA; p.GA = GA;
     p.xb = xb ? xb->p : nullptr; p.statsB = stB; p.gB = gB; p.bB = bB; p.GB = GB; p.modeB = modeB;
-    p.film = film_off >= 0 ? film + film_off : nullptr; p.film_stride = E.film_total;
+    p.film = film_off >= 0 ? film + film_off : nullptr; p.film_stride = film_stride;
     p.act = act; p.out = o.p; p.N = xa.N; p.HW = xa.H * xa.W; p.C = xa.C; p.eps = 1e-5f;
     Plan* pp = &P; const bool bf = E.bf;
     op([pp, p, bf](cudaStream_t s) {
@@ -705,9 +706,10 @@ static int build_unet_plan(Engine& E, Plan& P, int N, int H, int W, const float*
   // time embedding + FiLM vectors
   Ten st = B.alloc(N, 1, 1, 4 * E.d.dim, 4), fl = B.alloc(N, 1, 1, E.film_total, 4);
   B.film = (float*)fl.p;
+  B.film_stride = t_scalar ? 0 : E.film_total;
   {
     TimeP tp{};
-    tp.t = t64; tp.t_scalar = t_scalar; tp.N = N; tp.dim = E.d.dim; tp.theta = E.d.sinusoidal_theta;
+    tp.t = t64; tp.t_scalar = t_scalar; tp.N = t_scalar ? 1 : N; tp.dim = E.d.dim; tp.theta = E.d.sinusoidal_theta;
     tp.neg_step = (float)(-(std::log((double)E.d.sinusoidal_theta) / (double)(E.d.dim / 2 - 1)));
     tp.w1 = E.tw1; tp.b1 = E.tb1; tp.w2 = E.tw2; tp.b2 = E.tb2; tp.st = (float*)st.p;
     tp.wf = E.film_w; tp.bf_ = E.film_b; tp.total = E.film_total; tp.film = (float*)fl.p;

@@ -779,22 +779,37 @@ __global__ void time_embed_kernel(TimeP p) {
     p.st[(size_t)n * td + j] = a / (1.0f + expf(-a));  // SiLU in front of every block MLP (ddpm.py:192)
   }
 }
+// all block MLPs at once (ddpm.py:191-194): one warp per output row j, coalesced weight reads, every image of the batch
 __global__ void film_kernel(TimeP p) {
-  extern __shared__ float st[];  // [4dim]
-  const int n = blockIdx.y, td = 4 * p.dim;
-  for (int i = threadIdx.x; i < td; i += blockDim.x) st[i] = p.st[(size_t)n * td + i];
+  extern __shared__ float st[];  // [N][4dim]
+  const int td = 4 * p.dim;
+  for (int i = threadIdx.x; i < p.N * td; i += blockDim.x) st[i] = p.st[i];
   __syncthreads();
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (j >= p.total) return;
-  float a = p.bf_[j];
   const float* w = p.wf + (size_t)j * td;
-  for (int k = 0; k < td; ++k) a = fmaf(w[k], st[k], a);
-  p.film[(size_t)n * p.total + j] = a;
+  const float bj = p.bf_[j];
+  for (int n = 0; n < p.N; ++n) {
+    float a = 0.f;
+    for (int k = lane; k < td; k += 32) a = fmaf(w[k], st[n * td + k], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) p.film[(size_t)n * p.total + j] = a + bj;
+  }
 }
 int launch_time_film(const TimeP& p, cudaStream_t s) {
+  // the sampler shares one timestep across the batch (t_scalar): a single row is computed and consumers use stride 0
   time_embed_kernel<<<p.N, 128, (size_t)5 * p.dim * sizeof(float), s>>>(p);
-  film_kernel<<<dim3(cdiv(p.total, 128), p.N), 128, (size_t)4 * p.dim * sizeof(float), s>>>(p);
-  return 2;
+  int launches = 1;
+  for (int n0 = 0; n0 < p.N; n0 += 16) {   // 16 images per launch keep the staged embeddings inside 48 KB
+    TimeP q = p;
+    q.N = p.N - n0 < 16 ? p.N - n0 : 16;
+    q.st = p.st + (size_t)n0 * 4 * p.dim; q.film = p.film + (size_t)n0 * p.total;
+    film_kernel<<<cdiv(p.total, 8), 256, (size_t)q.N * 4 * p.dim * sizeof(float), s>>>(q);
+    ++launches;
+  }
+  return launches;
 }
 
 // =================================================================================================
