@@ -170,6 +170,12 @@ LD_API int ld_debug_conv_fused(const float* x0, int C0, int N, int H, int W, con
                                int Cout, const double* pro_stats, const float* pro_gamma, const float* pro_beta,
                                const float* pro_film, int pro_film_stride, int pro_G, int pro_act, double* stats_out,
                                int stats_G, float* out, void* stream);
+/* Test hook: ResnetBlock block1.proj (3x3, GroupNorm statistics of its output) and res_conv (1x1) of the same virtual
+ * concat [x0 | x1] in one tcgen05 launch with two accumulators (ddpm.py:207,212).  x0/x1/out/out2: fp32 NHWC device;
+ * w3 [Cout][C0+C1][3][3], w1 [Cout][C0+C1], biases: host fp32. */
+LD_API int ld_debug_conv_dual(const float* x0, int C0, const float* x1, int C1, int N, int H, int W, const float* w3_host,
+                              const float* b3_host, const float* w1_host, const float* b1_host, int Cout, double* stats_out,
+                              int stats_G, float* out, float* out2, void* stream);
 /* Test hook: the fused tcgen05 LinearAttention block, attn(x) + x (ddpm.py:214-251, 425).  x/out: fp32 NHWC device;
  * wqkv [384][C], g [C], wout [C][128], bout [C], g2 [C]: host fp32 in the reference's parameter layout. */
 LD_API int ld_debug_linattn(const float* x, int C, int N, int HW, const float* wqkv, const float* g, const float* wout,

@@ -74,6 +74,7 @@ struct alignas(64) KParams {
   const __nv_bfloat16* w; const float* bias;
   int Cout;
   __nv_bfloat16* dst; const __nv_bfloat16* res;
+  __nv_bfloat16* dst2; const float* bias2; int dual;   // fused 1x1 convolution of the same input (second accumulator)
   long long M;
   int resident, nb_stages, coef_floats;
   int tma_in, tma_out, sa;           // TMA activation loads / TMA output store / number of activation stages
@@ -197,7 +198,9 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
   constexpr int kThreads = R::kThreads, kEpiWarp0 = R::kEpiWarp0, kMmaWarp = R::kMmaWarp, kWWarp = R::kWWarp;
   constexpr int TAPS = KS * KS;
   constexpr int B_STAGE = NT * KC * 2;
-  constexpr uint32_t TM_COLS = 2 * NT;   // two accumulator stages; NT in {32,64,128,256} -> power of two >= 64
+  // two accumulator stages of NT (dual: 2 NT) fp32 columns; NT in {32,64,128,256} -> power of two >= 64
+  const uint32_t acc_cols = p.dual ? 2 * NT : NT, TM_COLS = 2 * acc_cols;
+  const int TAPSW = TAPS + (p.dual ? 1 : 0);   // weight stages per channel chunk
   constexpr int O_ROW = NT * 2;          // bytes of one staged output row (TMA store path, NT <= 64)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* o_s = smem;                                // [2][128 rows][O_ROW] swizzled output tiles (TMA store path)
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
   float* coef = reinterpret_cast<float*>(smem + p.off_coef);
   float* sacc = coef + p.coef_floats;                 // [256] per-tile GroupNorm partial sums
   float* bias_s = sacc + 256;                         // [NT] bias of this CTA's output channels
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + NT);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 2 * NT);   // bias_s[NT..2NT): bias of the fused 1x1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA_MAX + 2 * SB + 4);
   const uint32_t a_full = smem_u32(bars), a_empty = a_full + 8 * SA_MAX, b_full = a_empty + 8 * SA_MAX, b_empty = b_full + 8 * SB,
                  acc_full = b_empty + 8 * SB, acc_empty = acc_full + 16;
@@ -222,7 +225,10 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
     if (p.tma_out) tma_prefetch_desc(&p.map_out);
   }
   for (int i = threadIdx.x; i < 256; i += kThreads) sacc[i] = 0.f;
-  for (int i = threadIdx.x; i < NT; i += kThreads) bias_s[i] = p.bias ? p.bias[blockIdx.y * NT + i] : 0.f;
+  for (int i = threadIdx.x; i < NT; i += kThreads) {
+    bias_s[i] = p.bias ? p.bias[blockIdx.y * NT + i] : 0.f;
+    bias_s[NT + i] = (p.dual && p.bias2) ? p.bias2[blockIdx.y * NT + i] : 0.f;
+  }
   if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), TM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -381,7 +387,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
       }
       mbar_wait(acc_full + 8 * as, (it_tile >> 1) & 1);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * NT);
+      const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)as * acc_cols;
       // TMA store path: the store that read this staging buffer two tiles ago must have finished reading it
       if (NT <= 64 && p.tma_out) {
         if (etid == 0) bulk_wait_group_read<1>();
@@ -393,7 +399,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
         uint32_t r32[32];
         tmem_ld32(trow + j1, r32);
         tmem_ld_wait();
-        if (j1 + 32 == NT) {              // every TMEM read of this thread is complete: hand the stage back
+        if (j1 + 32 == NT && !p.dual) {   // every TMEM read of this thread is complete: hand the stage back
           tc_fence_before();
           mbar_arrive(acc_empty + 8 * as);
         }
@@ -443,6 +449,28 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
           }
         }
       }
+      if (p.dual) {
+        // second accumulator: the 1x1 res_conv of the same input tile (ddpm.py:198,212), direct 16-byte stores
+#pragma unroll 1
+        for (int j1 = 0; j1 < NT; j1 += 32) {
+          uint32_t r32[32];
+          tmem_ld32(trow + NT + j1, r32);
+          tmem_ld_wait();
+          if (j1 + 32 == NT) { tc_fence_before(); mbar_arrive(acc_empty + 8 * as); }
+          if (opix >= 0 && !(p.dbg & 4)) {
+            __nv_bfloat16* o2 = p.dst2 + (size_t)opix * p.Cout + nbase + j1;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                pk[j] = pack_bf16x2(__uint_as_float(r32[8 * c + 2 * j]) + bias_s[NT + j1 + 8 * c + 2 * j],
+                                    __uint_as_float(r32[8 * c + 2 * j + 1]) + bias_s[NT + j1 + 8 * c + 2 * j + 1]);
+              *reinterpret_cast<uint4*>(o2 + 8 * c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        }
+      }
       if (NT <= 64 && p.tma_out) {
         fence_proxy_async();               // my generic-proxy writes are visible to the TMA unit
         named_bar(3, 128);
@@ -476,14 +504,14 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
         const int as = it_tile & 1;
         mbar_wait(acc_empty + 8 * as, ((it_tile >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t dcol = tmem_base + (uint32_t)(as * NT);
+        const uint32_t dcol = tmem_base + (uint32_t)as * acc_cols;
         uint32_t acc = 0;
         for (int c = 0; c < p.nchunks; ++c) {
           mbar_wait(a_full + 8 * ra.s, ra.ph);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + (uint32_t)ra.s * a_stage16;
           if (p.resident) {
-            const uint32_t b_lo = b_lo0 + (uint32_t)(c * TAPS * (B_STAGE >> 4));
+            const uint32_t b_lo = b_lo0 + (uint32_t)(c * TAPSW * (B_STAGE >> 4));
             if (elect_one()) {
               if (!(p.dbg & 2)) {
 #pragma unroll
@@ -496,6 +524,12 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
                     acc = 1;
                   }
                 }
+                if (p.dual) {   // fused 1x1: centre-tap view of the same patch, tenth weight stage, second accumulator
+#pragma unroll
+                  for (int k = 0; k < KC / 16; ++k)
+                    umma_bf16_lh(dcol + NT, a_lo + (uint32_t)(G::PITCH + 1) + (uint32_t)(2 * k) * lbo16, a_hi,
+                                 b_lo + (uint32_t)(TAPS * (B_STAGE >> 4) + 2 * k * NT), b_hi, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                }
               }
               umma_commit(a_empty + 8 * ra.s);
               if (c == p.nchunks - 1) umma_commit(acc_full + 8 * as);
@@ -504,25 +538,33 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
             __syncwarp();
           } else {
 #pragma unroll 1
-            for (int tap = 0; tap < TAPS; ++tap) {
+            for (int tap = 0; tap < TAPSW; ++tap) {
               mbar_wait(b_full + 8 * rb.s, rb.ph);
               tc_fence_after();
               const uint32_t b_lo = b_lo0 + (uint32_t)(rb.s * (B_STAGE >> 4));
-              const int ky = tap / KS, kx = tap - ky * KS;
+              const bool extra = tap == TAPS;   // fused 1x1 on the centre-tap view, second accumulator
+              const int ky = extra ? KS / 2 : tap / KS, kx = extra ? KS / 2 : tap - ky * KS;
               const uint32_t a_t = a_lo + (uint32_t)(ky * G::PITCH + kx);
               if (elect_one()) {
+                if (extra) {
 #pragma unroll
-                for (int k = 0; k < KC / 16; ++k) {
-                  umma_bf16_lh(dcol, a_t + (uint32_t)(2 * k) * lbo16, a_hi, b_lo + (uint32_t)(2 * k * NT), b_hi, idesc, acc);
-                  acc = 1;
+                  for (int k = 0; k < KC / 16; ++k)
+                    umma_bf16_lh(dcol + NT, a_t + (uint32_t)(2 * k) * lbo16, a_hi, b_lo + (uint32_t)(2 * k * NT), b_hi, idesc,
+                                 (c > 0 || k > 0) ? 1u : 0u);
+                } else {
+#pragma unroll
+                  for (int k = 0; k < KC / 16; ++k) {
+                    umma_bf16_lh(dcol, a_t + (uint32_t)(2 * k) * lbo16, a_hi, b_lo + (uint32_t)(2 * k * NT), b_hi, idesc, acc);
+                    acc = 1;
+                  }
                 }
                 umma_commit(b_empty + 8 * rb.s);
-                if (tap == TAPS - 1) {
+                if (tap == TAPSW - 1) {
                   umma_commit(a_empty + 8 * ra.s);
                   if (c == p.nchunks - 1) umma_commit(acc_full + 8 * as);
                 }
               }
-              acc = 1;
+              if (!extra) acc = 1;
               __syncwarp();
               rb.advance(SB);
             }
@@ -534,8 +576,8 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
   } else if (warp == kWWarp) {
     // ================================================================== weight pipeline ===============
     if (lane == 0) {
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)n_tile * p.nchunks * TAPS * B_STAGE;
-      const int total = p.nchunks * TAPS;
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)n_tile * p.nchunks * TAPSW * B_STAGE;
+      const int total = p.nchunks * TAPSW;
       if (p.resident) {
         mbar_arrive_expect_tx(b_full, (uint32_t)total * B_STAGE);
         for (int i = 0; i < total; ++i) bulk_g2s(smem_u32(b_s + (size_t)i * B_STAGE), wsrc + (size_t)i * B_STAGE, B_STAGE, b_full);
@@ -680,13 +722,13 @@ size_t layout(KParams& p, int sa, int nb_stages) {
   p.off_b = (int)off;
   off += (size_t)nb_stages * NT * KC * 2;
   p.off_coef = (int)off;
-  off += (size_t)(p.coef_floats + 256 + NT) * 4 + (2 * SA_MAX + 2 * SB + 4) * 8 + 16;
+  off += (size_t)(p.coef_floats + 256 + 2 * NT) * 4 + (2 * SA_MAX + 2 * SB + 4) * 8 + 16;
   return off;
 }
 
 template <int NT, int KS, int KC>
 int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
-  const int total = p.nchunks * KS * KS;
+  const int total = p.nchunks * (KS * KS + (p.dual ? 1 : 0));
   const size_t limit = (size_t)cfg().max_smem < kResidentBudget ? (size_t)cfg().max_smem : kResidentBudget;
   // weights resident in shared memory when everything fits; more activation stages when fed by TMA
   int sa = p.tma_in ? 4 : 3;
@@ -697,7 +739,7 @@ int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
   if (smem > (size_t)cfg().max_smem) return -1;
   if (p.tma_in && sa == 4) {   // a third co-resident CTA is worth more than a fourth activation stage
     const size_t smem3 = layout<NT, KS, KC>(p, 3, p.nb_stages);
-    if ((size_t)cfg().max_smem_sm / (smem3 + 1024) >= 3 && (size_t)cfg().max_smem_sm / (smem + 1024) < 3 && 512 / (2 * NT) >= 3) { sa = 3; smem = smem3; }
+    if ((size_t)cfg().max_smem_sm / (smem3 + 1024) >= 3 && (size_t)cfg().max_smem_sm / (smem + 1024) < 3 && 512 / ((p.dual ? 4 : 2) * NT) >= 3) { sa = 3; smem = smem3; }
     else layout<NT, KS, KC>(p, sa, p.nb_stages);
   }
   p.sa = sa;
@@ -705,7 +747,7 @@ int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
   const bool lean = p.tma_in != 0;
   int occ = (int)((size_t)cfg().max_smem_sm / (smem + 1024));
   if (occ > (lean ? 3 : 2)) occ = lean ? 3 : 2;
-  const int tm = 512 / (2 * NT);
+  const int tm = 512 / ((p.dual ? 4 : 2) * NT);
   if (occ > tm) occ = tm;
   if (occ < 1) occ = 1;
   int gx = cfg().sms * occ / ntiles_y;
@@ -777,8 +819,11 @@ static int pick_ntile(int Cout) {
   return 0;
 }
 
-int conv_tc_pack(const float* w, const float* bias, int Cin, int Cout, int ks, int stride, int pad, ConvTcW* out) {
+int conv_tc_pack(const float* w, const float* bias, int Cin, int Cout, int ks, int stride, int pad, ConvTcW* out, const float* w1,
+                 const float* bias1) {
   out->ready = false;
+  out->dual = false; out->bias2 = nullptr;
+  if (w1 && ks != 3) return 0;
   if (!((ks == 3 && pad == 1) || (ks == 1 && pad == 0)) || stride != 1) return 0;
   const int nt = pick_ntile(Cout);
   if (!nt || Cin % 32) return 0;
@@ -791,16 +836,17 @@ int conv_tc_pack(const float* w, const float* bias, int Cin, int Cout, int ks, i
     *slot = nullptr;
     if (Cin % kc) continue;
     const int nch = Cin / kc, ntiles = Cout / nt;
-    std::vector<__nv_bfloat16> pk((size_t)Cin * Cout * taps);
+    const int tapsw = taps + (w1 ? 1 : 0);   // dual: stage `taps` of every chunk holds the 1x1 weights
+    std::vector<__nv_bfloat16> pk((size_t)Cin * Cout * tapsw);
     for (int nti = 0; nti < ntiles; ++nti)
       for (int c = 0; c < nch; ++c)
-        for (int t = 0; t < taps; ++t)
+        for (int t = 0; t < tapsw; ++t)
           for (int k8 = 0; k8 < kc / 8; ++k8)
             for (int n = 0; n < nt; ++n)
               for (int e = 0; e < 8; ++e) {
                 const int cin = c * kc + k8 * 8 + e, co = nti * nt + n;
-                const size_t dst = (((((size_t)nti * nch + c) * taps + t) * (kc / 8) + k8) * nt + n) * 8 + e;
-                pk[dst] = __float2bfloat16_rn(w[((size_t)t * Cin + cin) * Cout + co]);
+                const size_t dst = (((((size_t)nti * nch + c) * tapsw + t) * (kc / 8) + k8) * nt + n) * 8 + e;
+                pk[dst] = __float2bfloat16_rn(t < taps ? w[((size_t)t * Cin + cin) * Cout + co] : w1[(size_t)cin * Cout + co]);
               }
     if (cudaMalloc(slot, pk.size() * 2) != cudaSuccess) return -1;
     if (cudaMemcpy(*slot, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
@@ -809,6 +855,13 @@ int conv_tc_pack(const float* w, const float* bias, int Cin, int Cout, int ks, i
   if (bias) {
     if (cudaMalloc(&out->bias, Cout * sizeof(float)) != cudaSuccess) return -1;
     if (cudaMemcpy(out->bias, bias, Cout * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+  }
+  if (w1) {
+    out->dual = true;
+    if (bias1) {
+      if (cudaMalloc(&out->bias2, Cout * sizeof(float)) != cudaSuccess) return -1;
+      if (cudaMemcpy(out->bias2, bias1, Cout * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+    }
   }
   if (ks == 3) { if (configure_nt<3, 64>(nt) || configure_nt<3, 32>(nt)) return -1; }
   else { if (configure_nt<1, 64>(nt) || configure_nt<1, 32>(nt)) return -1; }
@@ -821,6 +874,8 @@ bool conv_tc_supports(const ConvTcW& w, const ConvTcArgs& a) {
   if (a.ds) return w.ks == 1 && w.Cin == 4 * a.C0 && a.C0 % 32 == 0 && !a.src1 && !a.up && !a.pro_ab && !a.stats && !a.res &&
                   a.Hin == 2 * a.H && a.Win == 2 * a.W && encode_fn() != nullptr;
   if (a.C0 + a.C1 != w.Cin || a.C0 % 32 || a.C1 % 32) return false;
+  if (w.dual != (a.dst2 != nullptr)) return false;
+  if (w.dual && (w.ks != 3 || w.ntile > 64 || w.Cout != w.ntile || a.up || a.res)) return false;   // 4 NT TMEM columns, two CTAs per SM
   if (a.up && (w.ks != 3 || a.src1)) return false;
   if (a.pro_ab && (w.ks != 3 || a.src1 || a.up)) return false;
   if (a.stats) {
@@ -846,6 +901,7 @@ static bool build_params(const ConvTcW& w, const ConvTcArgs& a, KParams& p) {
   p.nchunks = w.Cin / kc;
   p.w = (const __nv_bfloat16*)(k64 ? w.w : w.w32); p.bias = w.bias; p.Cout = w.Cout;
   p.dst = (__nv_bfloat16*)a.dst; p.res = (const __nv_bfloat16*)a.res;
+  p.dst2 = (__nv_bfloat16*)a.dst2; p.bias2 = w.bias2; p.dual = w.dual ? 1 : 0;
   p.M = (long long)a.N * a.H * a.W;
   p.pro_ab = a.pro_ab; p.pro_act = a.pro_act;
   p.coef_floats = 0;
@@ -877,7 +933,7 @@ int conv_tc_launch(const ConvTcW& w, const ConvTcArgs& a, cudaStream_t s) {
   struct Cached { KParams p; bool k64; };
   static std::unordered_map<std::string, Cached> cache;
   std::string key(reinterpret_cast<const char*>(&a), sizeof(ConvTcArgs));
-  const void* wk[3] = {w.w, w.w32, w.bias};
+  const void* wk[4] = {w.w, w.w32, w.bias, w.bias2};
   key.append(reinterpret_cast<const char*>(wk), sizeof wk);
   auto it = cache.find(key);
   if (it == cache.end()) {

@@ -13,6 +13,10 @@ struct ConvTcW {
   void* w = nullptr;     // bf16, [n_tile][cchunk][tap][kc/8][ntile][8] with kc = 64 (null if Cin % 64)
   void* w32 = nullptr;   // same with kc = 32 (used when a concat source is not a multiple of 64 channels)
   float* bias = nullptr; // fp32 [Cout] or null
+  // dual packing: every channel chunk carries a tenth stage, the 1x1 res_conv (ddpm.py:198) of the same input, whose
+  // product with the centre-tap view goes to a second accumulator and a second output tensor (ConvTcArgs::dst2)
+  bool dual = false;
+  float* bias2 = nullptr;
 };
 
 struct ConvTcArgs {
@@ -24,6 +28,7 @@ struct ConvTcArgs {
   int ds = 0;                  // pixel-unshuffle down-sampling (ddpm.py:122): weights packed as a 1x1 over (p1, p2, c); Hin = 2H
   void* dst = nullptr;         // bf16 [N,H,W,Cout]
   const void* res = nullptr;   // optional bf16 residual added in the epilogue
+  void* dst2 = nullptr;        // dual weights only: bf16 [N,H,W,Cout] output of the fused 1x1 convolution
   // fused "normalise on load" prologue on src0 (3x3, single source, no up-sampling):
   //   x' = act(a[n,c] * x + b[n,c]) with the GroupNorm (+FiLM) coefficients of gn_coef_launch  (ddpm.py:174-185, unet_model.py:21-22)
   const float* pro_ab = nullptr;       // [N][2][C0] (scale, shift) or null
@@ -33,7 +38,9 @@ struct ConvTcArgs {
 };
 
 // host: pack fp32 [taps][Cin][Cout] weights; leaves `ready == false` for unsupported shapes
-int conv_tc_pack(const float* w_tap_cin_cout, const float* bias, int Cin, int Cout, int ks, int stride, int pad, ConvTcW* out);
+// `w_1x1` ([Cin][Cout]) / `bias_1x1`: optional 1x1 convolution of the same input fused as a second output (3x3 only)
+int conv_tc_pack(const float* w_tap_cin_cout, const float* bias, int Cin, int Cout, int ks, int stride, int pad, ConvTcW* out,
+                 const float* w_1x1 = nullptr, const float* bias_1x1 = nullptr);
 bool conv_tc_supports(const ConvTcW& w, const ConvTcArgs& a);
 // GroupNorm statistics {sum, sumsq}[N][G][2] (+ optional per-image FiLM [2C] scale, shift) -> coefficient table [N][2][C]
 int gn_coef_launch(const double* stats, const float* gamma, const float* beta, const float* film, int film_stride, int G, int C, int N,

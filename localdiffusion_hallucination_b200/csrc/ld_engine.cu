@@ -61,7 +61,7 @@ struct ConvW {
   ConvTcW tc;             // bf16 tcgen05 packing (empty in fp32 mode)
 };
 
-struct ResW { ConvW c1, c2, res; bool has_res = false, has_film = false; int film_off = 0; float *g1, *b1, *g2, *b2; int Cin, Cout; };
+struct ResW { ConvW c1, c2, res; ConvTcW c1_dual; bool has_res = false, has_film = false; int film_off = 0; float *g1, *b1, *g2, *b2; int Cin, Cout; };
 struct AttnW { bool full; int C; float* g; ConvW qkv; ConvW out; float* g2 = nullptr; LinAttnTcW la; };
 struct CondW { ConvW a, b, id; float *ga, *ba, *gb, *bb, *gi, *bi; int Cin, Cmid, Cout; };
 
@@ -294,6 +294,20 @@ static int pack_res(Engine& E, const std::string& p, bool film, std::vector<floa
   r.Cin = r.c1.Cin; r.Cout = r.c1.Cout;
   r.has_res = has(E, p + ".res_conv.weight");
   if (r.has_res && (rc = pack_conv(E, p + ".res_conv", true, false, &r.res))) return rc;
+  if (r.has_res && E.use_tc && r.c1.tc.ready && r.c1.tc.ntile <= 64 && r.c1.Cout == r.c1.tc.ntile) {
+    // block1.proj and res_conv read the same input (ddpm.py:207,212): one launch, two accumulators (ConvTcW::dual)
+    const WSpec& w3 = W(E, p + ".block1.proj.weight"); const WSpec& w1 = W(E, p + ".res_conv.weight");
+    const int co = r.c1.Cout, ci = r.c1.Cin;
+    std::vector<float> p3((size_t)9 * ci * co), p1((size_t)ci * co);
+    for (int o = 0; o < co; ++o)
+      for (int c = 0; c < ci; ++c) {
+        for (int t = 0; t < 9; ++t) p3[((size_t)t * ci + c) * co + o] = w3.host[((size_t)o * ci + c) * 9 + t];
+        p1[(size_t)c * co + o] = w1.host[(size_t)o * ci + c];
+      }
+    if (conv_tc_pack(p3.data(), W(E, p + ".block1.proj.bias").host.data(), ci, co, 3, 1, 1, &r.c1_dual, p1.data(),
+                     W(E, p + ".res_conv.bias").host.data()))
+      return fail(LD_ERR_CUDA, "conv_tc_pack(dual %s) failed", p.c_str());
+  }
   if ((rc = vecp(E, p + ".block1.norm.weight", &r.g1))) return rc;
   if ((rc = vecp(E, p + ".block1.norm.bias", &r.b1))) return rc;
   if ((rc = vecp(E, p + ".block2.norm.weight", &r.g2))) return rc;
@@ -514,6 +528,26 @@ struct Builder {
     if (stats_off && !stats_fused) stats_into(o, stats_G, stats_off);
     return o;
   }
+  // block1.proj (3x3, GroupNorm statistics of its output) and res_conv (1x1) of the same input in one launch
+  bool conv_dual(const ConvTcW& w, const Ten& a, const Ten* b, double* stats_off, int stats_G, Ten* o1, Ten* o2) {
+    if (!E.use_tc || !w.ready || !w.dual) return false;
+    ConvTcArgs ta;
+    ta.src0 = a.p; ta.C0 = a.C; ta.src1 = b ? b->p : nullptr; ta.C1 = b ? b->C : 0;
+    ta.N = a.N; ta.H = a.H; ta.W = a.W; ta.Hin = a.H; ta.Win = a.W;
+    ta.stats = (double*)8; ta.stats_G = stats_G; ta.dst2 = (void*)8;
+    if (!conv_tc_supports(w, ta)) return false;
+    *o1 = act(a.N, a.H, a.W, w.Cout);
+    *o2 = act(a.N, a.H, a.W, w.Cout);
+    if (err) return true;
+    ta.dst = o1->p; ta.dst2 = o2->p; ta.stats = nullptr;
+    const ConvTcW* wp = &w; Plan* pp = &P; const size_t st_off = (size_t)stats_off;
+    op([ta, wp, pp, st_off](cudaStream_t s) {
+      ConvTcArgs q = ta;
+      q.stats = (double*)((char*)pp->zero_arena + st_off);
+      return conv_tc_launch(*wp, q, s);
+    });
+    return true;
+  }
   Ten conv_same(const ConvW& cw, const Ten& a, const Ten* b = nullptr, const Ten* resid = nullptr,
                 const ProSpec* pro = nullptr, double* stats_off = nullptr, int stats_G = 0) {
     return conv(cw, a, b, false, resid, a.H, a.W, pro, stats_off, stats_G);
@@ -553,14 +587,16 @@ struct Builder {
     const ResW& r = E.res[E.res_index.at(name)];
     const int G = E.d.resnet_groups;
     double* s1 = stats_alloc(a.N, G);
-    Ten h1 = conv_same(r.c1, a, b, nullptr, nullptr, s1, G);
+    Ten h1, rs;
+    const bool dual = r.has_res && conv_dual(r.c1_dual, a, b, s1, G, &h1, &rs);
+    if (!dual) h1 = conv_same(r.c1, a, b, nullptr, nullptr, s1, G);
     ProSpec pr{s1, r.g1, r.b1, G, r.has_film ? r.film_off : -1, 1};
     double* s2 = stats_alloc(a.N, G);
     Ten h2 = conv_same(r.c2, h1, nullptr, nullptr, &pr, s2, G);
     release(h1);
     Ten o;
     if (r.has_res) {
-      Ten rs = conv_same(r.res, a, b);
+      if (!dual) rs = conv_same(r.res, a, b);
       o = gn_apply(h2, s2, r.g2, r.b2, G, -1, 1, &rs, 1);
       release(rs);
     } else {
@@ -1316,6 +1352,43 @@ int ld_debug_conv_fused(const float* x0, int C0, int N, int H, int W, const floa
   cudaError_t e = cudaStreamSynchronize(s);
   cudaFree(tw.w); cudaFree(tw.w32); cudaFree(tw.bias); cudaFree(a0); cudaFree(ao); cudaFree(abd);
   if (e != cudaSuccess) return fail(LD_ERR_CUDA, "debug fused conv failed: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+// 3x3 tcgen05 convolution of the virtual concat [x0 | x1] with GroupNorm statistics, fused with the 1x1 convolution of
+// the same input as a second output: ResnetBlock block1.proj + res_conv (ddpm.py:207,212) (test hook).
+int ld_debug_conv_dual(const float* x0, int C0, const float* x1, int C1, int N, int H, int W, const float* w3_host,
+                       const float* b3_host, const float* w1_host, const float* b1_host, int Cout, double* stats_out, int stats_G,
+                       float* out, float* out2, void* stream) {
+  if (ld_device_count() == 0) return fail(LD_ERR_NO_DEVICE, "no sm_100 CUDA device is available (there is no CPU fallback)");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int Cin = C0 + C1;
+  std::vector<float> p3((size_t)9 * Cin * Cout), p1((size_t)Cin * Cout);
+  for (int o = 0; o < Cout; ++o)
+    for (int c = 0; c < Cin; ++c) {
+      for (int t = 0; t < 9; ++t) p3[((size_t)t * Cin + c) * Cout + o] = w3_host[((size_t)o * Cin + c) * 9 + t];
+      p1[(size_t)c * Cout + o] = w1_host[(size_t)o * Cin + c];
+    }
+  const size_t npx = (size_t)N * H * W;
+  void *a0 = nullptr, *a1 = nullptr, *ao = nullptr, *ao2 = nullptr;
+  CK(cudaMalloc(&a0, npx * C0 * 2)); launch_convert(x0, false, a0, true, (long long)npx * C0, s);
+  if (C1) { CK(cudaMalloc(&a1, npx * C1 * 2)); launch_convert(x1, false, a1, true, (long long)npx * C1, s); }
+  CK(cudaMalloc(&ao, npx * Cout * 2)); CK(cudaMalloc(&ao2, npx * Cout * 2));
+  CK(cudaMemsetAsync(stats_out, 0, (size_t)N * stats_G * 2 * sizeof(double), s));
+  ConvTcW tw;
+  int rc = 0;
+  if (conv_tc_pack(p3.data(), b3_host, Cin, Cout, 3, 1, 1, &tw, p1.data(), b1_host) || !tw.ready)
+    rc = fail(LD_ERR_INVALID, "conv_tc_pack: unsupported shape");
+  else {
+    ConvTcArgs ta; ta.src0 = a0; ta.C0 = C0; ta.src1 = a1; ta.C1 = C1; ta.N = N; ta.H = H; ta.W = W; ta.Hin = H; ta.Win = W;
+    ta.dst = ao; ta.dst2 = ao2; ta.stats = stats_out; ta.stats_G = stats_G;
+    if (conv_tc_launch(tw, ta, s) < 0) rc = fail(LD_ERR_INVALID, "conv_tc_launch: unsupported arguments");
+  }
+  launch_convert(ao, true, out, false, (long long)npx * Cout, s);
+  launch_convert(ao2, true, out2, false, (long long)npx * Cout, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  cudaFree(tw.w); cudaFree(tw.w32); cudaFree(tw.bias); cudaFree(tw.bias2); cudaFree(a0); cudaFree(a1); cudaFree(ao); cudaFree(ao2);
+  if (e != cudaSuccess) return fail(LD_ERR_CUDA, "debug dual conv failed: %s", cudaGetErrorString(e));
   return rc;
 }
 

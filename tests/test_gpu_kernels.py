@@ -128,6 +128,48 @@ def test_conv_fused_groupnorm_prologue_and_stats(case):
         assert float(((got[..., 1] - want[..., 1]).abs() / want[..., 1]).max()) < 5e-3
 
 
+# (C0, C1, Cout, N, H, W, stats_G)
+DUAL_CASES = [
+    (32, 32, 32, 2, 32, 32, 8),     # up-path ResnetBlock(64 -> 32): virtual concat of two 32-channel sources
+    (64, 32, 64, 1, 20, 12, 8),     # ResnetBlock(96 -> 64), ragged tiles, KC = 32 packing
+    (64, 0, 32, 3, 16, 24, 8),      # single source, KC = 64
+    (64, 64, 64, 37, 16, 8, 8),     # many images per persistent CTA
+]
+
+
+@pytest.mark.parametrize("case", DUAL_CASES)
+def test_conv_dual_block1_and_res_conv(case):
+    """block1.proj + GroupNorm statistics and res_conv of the same input from one launch (ddpm.py:207,212)."""
+    C0, C1, Cout, N, H, W, sG = case
+    lib = _lib.lib()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(C0 + 3 * C1 + 5 * Cout + H)
+    Cin = C0 + C1
+    x = (torch.randn(N, H, W, Cin, generator=g) * 1.3 + 0.2).bfloat16().float()
+    w3 = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    w1 = torch.randn(Cout, Cin, generator=g) / Cin ** 0.5
+    b3, b1 = torch.randn(Cout, generator=g), torch.randn(Cout, generator=g)
+    xc = x.permute(0, 3, 1, 2).double()
+    ref = F.conv2d(xc, w3.bfloat16().double(), b3.double(), padding=1).permute(0, 2, 3, 1)
+    ref2 = F.conv2d(xc, w1.bfloat16().double()[:, :, None, None], b1.double()).permute(0, 2, 3, 1)
+    x0 = x[..., :C0].contiguous().to(dev)
+    x1 = x[..., C0:].contiguous().to(dev) if C1 else None
+    out, out2 = torch.empty(N, H, W, Cout, device=dev), torch.empty(N, H, W, Cout, device=dev)
+    stats = torch.full((N, sG, 2), 7.0, dtype=torch.float64, device=dev)
+    rc = lib.ld_debug_conv_dual(x0.data_ptr(), C0, x1.data_ptr() if C1 else None, C1, N, H, W, w3.contiguous().data_ptr(),
+                                b3.data_ptr(), w1.contiguous().data_ptr(), b1.data_ptr(), Cout, stats.data_ptr(), sG,
+                                out.data_ptr(), out2.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc)
+    assert util.rel_err(out, ref) < 4e-3
+    assert util.rel_err(out2, ref2) < 4e-3
+    rg = ref.view(N, H * W, sG, Cout // sG)
+    want = torch.stack([rg.sum(dim=(1, 3)), (rg * rg).sum(dim=(1, 3))], dim=-1)
+    got = stats.cpu()
+    scale = want[..., 1].sqrt().unsqueeze(-1) * (H * W * (Cout // sG)) ** 0.5
+    assert float(((got[..., 0] - want[..., 0]).abs() / scale[..., 0]).max()) < 2e-3
+    assert float(((got[..., 1] - want[..., 1]).abs() / want[..., 1]).max()) < 5e-3
+
+
 # (C, N, HW)
 LINATTN_CASES = [(32, 2, 1024), (64, 1, 784), (128, 2, 256), (32, 3, 4096), (64, 5, 1000)]
 
