@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libld_sampler.so")
+# LD_SAMPLER_LIB: development override (A/B builds of the same ABI); the product path is the in-tree library
+LIB_PATH = os.path.abspath(os.environ["LD_SAMPLER_LIB"]) if os.environ.get("LD_SAMPLER_LIB") else os.path.join(_HERE, "libld_sampler.so")
 LD_MAX_LEVELS = 8
 
 LD_OK, LD_ERR_INVALID, LD_ERR_NO_DEVICE, LD_ERR_CUDA, LD_ERR_STATE, LD_ERR_KEY, LD_ERR_MASK = 0, -1, -2, -3, -4, -5, -6

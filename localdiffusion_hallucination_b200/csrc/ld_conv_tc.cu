@@ -46,18 +46,27 @@ using namespace tc;
 
 namespace {
 
+#ifndef LD_CONV_MX
+#define LD_CONV_MX 0                   // merged-x geometry for 3x3 / 32-cout layers (see Geo): parity-green, not faster yet (epilogue bound); -DLD_CONV_MX=1 for A/B builds
+#endif
+#ifndef LD_CONV_EG
+#define LD_CONV_EG 2                   // epilogue warp-groups of the lean kernel (alternate tiles)
+#endif
+constexpr bool kUseMX = LD_CONV_MX != 0;
 constexpr int kTeamThreads = 128;      // one producer team = 4 warps
 constexpr int kTeams = 2;
 // Warp roles.  Full kernel (register-staging producers): warps 0-7 producers, 8-11 epilogue, 12 MMA, 13 weights.
-// Lean kernel (TMA activation loads only): warp 0 TMA, 1 MMA, 2 weights, 4-7 epilogue -- 8 warps, so three CTAs
-// fit an SM and overlap each other's per-tile hand-shake chains.
+// Lean kernel (TMA activation loads only): warp 0 TMA, 1 MMA, 2 weights, 4-7 and 8-11 two epilogue warp-groups that
+// drain alternate tiles (one accumulator stage each): a tile's epilogue is a ~1.4 k-clock dependent instruction chain of
+// one warp per TMEM lane quarter (measured with LD_CONV_DBG=7), so what counts is how many of them run per SM.
 template <bool LEAN> struct Roles {
   static constexpr int kProdWarps = LEAN ? 1 : 8;
-  static constexpr int kEpiWarp0 = LEAN ? 4 : 8;       // four warps, warp % 4 == TMEM lane quarter
+  static constexpr int kEpiWarp0 = LEAN ? 4 : 8;       // warp % 4 == TMEM lane quarter
+  static constexpr int kEpiGroups = LEAN ? LD_CONV_EG : 1;   // epilogue warp-groups; group g drains accumulator stage g
   static constexpr int kMmaWarp = LEAN ? 1 : 12;
   static constexpr int kWWarp = LEAN ? 2 : 13;
-  static constexpr int kThreads = LEAN ? 8 * 32 : 14 * 32;
-  static constexpr int kMinCtas = LEAN ? 3 : 2;
+  static constexpr int kThreads = LEAN ? (4 + 4 * kEpiGroups) * 32 : 14 * 32;
+  static constexpr int kMinCtas = LEAN ? (kEpiGroups == 2 ? 2 : 3) : 2;
 };
 constexpr int SA_MAX = 6;              // activation stages (runtime: 3..6)
 constexpr int SB = 4;                  // weight stages (streaming mode)
@@ -90,17 +99,22 @@ struct alignas(64) KParams {
   int dbg;   // development aid (env LD_CONV_DBG): 1 no activation loads, 2 no MMAs, 4 no output stores
 };
 
-template <int KS, int KC>
+// MX ("merged x", 3x3 with 32 output channels): D[128, 32] tiles make every MMA read 4 KB of A for 1 KB of B, and the
+// tensor pipe is bound by those shared-memory operand reads.  MX widens N to 96 = (kx, cout): the three horizontal taps
+// share one A view, a tile is 8 rows x 16 patch columns (14 outputs + the 2 halo columns, so the 128 MMA rows are one
+// linear run of patch pixels) and only the three vertical taps are issued as shifted views; the epilogue combines
+// out[c] = D[c][kx=0] + D[c+1][kx=1] + D[c+2][kx=2] with two warp shuffles per channel.  A reads drop 3x.
+template <int KS, int KC, bool MX = false>
 struct Geo {
-  static constexpr int TH = KS == 3 ? 16 : 1;
-  static constexpr int TW = KS == 3 ? 8 : 128;
+  static constexpr int TH = KS == 3 ? (MX ? 8 : 16) : 1;
+  static constexpr int TW = KS == 3 ? (MX ? 14 : 8) : 128;
   static constexpr int PITCH = TW + KS - 1;
   static constexpr int HPIX = (TH + KS - 1) * PITCH;                   // staged pixels per chunk
   static constexpr int CH = KC / 8;                                    // 16-byte channel groups per pixel
   static constexpr int LBO_REG = ((HPIX * 16 + 127) / 128) * 128 + 16; // register path: == 16 (mod 128), conflict-free stores
   static constexpr int LBO_TMA = HPIX * 16;                            // TMA path: dense box image
   static constexpr int ITEMS = (HPIX * CH + kTeamThreads - 1) / kTeamThreads;
-  static constexpr int SBO = (KS == 3 ? PITCH : 8) * 16;               // stride between 8-pixel core-matrix groups
+  static constexpr int SBO = MX ? 128 : (KS == 3 ? PITCH : 8) * 16;    // stride between 8-pixel core-matrix groups
 };
 
 // walks tile = blockIdx.x + k * gridDim.x and keeps its (image, tile row, tile column) without integer divisions
@@ -193,22 +207,25 @@ __device__ __forceinline__ void stats_chunk(const float (&f)[16], bool valid, fl
 
 template <int NT, int KS, int KC, bool LEAN>
 __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) conv_tc_kernel(const __grid_constant__ KParams p) {
-  using G = Geo<KS, KC>;
+  constexpr bool MX = kUseMX && KS == 3 && NT == 32;
+  using G = Geo<KS, KC, MX>;
   using R = Roles<LEAN>;
   constexpr int kThreads = R::kThreads, kEpiWarp0 = R::kEpiWarp0, kMmaWarp = R::kMmaWarp, kWWarp = R::kWWarp;
-  constexpr int TAPS = KS * KS;
-  constexpr int B_STAGE = NT * KC * 2;
+  constexpr int TAPS = MX ? 3 : KS * KS;  // MMA taps per channel chunk (MX: vertical taps only)
+  constexpr int NMMA = MX ? 3 * NT : NT;  // UMMA N
+  constexpr int B_STAGE = NMMA * KC * 2;
   // two accumulator stages of NT (dual: 2 NT) fp32 columns; NT in {32,64,128,256} -> power of two >= 64
-  const uint32_t acc_cols = p.dual ? 2 * NT : NT, TM_COLS = 2 * acc_cols;
+  const uint32_t acc_cols = MX ? 4 * NT : (p.dual ? 2 * NT : NT), TM_COLS = 2 * acc_cols;   // MX: 96 + 32 (fused 1x1)
   const int TAPSW = TAPS + (p.dual ? 1 : 0);   // weight stages per channel chunk
   constexpr int O_ROW = NT * 2;          // bytes of one staged output row (TMA store path, NT <= 64)
+  constexpr int DUALC = MX ? 3 * NT : NT; // first TMEM column of the fused-1x1 accumulator inside a stage
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* o_s = smem;                                // [2][128 rows][O_ROW] swizzled output tiles (TMA store path)
   uint8_t* a_s = smem + p.off_a;
   uint8_t* b_s = smem + p.off_b;
   float* coef = reinterpret_cast<float*>(smem + p.off_coef);
-  float* sacc = coef + p.coef_floats;                 // [256] per-tile GroupNorm partial sums
-  float* bias_s = sacc + 256;                         // [NT] bias of this CTA's output channels
+  float* sacc_all = coef + p.coef_floats;             // [2][256] GroupNorm partial sums of each epilogue warp-group
+  float* bias_s = sacc_all + 512;                         // [NT] bias of this CTA's output channels
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 2 * NT);   // bias_s[NT..2NT): bias of the fused 1x1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA_MAX + 2 * SB + 4);
   const uint32_t a_full = smem_u32(bars), a_empty = a_full + 8 * SA_MAX, b_full = a_empty + 8 * SA_MAX, b_empty = b_full + 8 * SB,
@@ -224,7 +241,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
     if (p.tma_in) { tma_prefetch_desc(&p.map_a0); if (p.C1) tma_prefetch_desc(&p.map_a1); }
     if (p.tma_out) tma_prefetch_desc(&p.map_out);
   }
-  for (int i = threadIdx.x; i < 256; i += kThreads) sacc[i] = 0.f;
+  for (int i = threadIdx.x; i < 512; i += kThreads) sacc_all[i] = 0.f;
   for (int i = threadIdx.x; i < NT; i += kThreads) {
     bias_s[i] = p.bias ? p.bias[blockIdx.y * NT + i] : 0.f;
     bias_s[NT + i] = (p.dual && p.bias2) ? p.bias2[blockIdx.y * NT + i] : 0.f;
@@ -346,9 +363,13 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
         }
       }
     }
-  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4 * R::kEpiGroups) {
     // ================================================================== epilogue ======================
-    const int ew = warp - kEpiWarp0, etid = threadIdx.x - kEpiWarp0 * 32;
+    // warp-group eg drains the tiles whose accumulator stage is eg (every tile when there is one group)
+    const int eg = (warp - kEpiWarp0) >> 2;
+    const int ew = warp & 3, etid = threadIdx.x - (kEpiWarp0 + 4 * eg) * 32;
+    const int ebar = 3 + eg;                           // named barrier of this warp-group
+    float* sacc = sacc_all + 256 * eg;
     const int m = ew * 32 + lane;
     const int nbase = n_tile * NT;
     const int cpg = p.stats ? p.Cout / p.stats_G : 1;
@@ -360,7 +381,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
     // atomic per (group, statistic), when the walk leaves the image
     int stat_img = -1;
     auto flush_stats = [&](int im) {
-      named_bar(3, 128);
+      named_bar(ebar, 128);
       const int ng2 = 2 * (NT / cpg > 0 ? NT / cpg : 1);
       if (etid < ng2) {
         const float v = sacc[etid];
@@ -368,17 +389,21 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
         const int gi = nbase / cpg + (etid >> 1);
         atomicAdd(p.stats + ((size_t)im * p.stats_G + gi) * 2 + (etid & 1), (double)v);
       }
-      named_bar(3, 128);
+      named_bar(ebar, 128);
     };
     for (; tw.tile < tw.end; tw.next(p), ++it_tile) {
       const int as = it_tile & 1;
+      if (R::kEpiGroups == 2 && as != eg) continue;
       const int img = tw.img;
       if (p.stats && img != stat_img) {
         if (stat_img >= 0) flush_stats(stat_img);
         stat_img = img;
       }
       long long opix = -1;
-      if (tile2d) {
+      if (MX) {
+        const int gy = tw.ty * G::TH + (m >> 4), gx = tw.tx * G::TW + (m & 15);
+        if ((m & 15) < G::TW && gy < p.H && gx < p.W) opix = ((long long)img * p.H + gy) * p.W + gx;
+      } else if (tile2d) {
         const int gy = tw.ty * 16 + (m >> 3), gx = tw.tx * 8 + (m & 7);
         if (gy < p.H && gx < p.W) opix = ((long long)img * p.H + gy) * p.W + gx;
       } else {
@@ -390,28 +415,46 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
       const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)as * acc_cols;
       // TMA store path: the store that read this staging buffer two tiles ago must have finished reading it
       if (NT <= 64 && p.tma_out) {
-        if (etid == 0) bulk_wait_group_read<1>();
-        named_bar(3, 128);
+        if (etid == 0) { if (R::kEpiGroups == 2) bulk_wait_group_read<0>(); else bulk_wait_group_read<1>(); }
+        named_bar(ebar, 128);
       }
-      uint8_t* orow = o_s + (size_t)as * (128 * O_ROW) + (size_t)m * O_ROW;
+      // staged output row: MX tiles are 8 x 14 pixels dense (patch columns 14, 15 of every row produce nothing)
+      const int orow_i = MX ? (m >> 4) * G::TW + (m & 15) : m;
+      uint8_t* orow = o_s + (size_t)as * (128 * O_ROW) + (size_t)orow_i * O_ROW;
 #pragma unroll 1
       for (int j1 = 0; j1 < NT; j1 += 32) {
         uint32_t r32[32];
-        tmem_ld32(trow + j1, r32);
-        tmem_ld_wait();
-        if (j1 + 32 == NT && !p.dual) {   // every TMEM read of this thread is complete: hand the stage back
-          tc_fence_before();
-          mbar_arrive(acc_empty + 8 * as);
+        if (!MX) {
+          tmem_ld32(trow + j1, r32);
+          tmem_ld_wait();
+          if (j1 + 32 == NT && !p.dual) {   // every TMEM read of this thread is complete: hand the stage back
+            tc_fence_before();
+            mbar_arrive(acc_empty + 8 * as);
+          }
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int j0 = j1 + 16 * h;
           float f[16];
+          if (MX) {
+            // out[lane] = D[lane][kx=0] + D[lane+1][kx=1] + D[lane+2][kx=2]: neighbours along the patch row are the next lanes
+            uint32_t a0[16], a1[16], a2[16];
+            tmem_ld16(trow + j0, a0);
+            tmem_ld16(trow + NT + j0, a1);
+            tmem_ld16(trow + 2 * NT + j0, a2);
+            tmem_ld_wait();
+            if (h == 1 && !p.dual) { tc_fence_before(); mbar_arrive(acc_empty + 8 * as); }
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j0 + j);
-            f[j] = __uint_as_float(r32[16 * h + j]) + b4.x; f[j + 1] = __uint_as_float(r32[16 * h + j + 1]) + b4.y;
-            f[j + 2] = __uint_as_float(r32[16 * h + j + 2]) + b4.z; f[j + 3] = __uint_as_float(r32[16 * h + j + 3]) + b4.w;
+            for (int j = 0; j < 16; ++j)
+              f[j] = __uint_as_float(a0[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(a1[j]), 1) +
+                     __shfl_down_sync(0xffffffffu, __uint_as_float(a2[j]), 2) + bias_s[j0 + j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j0 + j);
+              f[j] = __uint_as_float(r32[16 * h + j]) + b4.x; f[j + 1] = __uint_as_float(r32[16 * h + j + 1]) + b4.y;
+              f[j + 2] = __uint_as_float(r32[16 * h + j + 2]) + b4.z; f[j + 3] = __uint_as_float(r32[16 * h + j + 3]) + b4.w;
+            }
           }
           if (p.stats) {
             const int grp0 = (nbase + j0) / cpg - nbase / cpg;
@@ -439,9 +482,11 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
           if (NT <= 64 && p.tma_out) {
             // 16-byte chunk index XOR row bits = the TMA 64B / 128B swizzle pattern: conflict-free row-per-thread stores
             const int c0 = j0 >> 3;
-            const int sw = NT == 32 ? ((m >> 1) & 3) : (m & 7);
-            *reinterpret_cast<uint4*>(orow + ((c0 ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(orow + (((c0 + 1) ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            const int sw = NT == 32 ? ((orow_i >> 1) & 3) : (orow_i & 7);
+            if (!MX || (m & 15) < G::TW) {
+              *reinterpret_cast<uint4*>(orow + ((c0 ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(orow + (((c0 + 1) ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
           } else if (opix >= 0 && !(p.dbg & 4)) {
             const size_t o = (size_t)opix * p.Cout + nbase + j0;
             *reinterpret_cast<uint4*>(p.dst + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -454,7 +499,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
 #pragma unroll 1
         for (int j1 = 0; j1 < NT; j1 += 32) {
           uint32_t r32[32];
-          tmem_ld32(trow + NT + j1, r32);
+          tmem_ld32(trow + DUALC + j1, r32);
           tmem_ld_wait();
           if (j1 + 32 == NT) { tc_fence_before(); mbar_arrive(acc_empty + 8 * as); }
           if (opix >= 0 && !(p.dbg & 4)) {
@@ -473,11 +518,12 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
       }
       if (NT <= 64 && p.tma_out) {
         fence_proxy_async();               // my generic-proxy writes are visible to the TMA unit
-        named_bar(3, 128);
+        named_bar(ebar, 128);
         if (etid == 0) {
           if (!(p.dbg & 4)) {
             const uint32_t src = smem_u32(o_s + (size_t)as * (128 * O_ROW));
-            if (tile2d) tma_store_4d(&p.map_out, nbase, tw.tx * 8, tw.ty * 16, img, src);
+            if (MX) tma_store_4d(&p.map_out, nbase, tw.tx * G::TW, tw.ty * G::TH, img, src);
+            else if (tile2d) tma_store_4d(&p.map_out, nbase, tw.tx * 8, tw.ty * 16, img, src);
             else tma_store_2d(&p.map_out, nbase, tw.tile * 128, src);
             bulk_commit_group();
           }
@@ -491,10 +537,11 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
     // The whole warp runs the loop (barrier waits); one elected lane issues tcgen05.mma / commit.  Descriptors
     // are (lo, hi) register pairs and every tap / k-step only adds a small constant to `lo`.
     {
-      constexpr uint32_t idesc = make_idesc(128, NT);
+      constexpr uint32_t idesc = make_idesc(128, NMMA), idesc_d = make_idesc(128, NT);
       const uint32_t a_hi = desc_hi(G::SBO), b_hi = desc_hi(128);
       const uint32_t lbo16 = (uint32_t)p.lbo16;
-      const uint32_t a_lo0 = desc_lo(smem_u32(a_s), lbo16 << 4), b_lo0 = desc_lo(smem_u32(b_s), NT * 16);
+      const uint32_t a_lo0 = desc_lo(smem_u32(a_s), lbo16 << 4), b_lo0 = desc_lo(smem_u32(b_s), NMMA * 16),
+                     bd_lo0 = desc_lo(smem_u32(b_s), NT * 16);   // fused-1x1 stage: [kc/8][NT][8] at the head of its slot
       const uint32_t a_stage16 = (uint32_t)p.a_stage >> 4;
       Ring ra, rb;
       int it_tile = 0;
@@ -516,19 +563,20 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
               if (!(p.dbg & 2)) {
 #pragma unroll
                 for (int tap = 0; tap < TAPS; ++tap) {
-                  const int ky = tap / KS, kx = tap - ky * KS;
+                  const int ky = MX ? tap : tap / KS, kx = MX ? 0 : tap - ky * KS;
 #pragma unroll
                   for (int k = 0; k < KC / 16; ++k) {
                     umma_bf16_lh(dcol, a_lo + (uint32_t)(ky * G::PITCH + kx) + (uint32_t)(2 * k) * lbo16, a_hi,
-                                 b_lo + (uint32_t)(tap * (B_STAGE >> 4) + 2 * k * NT), b_hi, idesc, acc);
+                                 b_lo + (uint32_t)(tap * (B_STAGE >> 4) + 2 * k * NMMA), b_hi, idesc, acc);
                     acc = 1;
                   }
                 }
-                if (p.dual) {   // fused 1x1: centre-tap view of the same patch, tenth weight stage, second accumulator
+                if (p.dual) {   // fused 1x1: centre-tap view of the same patch, last weight stage, second accumulator
+                  const uint32_t bd_lo = bd_lo0 + (uint32_t)((c * TAPSW + TAPS) * (B_STAGE >> 4));
 #pragma unroll
                   for (int k = 0; k < KC / 16; ++k)
-                    umma_bf16_lh(dcol + NT, a_lo + (uint32_t)(G::PITCH + 1) + (uint32_t)(2 * k) * lbo16, a_hi,
-                                 b_lo + (uint32_t)(TAPS * (B_STAGE >> 4) + 2 * k * NT), b_hi, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                    umma_bf16_lh(dcol + DUALC, a_lo + (uint32_t)(G::PITCH + 1) + (uint32_t)(2 * k) * lbo16, a_hi,
+                                 bd_lo + (uint32_t)(2 * k * NT), b_hi, idesc_d, (c > 0 || k > 0) ? 1u : 0u);
                 }
               }
               umma_commit(a_empty + 8 * ra.s);
@@ -543,18 +591,19 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
               tc_fence_after();
               const uint32_t b_lo = b_lo0 + (uint32_t)(rb.s * (B_STAGE >> 4));
               const bool extra = tap == TAPS;   // fused 1x1 on the centre-tap view, second accumulator
-              const int ky = extra ? KS / 2 : tap / KS, kx = extra ? KS / 2 : tap - ky * KS;
+              const int ky = extra ? KS / 2 : (MX ? tap : tap / KS), kx = extra ? KS / 2 : (MX ? 0 : tap - ky * KS);
               const uint32_t a_t = a_lo + (uint32_t)(ky * G::PITCH + kx);
               if (elect_one()) {
                 if (extra) {
+                  const uint32_t bd_lo = bd_lo0 + (uint32_t)(rb.s * (B_STAGE >> 4));
 #pragma unroll
                   for (int k = 0; k < KC / 16; ++k)
-                    umma_bf16_lh(dcol + NT, a_t + (uint32_t)(2 * k) * lbo16, a_hi, b_lo + (uint32_t)(2 * k * NT), b_hi, idesc,
+                    umma_bf16_lh(dcol + DUALC, a_t + (uint32_t)(2 * k) * lbo16, a_hi, bd_lo + (uint32_t)(2 * k * NT), b_hi, idesc_d,
                                  (c > 0 || k > 0) ? 1u : 0u);
                 } else {
 #pragma unroll
                   for (int k = 0; k < KC / 16; ++k) {
-                    umma_bf16_lh(dcol, a_t + (uint32_t)(2 * k) * lbo16, a_hi, b_lo + (uint32_t)(2 * k * NT), b_hi, idesc, acc);
+                    umma_bf16_lh(dcol, a_t + (uint32_t)(2 * k) * lbo16, a_hi, b_lo + (uint32_t)(2 * k * NMMA), b_hi, idesc, acc);
                     acc = 1;
                   }
                 }
@@ -671,7 +720,7 @@ bool map_in_1x1(CUtensorMap* m, const void* ptr, long long M, int C, int kc) {
            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // output [N][H][W][Cout]: box (NT, 8, 16, 1) (3x3) or [M][Cout]: box (NT, 128) (1x1), 64B / 128B swizzle for NT = 32 / 64
-bool map_out(CUtensorMap* m, void* ptr, int N, int H, int W, int Cout, int nt, int ks) {
+bool map_out(CUtensorMap* m, void* ptr, int N, int H, int W, int Cout, int nt, int ks, bool mx = false) {
   EncodeTiledFn f = encode_fn();
   if (!f || (nt != 32 && nt != 64)) return false;
   const CUtensorMapSwizzle sw = nt == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
@@ -679,7 +728,7 @@ bool map_out(CUtensorMap* m, void* ptr, int N, int H, int W, int Cout, int nt, i
   if (ks == 3) {
     const cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t strides[3] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)nt, 8, 16, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)nt, mx ? 14u : 8u, mx ? 8u : 16u, 1};   // MX tiles: 8 rows x 14 pixels
     return f(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   }
@@ -710,7 +759,8 @@ int configure_nt(int NT) {
 // shared memory carve-up; returns total bytes
 template <int NT, int KS, int KC>
 size_t layout(KParams& p, int sa, int nb_stages) {
-  using G = Geo<KS, KC>;
+  constexpr bool MX = kUseMX && KS == 3 && NT == 32;
+  using G = Geo<KS, KC, MX>;
   size_t off = 0;
   if (p.tma_out) off += 2 * 128 * NT * 2;                      // output staging (1024-byte aligned, first)
   p.off_a = (int)off;
@@ -720,15 +770,17 @@ size_t layout(KParams& p, int sa, int nb_stages) {
   off += (size_t)sa * p.a_stage;
   off = (off + 127) & ~(size_t)127;
   p.off_b = (int)off;
-  off += (size_t)nb_stages * NT * KC * 2;
+  off += (size_t)nb_stages * (MX ? 3 * NT : NT) * KC * 2;
   p.off_coef = (int)off;
-  off += (size_t)(p.coef_floats + 256 + 2 * NT) * 4 + (2 * SA_MAX + 2 * SB + 4) * 8 + 16;
+  off += (size_t)(p.coef_floats + 512 + 2 * NT) * 4 + (2 * SA_MAX + 2 * SB + 4) * 8 + 16;
   return off;
 }
 
 template <int NT, int KS, int KC>
 int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
-  const int total = p.nchunks * (KS * KS + (p.dual ? 1 : 0));
+  constexpr bool MX = kUseMX && KS == 3 && NT == 32;
+  const int total = p.nchunks * ((MX ? 3 : KS * KS) + (p.dual ? 1 : 0));
+  const int tm_cols = MX ? 8 * NT : (p.dual ? 4 : 2) * NT;   // TMEM columns per CTA (two accumulator stages)
   const size_t limit = (size_t)cfg().max_smem < kResidentBudget ? (size_t)cfg().max_smem : kResidentBudget;
   // weights resident in shared memory when everything fits; more activation stages when fed by TMA
   int sa = p.tma_in ? 4 : 3;
@@ -739,15 +791,17 @@ int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
   if (smem > (size_t)cfg().max_smem) return -1;
   if (p.tma_in && sa == 4) {   // a third co-resident CTA is worth more than a fourth activation stage
     const size_t smem3 = layout<NT, KS, KC>(p, 3, p.nb_stages);
-    if ((size_t)cfg().max_smem_sm / (smem3 + 1024) >= 3 && (size_t)cfg().max_smem_sm / (smem + 1024) < 3 && 512 / ((p.dual ? 4 : 2) * NT) >= 3) { sa = 3; smem = smem3; }
+    const size_t want = (size_t)Roles<true>::kMinCtas;   // co-resident CTAs the launch bounds allow
+    if ((size_t)cfg().max_smem_sm / (smem3 + 1024) >= want && (size_t)cfg().max_smem_sm / (smem + 1024) < want && (size_t)(512 / tm_cols) >= want) { sa = 3; smem = smem3; }
     else layout<NT, KS, KC>(p, sa, p.nb_stages);
   }
   p.sa = sa;
   // persistent grid: as many CTAs as are co-resident (registers allow two per SM; 2*NT of 512 TMEM columns each)
   const bool lean = p.tma_in != 0;
   int occ = (int)((size_t)cfg().max_smem_sm / (smem + 1024));
-  if (occ > (lean ? 3 : 2)) occ = lean ? 3 : 2;
-  const int tm = 512 / ((p.dual ? 4 : 2) * NT);
+  const int occ_max = lean ? Roles<true>::kMinCtas : Roles<false>::kMinCtas;
+  if (occ > occ_max) occ = occ_max;
+  const int tm = 512 / tm_cols;
   if (occ > tm) occ = tm;
   if (occ < 1) occ = 1;
   int gx = cfg().sms * occ / ntiles_y;
@@ -836,18 +890,32 @@ int conv_tc_pack(const float* w, const float* bias, int Cin, int Cout, int ks, i
     *slot = nullptr;
     if (Cin % kc) continue;
     const int nch = Cin / kc, ntiles = Cout / nt;
-    const int tapsw = taps + (w1 ? 1 : 0);   // dual: stage `taps` of every chunk holds the 1x1 weights
-    std::vector<__nv_bfloat16> pk((size_t)Cin * Cout * tapsw);
+    // MX (3x3, 32 couts): a stage is one vertical tap with N = (kx, cout) = 96 rows; else one (ky, kx) tap with nt rows.
+    // dual: the last stage of every chunk holds the 1x1 weights as [kc/8][nt][8] at the head of a full-size slot.
+    const bool mx = kUseMX && ks == 3 && nt == 32;
+    const int mtaps = mx ? 3 : taps, nrow = mx ? 3 * nt : nt;
+    const int tapsw = mtaps + (w1 ? 1 : 0);
+    const size_t slot_elems = (size_t)nrow * kc;
+    std::vector<__nv_bfloat16> pk((size_t)ntiles * nch * tapsw * slot_elems, __float2bfloat16_rn(0.f));
     for (int nti = 0; nti < ntiles; ++nti)
       for (int c = 0; c < nch; ++c)
-        for (int t = 0; t < tapsw; ++t)
+        for (int t = 0; t < tapsw; ++t) {
+          const size_t base = (((size_t)nti * nch + c) * tapsw + t) * slot_elems;
+          const bool extra = t == mtaps;
+          const int rows = extra ? nt : nrow;
           for (int k8 = 0; k8 < kc / 8; ++k8)
-            for (int n = 0; n < nt; ++n)
+            for (int r = 0; r < rows; ++r)
               for (int e = 0; e < 8; ++e) {
-                const int cin = c * kc + k8 * 8 + e, co = nti * nt + n;
-                const size_t dst = (((((size_t)nti * nch + c) * tapsw + t) * (kc / 8) + k8) * nt + n) * 8 + e;
-                pk[dst] = __float2bfloat16_rn(t < taps ? w[((size_t)t * Cin + cin) * Cout + co] : w1[(size_t)cin * Cout + co]);
+                const int cin = c * kc + k8 * 8 + e, co = nti * nt + (r % nt);
+                float v;
+                if (extra) v = w1[(size_t)cin * Cout + co];
+                else {
+                  const int tap = mx ? t * 3 + r / nt : t;   // MX: stage = ky, row block = kx
+                  v = w[((size_t)tap * Cin + cin) * Cout + co];
+                }
+                pk[base + ((size_t)k8 * rows + r) * 8 + e] = __float2bfloat16_rn(v);
               }
+        }
     if (cudaMalloc(slot, pk.size() * 2) != cudaSuccess) return -1;
     if (cudaMemcpy(*slot, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
   }
@@ -894,6 +962,7 @@ long long* conv_tc_trace() { return nullptr; }
 static bool build_params(const ConvTcW& w, const ConvTcArgs& a, KParams& p) {
   const bool k64 = w.w && a.C0 % 64 == 0 && a.C1 % 64 == 0;
   const int kc = k64 ? 64 : 32;
+  const bool mx = kUseMX && w.ks == 3 && w.ntile == 32;   // merged-x geometry (see Geo): 8 x 14 output tiles
   p = KParams{};
   p.ds = a.ds; p.ds_cs = a.C0;
   p.src0 = (const __nv_bfloat16*)a.src0; p.src1 = (const __nv_bfloat16*)a.src1; p.C0 = a.C0; p.C1 = a.C1;
@@ -912,13 +981,16 @@ static bool build_params(const ConvTcW& w, const ConvTcArgs& a, KParams& p) {
   if (a.ds) {
     p.tma_in = map_in_ds(&p.map_a0, a.src0, a.N, a.Hin, a.Win, a.C0, kc) ? 1 : 0;
   } else if (!a.up && !a.pro_ab) {
-    bool ok = w.ks == 3 ? map_in_3x3(&p.map_a0, a.src0, a.N, a.Hin, a.Win, a.C0, kc, 10, 18) : map_in_1x1(&p.map_a0, a.src0, p.M, a.C0, kc);
+    bool ok = w.ks == 3 ? map_in_3x3(&p.map_a0, a.src0, a.N, a.Hin, a.Win, a.C0, kc, mx ? 16 : 10, mx ? 10 : 18) : map_in_1x1(&p.map_a0, a.src0, p.M, a.C0, kc);
     if (ok && a.src1)
-      ok = w.ks == 3 ? map_in_3x3(&p.map_a1, a.src1, a.N, a.Hin, a.Win, a.C1, kc, 10, 18) : map_in_1x1(&p.map_a1, a.src1, p.M, a.C1, kc);
+      ok = w.ks == 3 ? map_in_3x3(&p.map_a1, a.src1, a.N, a.Hin, a.Win, a.C1, kc, mx ? 16 : 10, mx ? 10 : 18) : map_in_1x1(&p.map_a1, a.src1, p.M, a.C1, kc);
     p.tma_in = ok ? 1 : 0;
   }
-  p.tma_out = map_out(&p.map_out, a.dst, a.N, a.H, a.W, w.Cout, w.ntile, a.ds ? 3 : w.ks) ? 1 : 0;
-  if (w.ks == 3 || a.ds) {
+  p.tma_out = map_out(&p.map_out, a.dst, a.N, a.H, a.W, w.Cout, w.ntile, a.ds ? 3 : w.ks, mx) ? 1 : 0;
+  if (mx) {
+    p.tiles_x = (a.W + 13) / 14; p.tiles_y = (a.H + 7) / 8;
+    p.ntiles = a.N * p.tiles_x * p.tiles_y;
+  } else if (w.ks == 3 || a.ds) {
     p.tiles_x = (a.W + 7) / 8; p.tiles_y = (a.H + 15) / 16;
     p.ntiles = a.N * p.tiles_x * p.tiles_y;
   } else {

@@ -1,8 +1,14 @@
+"""One isolated conv timing (development aid).  env: LD_SAMPLER_LIB (alternative library), LD_CONV_DBG.
+usage: gpu_conv_one.py [C0 C1 HW Cout ks up N]"""
 import ctypes as C, os, sys
 import torch
 sys.path.insert(0, ".")
 from localdiffusion_hallucination_b200 import _lib
+if os.environ.get("LD_SAMPLER_LIB"):
+    _lib.LIB_PATH = os.path.abspath(os.environ["LD_SAMPLER_LIB"])
 lib = _lib.lib(); torch.zeros(1, device="cuda")
+a = [int(v) for v in sys.argv[1:]] or [32, 0, 256, 32, 3, 0, 32]
+c0, c1, hw, co, ks, up, N = a
 ms = C.c_float(0)
-lib.ld_debug_conv_time(2, 32, 0, 32, 256, 256, 0, 32, 3, 3, C.byref(ms), None)
-print(f"dbg={os.environ.get('LD_CONV_DBG','0')}: {ms.value*1000:.1f} us")
+rc = lib.ld_debug_conv_time(2, c0, c1, N, hw, hw, up, co, ks, 10, C.byref(ms), None)
+print(f"lib={os.path.basename(_lib.LIB_PATH)} dbg={os.environ.get('LD_CONV_DBG','0')} C{c0}+{c1}->{co} k{ks} @{hw} up{up} N={N}: {ms.value*1000:.1f} us rc={rc}")
