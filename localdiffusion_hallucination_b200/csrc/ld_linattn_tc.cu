@@ -115,7 +115,18 @@ struct XStage {
 };
 
 // the producer loop shared by both passes: stage i covers pixels [(first + i) * ROWS, +ROWS) of one image
-template <int C, int ROWS, int XS, bool WITH_T>
+// EXT (pass A): two more 8-channel chunks behind the C/8 real ones: channel C is 1 for pixels that exist (0 past the end of
+// the image), channels C+1 .. C+15 are 0.  MMA1 uses it to add the per-row soft-max shift, MMA2 to sum P over pixels.
+template <int ROWS>
+__device__ __forceinline__ void write_ext(uint8_t* stage, int chunks, int valid, int tid) {
+  if (tid < 2 * ROWS) {
+    const int which = tid / ROWS, p = tid - which * ROWS;
+    const uint32_t one = (which == 0 && p < valid) ? 0x3F80u : 0u;   // bf16 1.0 in element 0
+    *reinterpret_cast<uint4*>(stage + (size_t)(chunks + which) * (ROWS * 16) + p * 16) = make_uint4(one, 0u, 0u, 0u);
+  }
+}
+
+template <int C, int ROWS, int XS, bool WITH_T, bool EXT = false>
 __device__ __forceinline__ void produce_x(const __nv_bfloat16* __restrict__ ximg, int first, int count, int HW, uint8_t* x_s,
                                           int x_stage_bytes, uint32_t x_full, uint32_t x_empty, int tid, int lane) {
   using X = XStage<C, ROWS>;
@@ -131,6 +142,7 @@ __device__ __forceinline__ void produce_x(const __nv_bfloat16* __restrict__ ximg
         const int s = i % XS;
         mbar_wait(x_empty + 8 * s, ((i / XS) & 1) ^ 1);
         fifo[d].template store<WITH_T>(x_s + (size_t)s * x_stage_bytes, tid);
+        if (EXT) write_ext<ROWS>(x_s + (size_t)s * x_stage_bytes, C / 8, HW - (first + i) * ROWS, tid);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(x_full + 8 * s);
@@ -143,7 +155,7 @@ __device__ __forceinline__ void produce_x(const __nv_bfloat16* __restrict__ ximg
 // Same producer fed by the bulk-copy engine: a stage of x is ROWS*C*2 contiguous bytes in global memory, so one lane
 // issues cp.async.bulk copies RS stages ahead into a raw ring (no registers, no scoreboards tied up: the register
 // FIFO above cannot keep more than ~6 load batches in flight per warp), and the four warps normalise smem -> smem.
-template <int C, int ROWS, int XS, int RS>
+template <int C, int ROWS, int XS, int RS, bool EXT = false>
 __device__ __forceinline__ void produce_x_raw(const __nv_bfloat16* __restrict__ ximg, int first, int count, int HW, uint8_t* x_s,
                                               int x_stage_bytes, uint32_t x_full, uint32_t x_empty, uint8_t* raw_s, uint32_t raw_full,
                                               uint32_t raw_empty, int tid, int lane) {
@@ -190,6 +202,7 @@ __device__ __forceinline__ void produce_x_raw(const __nv_bfloat16* __restrict__ 
       for (int j = 0; j < 4; ++j) o4[j] = pack_bf16x2(f[2 * j] * inv, f[2 * j + 1] * inv);
       *reinterpret_cast<uint4*>(stage + (size_t)c8 * (ROWS * 16) + p * 16) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
     }
+    if (EXT) write_ext<ROWS>(stage, C / 8, valid, tid);
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) { mbar_arrive(x_full + 8 * s); mbar_arrive(raw_empty + 8 * slot); }
@@ -201,25 +214,30 @@ __device__ __forceinline__ void produce_x_raw(const __nv_bfloat16* __restrict__ 
 // ================================================================================================
 template <int C>
 struct CtxCfg {
-  static constexpr int XS = C >= 128 ? 6 : 8;         // xhat stages: released only after MMA2, ~4 half tiles after MMA1
-  static constexpr int X_STAGE = 64 * C * 2;          // xhat [C/8][64 px][16 B]: K-major for MMA1, MN-major for MMA2
-  static constexpr int W_BYTES = 128 * C * 2;
+  static constexpr int CE = C + 16;                   // channels incl. the ones / zero extension (see write_ext)
+  static constexpr int CTAS = C >= 128 ? 1 : 2;       // co-resident CTAs per SM (C <= 64: 256 TMEM columns and < 113 KB each)
+  static constexpr int NB = C >= 128 ? 4 : 2;         // K^T (TMEM) and P (smem) buffers: NB / 2 per transform warp-group
+  static constexpr int LOGNB = C >= 128 ? 2 : 1;
+  static constexpr int XS = C >= 128 ? 6 : (C >= 64 ? 5 : 6);   // xhat stages: released only after MMA2
+  static constexpr int X_STAGE = 64 * CE * 2;         // xhat [CE/8][64 px][16 B]: K-major for MMA1, MN-major for MMA2
+  static constexpr int W_BYTES = 128 * CE * 2;
   static constexpr int P_BYTES = 128 * 64 * 2;        // one P buffer
-  static constexpr int NB = 4;                        // K^T (TMEM) and P (smem) buffers: two per transform warp-group
-  static constexpr int RS = C >= 128 ? 0 : 4;         // raw x ring fed by cp.async.bulk (C = 128: register FIFO, smem is full)
-  static constexpr int SMEM = W_BYTES + XS * X_STAGE + NB * P_BYTES + RS * X_STAGE + 128 * 4 + 48 * 8 + 16;
+  static constexpr int RS = C >= 128 ? 0 : (C >= 64 ? 2 : 3);   // raw x ring fed by cp.async.bulk (C = 128: register FIFO)
+  static constexpr int RAW_STAGE = 64 * C * 2;
+  static constexpr int ZCOL = NB * 64;                // TMEM: K^T buffer b at b*64 (64 pixels each); Z at ZCOL .. ZCOL+CE
+  static constexpr int TMEM_COLS = C >= 128 ? 512 : 256;
+  static constexpr int SMEM = W_BYTES + XS * X_STAGE + NB * P_BYTES + RS * RAW_STAGE + 48 * 8 + 16;
 };
 
 template <int C>
-__global__ void __launch_bounds__(kThreads, 1) la_ctx_kernel(const CtxParams p) {
+__global__ void __launch_bounds__(kThreads, CtxCfg<C>::CTAS) la_ctx_kernel(const CtxParams p) {
   using K = CtxCfg<C>;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* w_s = smem;
   uint8_t* x_s = w_s + K::W_BYTES;
   uint8_t* p_s = x_s + K::XS * K::X_STAGE;            // [buffer][128 rows (h,d)][64 px]
   uint8_t* raw_s = p_s + K::NB * K::P_BYTES;
-  float* kb_s = reinterpret_cast<float*>(raw_s + K::RS * K::X_STAGE);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(kb_s + 128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw_s + K::RS * K::RAW_STAGE);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 48);
   const uint32_t w_full = smem_u32(bars), x_full = w_full + 8, x_empty = x_full + 64, d1_full = x_empty + 64,
                  d1_empty = d1_full + 32, p_full = d1_empty + 32, p_empty = p_full + 32, z_full = p_empty + 32,
@@ -234,22 +252,21 @@ __global__ void __launch_bounds__(kThreads, 1) la_ctx_kernel(const CtxParams p) 
     mbar_init(w_full, 1);
     for (int i = 0; i < K::XS; ++i) { mbar_init(x_full + 8 * i, 4); mbar_init(x_empty + 8 * i, 1); }
     for (int i = 0; i < K::NB; ++i) {
-      mbar_init(d1_full + 8 * i, 1); mbar_init(d1_empty + 8 * i, 128);
-      mbar_init(p_full + 8 * i, 128); mbar_init(p_empty + 8 * i, 1);
+      mbar_init(d1_full + 8 * i, 1); mbar_init(d1_empty + 8 * i, 4);
+      mbar_init(p_full + 8 * i, 4); mbar_init(p_empty + 8 * i, 1);
     }
     mbar_init(z_full, 1);
     for (int i = 0; i < K::RS; ++i) { mbar_init(raw_full + 8 * i, 1); mbar_init(raw_empty + 8 * i, 4); }
     fence_barrier_init();
   }
-  if (threadIdx.x < 128) kb_s[threadIdx.x] = p.kb2[threadIdx.x];
-  if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), K::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: K^T buffer b at b*64 (64 pixels each);  Z at 256 .. 256+C
+  // TMEM columns: K^T buffer b at b*64 (64 pixels each);  Z at ZCOL .. ZCOL+C, its column C = sum of P over pixels (ksum)
   if (nh <= 0) {
-    if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, K::TMEM_COLS);
     return;
   }
 
@@ -257,10 +274,10 @@ __global__ void __launch_bounds__(kThreads, 1) la_ctx_kernel(const CtxParams p) 
     // ---------------------------------------------------------------- producers ------------------
     const __nv_bfloat16* ximg = p.x + (size_t)n * p.HW * C;
     if constexpr (K::RS > 0)
-      produce_x_raw<C, 64, K::XS, (K::RS > 0 ? K::RS : 1)>(ximg, h0, nh, p.HW, x_s, K::X_STAGE, x_full, x_empty, raw_s, raw_full, raw_empty,
-                                                          threadIdx.x, lane);
+      produce_x_raw<C, 64, K::XS, (K::RS > 0 ? K::RS : 1), true>(ximg, h0, nh, p.HW, x_s, K::X_STAGE, x_full, x_empty, raw_s, raw_full,
+                                                                raw_empty, threadIdx.x, lane);
     else
-      produce_x<C, 64, K::XS, false>(ximg, h0, nh, p.HW, x_s, K::X_STAGE, x_full, x_empty, threadIdx.x, lane);
+      produce_x<C, 64, K::XS, false, true>(ximg, h0, nh, p.HW, x_s, K::X_STAGE, x_full, x_empty, threadIdx.x, lane);
   } else if (warp == kMmaWarp) {
     // ---------------------------------------------------------------- MMA issue ------------------
     // The whole warp runs the loop (barrier waits), one elected lane issues tcgen05.mma / commit.  MMA1 runs NB
@@ -274,19 +291,19 @@ __global__ void __launch_bounds__(kThreads, 1) la_ctx_kernel(const CtxParams p) 
     tc_fence_after();
     // MMA2 reads xhat as an MN-major B operand (N = channels contiguous in 16-byte groups, K = pixels at 16 B stride):
     // the same shared-memory image MMA1 reads K-major, no transposed copy.  idesc bit 16 = B is MN-major.
-    constexpr uint32_t idesc1 = make_idesc(128, 64), idesc2 = make_idesc(128, C) | (1u << 16);
+    constexpr uint32_t idesc1 = make_idesc(128, 64), idesc2 = make_idesc(128, K::CE) | (1u << 16);
     const uint32_t hi128 = desc_hi(128), hi_xt = desc_hi(64 * 16);
     const uint32_t w_lo = desc_lo(smem_u32(w_s), 2048), x_lo0 = desc_lo(smem_u32(x_s), 1024), xt_lo0 = desc_lo(smem_u32(x_s), 128),
                    p_lo0 = desc_lo(smem_u32(p_s), 2048);
     auto mma1 = [&](int i) {            // K^T(i) = W'_k . xhat(i)^T
       const int s = i % K::XS, b = i & (K::NB - 1);
       mbar_wait(x_full + 8 * s, (i / K::XS) & 1);
-      mbar_wait(d1_empty + 8 * b, ((i >> 2) & 1) ^ 1);
+      mbar_wait(d1_empty + 8 * b, ((i >> K::LOGNB) & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t x_lo = x_lo0 + (uint32_t)(s * (K::X_STAGE >> 4));
 #pragma unroll
-        for (int k = 0; k < C / 16; ++k)
+        for (int k = 0; k < K::CE / 16; ++k)   // the last k-step multiplies the ones channel with the (negative) row shift
           umma_bf16_lh(tmem_base + (uint32_t)(b * 64), w_lo + (uint32_t)(2 * k * 128), hi128, x_lo + (uint32_t)(2 * k * 64), hi128, idesc1,
                        k > 0 ? 1u : 0u);
         umma_commit(d1_full + 8 * b);
@@ -296,13 +313,13 @@ __global__ void __launch_bounds__(kThreads, 1) la_ctx_kernel(const CtxParams p) 
     for (int i = 0; i < K::NB && i < nh; ++i) mma1(i);
     for (int j = 0; j < nh; ++j) {      // Z += P(j) . xhat(j)
       const int b = j & (K::NB - 1), sj = j % K::XS;
-      mbar_wait(p_full + 8 * b, (j >> 2) & 1);
+      mbar_wait(p_full + 8 * b, (j >> K::LOGNB) & 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t p_lo = p_lo0 + (uint32_t)(b * (K::P_BYTES >> 4)), xt_lo = xt_lo0 + (uint32_t)(sj * (K::X_STAGE >> 4));
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // K = 64 pixels = 4 x 16
-          umma_bf16_lh(tmem_base + 256u, p_lo + (uint32_t)(2 * k * 128), hi128, xt_lo + (uint32_t)(k * 16), hi_xt, idesc2,
+          umma_bf16_lh(tmem_base + (uint32_t)K::ZCOL, p_lo + (uint32_t)(2 * k * 128), hi128, xt_lo + (uint32_t)(k * 16), hi_xt, idesc2,
                        (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(p_empty + 8 * b);
         umma_commit(x_empty + 8 * sj);
@@ -316,43 +333,44 @@ __global__ void __launch_bounds__(kThreads, 1) la_ctx_kernel(const CtxParams p) 
     // ---------------------------------------------------------------- transform ------------------
     const int q = warp & 3, g = (warp - kXfWarp0) >> 2;      // TMEM lane quarter, warp-group (alternate half tiles)
     const int r = q * 32 + lane;                             // row (h,d)
-    const float mb = kb_s[r];
-    float ksum = 0.f;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int i = g; i < nh; i += 2) {
       const int b = i & (K::NB - 1);
-      const uint32_t par = (uint32_t)(i >> 2) & 1u;
-      const int nvalid = p.HW - (h0 + i) * 64;               // valid pixel columns of this half tile
+      const uint32_t par = (uint32_t)(i >> K::LOGNB) & 1u;
       uint8_t* pbuf = p_s + (size_t)b * K::P_BYTES + r * 16;
       mbar_wait(d1_full + 8 * b, par);
       tc_fence_after();
-      mbar_wait(p_empty + 8 * b, par ^ 1);                   // MMA2 of half tile i - 4 has consumed this P buffer
+      // K^T arrives as log2(e) * k - shift_d (log2 e folded into W'_k, the shift added by MMA1 through the ones channel), so
+      // the weight is one ex2 per element; its sum over pixels comes back from MMA2 (ones channel again): no FMA, no adds.
+      // Pixels past the end of the image have xhat = 0 and ones = 0: their weight 2^0 multiplies zeros.
+      uint32_t kr0[32], kr1[32];
+      tmem_ld32(lane_base + (uint32_t)(b * 64), kr0);
+      tmem_ld32(lane_base + (uint32_t)(b * 64 + 32), kr1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d1_empty + 8 * b);
+      mbar_wait(p_empty + 8 * b, par ^ 1);                   // MMA2 of the tile that last used this P buffer has consumed it
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint32_t kr[32];
-        tmem_ld32(lane_base + (uint32_t)(b * 64 + c0), kr);
-        tmem_ld_wait();
-        if (c0 == 32) { tc_fence_before(); mbar_arrive(d1_empty + 8 * b); }
-        uint32_t pk[16];
+      for (int c = 0; c < 4; ++c) {     // chunks of 8 pixels along K
+        uint32_t pk[4];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float e0 = ex2_approx(fmaf(__uint_as_float(kr[2 * j]), kLog2e, -mb));
-          float e1 = ex2_approx(fmaf(__uint_as_float(kr[2 * j + 1]), kLog2e, -mb));
-          if (nvalid < 64) {     // ragged last tile of the image: pixels past the end carry no weight
-            if (c0 + 2 * j >= nvalid) e0 = 0.f;
-            if (c0 + 2 * j + 1 >= nvalid) e1 = 0.f;
-          }
-          pk[j] = pack_bf16x2(e0, e1);
-          ksum += e0 + e1;
-        }
+        for (int j = 0; j < 4; ++j)
+          pk[j] = pack_bf16x2(ex2_approx(__uint_as_float(kr0[8 * c + 2 * j])), ex2_approx(__uint_as_float(kr0[8 * c + 2 * j + 1])));
+        *reinterpret_cast<uint4*>(pbuf + (size_t)c * 2048) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
 #pragma unroll
-        for (int c = 0; c < 4; ++c)   // chunks of 8 pixels along K
-          *reinterpret_cast<uint4*>(pbuf + (size_t)(c0 / 8 + c) * 2048) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          pk[j] = pack_bf16x2(ex2_approx(__uint_as_float(kr1[8 * c + 2 * j])), ex2_approx(__uint_as_float(kr1[8 * c + 2 * j + 1])));
+        *reinterpret_cast<uint4*>(pbuf + (size_t)(4 + c) * 2048) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       fence_proxy_async();
-      mbar_arrive(p_full + 8 * b);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full + 8 * b);
     }
-    atomicAdd(p.ksum + (size_t)n * 128 + r, ksum);
     if (g == 0) {
       mbar_wait(z_full, 0);
       tc_fence_after();
@@ -360,16 +378,20 @@ __global__ void __launch_bounds__(kThreads, 1) la_ctx_kernel(const CtxParams p) 
 #pragma unroll 1
       for (int c0 = 0; c0 < C; c0 += 32) {
         uint32_t zr[32];
-        tmem_ld32(lane_base + 256u + (uint32_t)c0, zr);
+        tmem_ld32(lane_base + (uint32_t)(K::ZCOL + c0), zr);
         tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 32; ++e) atomicAdd(dst + c0 + e, __uint_as_float(zr[e]));
       }
+      uint32_t ks[16];
+      tmem_ld16(lane_base + (uint32_t)(K::ZCOL + C), ks);
+      tmem_ld_wait();
+      atomicAdd(p.ksum + (size_t)n * 128 + r, __uint_as_float(ks[0]));
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, K::TMEM_COLS);
 }
 
 // ================================================================================================
@@ -678,7 +700,7 @@ int launch_c(const LinAttnTcW& w, const LinAttnTcArgs& a, cudaStream_t s) {
   // slices per image: ONE wave of CTAs (each owns all 512 TMEM columns of its SM), at least 4 half tiles per CTA
   const int HT = (a.HW + 63) / 64, NTL = (a.HW + 127) / 128;
   int sl = sms() / a.N; if (sl < 1) sl = 1;
-  int slA = sl; if (slA > HT / 4) slA = HT / 4; if (slA < 1) slA = 1;
+  int slA = CtxCfg<C>::CTAS * sms() / a.N; if (slA > HT / 4) slA = HT / 4; if (slA < 1) slA = 1;
   int slB = sl; if (slB > NTL / 2) slB = NTL / 2; if (slB < 1) slB = 1;
   CtxParams cp{(const __nv_bfloat16*)a.x, (const __nv_bfloat16*)w.wk, w.kb2, a.Z, a.ksum, a.HW, slA};
   la_ctx_kernel<C><<<dim3(slA, a.N), kThreads, CtxCfg<C>::SMEM, s>>>(cp);
@@ -710,13 +732,18 @@ int linattn_tc_pack(const float* wqkv, const float* g, const float* wout, const 
   };
   std::vector<__nv_bfloat16> q, k;
   pack_rows(0, 1, q, 1.4426950408889634f);   // q rows carry log2(e): the soft-max over d uses ex2 directly
-  pack_rows(128, 1, k);
+  pack_rows(128, 1, k, 1.4426950408889634f);  // k rows carry log2(e) as well
+  // Soft-max over the pixel axis is shift invariant: row d is shifted by the analytic bound |k'_d| <= |W'_k[d,:]| * |xhat|
+  // (|xhat| <= 1 + 2^-8).  The (bf16) negative bound sits in the weight of the ones channel the producers append to xhat
+  // (two extra 8-channel chunks: [C/8] = {-bound, 0 x 7}, [C/8 + 1] = 0), so MMA1 delivers k' - bound directly.
   std::vector<float> kb(128);
+  k.resize((size_t)(C / 8 + 2) * 128 * 8, __float2bfloat16_rn(0.f));
   for (int r = 0; r < 128; ++r) {
     double ss = 0;
     for (int c8 = 0; c8 < C / 8; ++c8)
       for (int e = 0; e < 8; ++e) { const double v = (double)__bfloat162float(k[((size_t)c8 * 128 + r) * 8 + e]); ss += v * v; }
-    kb[r] = (float)(sqrt(ss) * 1.01 * 1.4426950408889634);   // |k_d| <= |W'_k[d,:]| * |xhat|, |xhat| <= 1 + 2^-8
+    kb[r] = (float)(sqrt(ss) * 1.01);
+    k[((size_t)(C / 8) * 128 + r) * 8] = __float2bfloat16_rn(-kb[r]);
   }
   // |q'_d| <= |W'_q[d,:]|: when every bound is small the soft-max over d needs no max subtraction (2^q' cannot overflow)
   double qb = 0;
