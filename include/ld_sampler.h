@@ -137,6 +137,18 @@ LD_API int ld_cond_encode(ld_handle* h, const float* cond, float* feat, int N, i
 LD_API int ld_sample(ld_handle* h, const ld_sample_desc* sd, const float* cond, const float* mask,
               const float* noise, float* out, float* x0_trace, void* stream);
 
+/* --- `GaussianDiffusion.ddim_sample` (ddpm.py:979-1075): the DDIM variant of the branch sampler -----------------
+ * times: host int32 [nsteps], the `time` of every step (ddpm.py:984-986 without the trailing -1).
+ * coefs: host fp32 [nsteps][5] = {sqrt_recip_alphas_cumprod[time], sqrt_recipm1_alphas_cumprod[time], sqrt(alpha_next), c, sigma}
+ *        (ddpm.py:637-641, 1013-1018); the last three are unused on the last step, which returns x_start.
+ * noise: device fp32 [nsteps, B,1,H,W]; noise[0] is x_T, noise[1+i] the draw of step i (none for the last step).
+ * fuse_step: index of the step that composites the branches (time <= start_timestep_ddim, ddpm.py:1022), -1 = never;
+ *        a fuse_step equal to the last step never fuses, exactly like the reference (its `continue` comes first).
+ * out: [B,1,H,W], or [2,B,1,H,W] when sd->return_pair (never fused: the reference returns the list [out, in]).
+ * sd->num_timesteps, start_timestep, start_intermediate and record_x0 are ignored here. */
+LD_API int ld_sample_ddim(ld_handle* h, const ld_sample_desc* sd, const float* cond, const float* mask, const float* noise,
+                          float* out, const int32_t* times, const float* coefs, int nsteps, int fuse_step, void* stream);
+
 /* --- one DDPM update on caller-owned state (ddpm.py:841-860 + 768-838), for parity tests -----
  * kind 0: branched step; kind 1: fusion step (composite, then single update); kind 2: single.
  * x_out/x_in/x0_out/x0_in/z/mask: device fp32 [n]; raw UNet outputs come in through x0_*, the

@@ -1217,6 +1217,104 @@ int ld_sample(ld_handle* h, const ld_sample_desc* sdp, const float* cond, const 
   return 0;
 }
 
+// DDIM variant of the branch sampler (ddpm.py:979-1075): same UNet plans and masks, the schedule of (time, coefficient)
+// pairs comes from the host (diffusion.py builds it with the reference's own tensor ops), the step index lives on the device.
+int ld_sample_ddim(ld_handle* h, const ld_sample_desc* sdp, const float* cond, const float* mask, const float* noise, float* out,
+                   const int32_t* times, const float* coefs, int nsteps, int fuse_step, void* stream) {
+  if (!h || !sdp || !cond || !noise || !out || !times || !coefs) return fail(LD_ERR_INVALID, "null argument");
+  Engine& E = h->E;
+  const ld_sample_desc sd = *sdp;
+  int rc = need_ready(E); if (rc) return rc;
+  if (nsteps < 1) return fail(LD_ERR_INVALID, "nsteps out of range");
+  if (sd.branch_out && !mask) return fail(LD_ERR_INVALID, "branch mode needs a mask");
+  if ((rc = check_shape(E, sd.height, sd.width))) return rc;
+  if ((rc = prepare_sampler(E, sd))) return rc;
+  auto& S = E.ss;
+  cudaStream_t cs = (cudaStream_t)stream, s = E.own_stream;
+  const long long n = (long long)sd.batch * sd.height * sd.width;
+  const bool pair_unet = sd.branch_out && !(sd.mask_x && sd.ood_uses_cond);
+  // device copy of the schedule + step index (freed at the end of the call)
+  int* times_d = nullptr; float* coefs_d = nullptr; int* idx_d = nullptr;
+  CK(cudaMalloc(&times_d, (size_t)nsteps * sizeof(int))); CK(cudaMalloc(&coefs_d, (size_t)nsteps * 5 * sizeof(float)));
+  CK(cudaMalloc(&idx_d, sizeof(int)));
+  auto cleanup = [&]() { cudaFree(times_d); cudaFree(coefs_d); cudaFree(idx_d); };
+  CK(cudaEventRecord(E.ev_in, cs));
+  CK(cudaStreamWaitEvent(s, E.ev_in, 0));
+  CK(cudaMemcpyAsync(times_d, times, (size_t)nsteps * sizeof(int), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(coefs_d, coefs, (size_t)nsteps * 5 * sizeof(float), cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(idx_d, 0, sizeof(int), s));
+  CK(cudaMemcpyAsync(S.t_dev, times, sizeof(int), cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(S.counters, 0, 4 * sizeof(unsigned int), s));
+  CK(cudaMemcpyAsync(S.cond, cond, n * 4, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(S.xs, noise, n * 4, cudaMemcpyDeviceToDevice, s));          // img = randn(shape) (ddpm.py:989)
+  bool branched = sd.branch_out != 0;
+  if (branched) {
+    CK(cudaMemcpyAsync(S.xs + n, noise, n * 4, cudaMemcpyDeviceToDevice, s));    // img = [img, img] (ddpm.py:1003-1004)
+    PrepP pp{}; pp.cond = S.cond; pp.mask = mask; pp.bm = S.bm; pp.cond_out = S.cond_out; pp.cond_in = S.cond_in;
+    pp.floor = sd.cond_in_floor; pp.n = n; pp.counters = S.counters;
+    E.launches += launch_prep_cond(pp, s);
+    if ((rc = run_plan(E, *E.plans["cond_pair"], s))) { cleanup(); return rc; }
+  }
+  const bool will_fuse = branched && fuse_step >= 0 && fuse_step < nsteps - 1;   // the last step never fuses (ddpm.py:1009-1012)
+  if (!branched || will_fuse) { if ((rc = run_plan(E, *E.plans["cond_full"], s))) { cleanup(); return rc; } }
+  Plan* up = branched ? E.plans["unet_pair"].get() : nullptr;
+  Plan* uf = E.plans["unet_full"].get();
+  auto mk = [&](int kind) {
+    DdimP p{};
+    p.kind = kind; p.o_out = pair_unet || kind == 2 ? S.o : nullptr; p.o_in = S.o + n; p.x_out = S.xs; p.x_in = S.xs + n;
+    p.bm = S.bm; p.cond_out = S.cond_out; p.z = noise; p.z_stride = n; p.idx_ptr = idx_d; p.nsteps = nsteps; p.coefs = coefs_d;
+    p.mask_x = sd.mask_x; p.ood_uses_cond = sd.ood_uses_cond; p.lo = sd.min_val; p.hi = sd.max_val; p.n = n; p.counters = S.counters;
+    return p;
+  };
+  auto body = [&](int kind, cudaStream_t st) -> int {
+    int r = run_plan(E, kind == 2 ? *uf : *up, st); if (r) return r;
+    E.launches += launch_ddim_step(mk(kind), st);
+    E.launches += launch_ddim_advance(idx_d, times_d, nsteps, S.t_dev, st);
+    return 0;
+  };
+  if (S.g_branch) { cudaGraphExecDestroy(S.g_branch); S.g_branch = nullptr; }
+  if (S.g_single) { cudaGraphExecDestroy(S.g_single); S.g_single = nullptr; }
+  const bool use_graph = E.opt_use_graph != 0;
+  int64_t per_branch = 0, per_single = 0;
+  if (use_graph) {
+    int64_t l0 = E.launches;
+    if (branched) { if ((rc = capture(E, &S.g_branch, [&](cudaStream_t st) { return body(0, st); }))) { cleanup(); return rc; } per_branch = E.launches - l0; }
+    l0 = E.launches;
+    if ((rc = capture(E, &S.g_single, [&](cudaStream_t st) { return body(2, st); }))) { cleanup(); return rc; }
+    per_single = E.launches - l0;
+    E.launches -= per_branch + per_single;
+  }
+  for (int i = 0; i < nsteps; ++i) {
+    if (branched) {
+      if (will_fuse && i >= fuse_step) {
+        if ((rc = body(1, s))) { cleanup(); return rc; }
+        branched = false;   // config['branch_out'] = False (ddpm.py:1023)
+      } else if (use_graph) {
+        CK(cudaGraphLaunch(S.g_branch, s)); E.launches += per_branch;
+      } else if ((rc = body(0, s))) { cleanup(); return rc; }
+    } else {
+      if (use_graph) { CK(cudaGraphLaunch(S.g_single, s)); E.launches += per_single; }
+      else if ((rc = body(2, s))) { cleanup(); return rc; }
+    }
+  }
+  CK(cudaMemcpyAsync(out, S.xs, n * 4, cudaMemcpyDeviceToDevice, s));
+  if (sd.return_pair) CK(cudaMemcpyAsync(out + n, branched ? S.xs + n : S.xs, n * 4, cudaMemcpyDeviceToDevice, s));
+  unsigned int cnt[4], la_under = 0;
+  CK(cudaMemcpyAsync(cnt, S.counters, sizeof cnt, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&la_under, E.la_flag, sizeof la_under, cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(E.ev_out, s));
+  CK(cudaStreamWaitEvent(cs, E.ev_out, 0));
+  CK(cudaStreamSynchronize(s));
+  cleanup();
+  if (la_under) {
+    cudaMemset(E.la_flag, 0, sizeof(unsigned int));
+    return fail(LD_ERR_STATE, "LinearAttention soft-max shift underflowed (%u rows): set option la_exact=1 for the exact-max path", la_under);
+  }
+  if (sd.branch_out && sd.mask_x && (cnt[0] == 0 || cnt[1] == 0)) return fail(LD_ERR_MASK, "mask should be binary");
+  if (will_fuse && !(cnt[2] > 0 && cnt[3] > 0)) return fail(LD_ERR_MASK, "x_out and x_in should be masked");
+  return 0;
+}
+
 int ld_posterior_step(ld_handle* h, int kind, int t, float* x_out, float* x_in, float* x0_out, float* x0_in, const float* cond,
                       const float* mask, const float* z, const ld_sample_desc* sd, int64_t n, void* stream) {
   if (!h || !sd || !x_out || !x0_out) return fail(LD_ERR_INVALID, "null argument");

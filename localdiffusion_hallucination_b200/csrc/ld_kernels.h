@@ -86,6 +86,28 @@ struct StepP {
   float* x0_trace; long long trace_stride;  // optional [tloop][2][n]
 };
 int launch_step(const StepP& p, cudaStream_t s);
+
+// DDIM update of the branch sampler (ddpm.py:979-1075).  Step i of the host-built schedule: time = times[i],
+// coefs[i] = {sqrt_recip_alphas_cumprod[time], sqrt_recipm1_alphas_cumprod[time], sqrt(alpha_next), c, sigma}; the last
+// step (time_next < 0) returns x_start itself.
+struct DdimP {
+  int kind;                 // 0 branched, 1 fusion (ddpm.py:1022-1043), 2 single
+  const float* o_out; const float* o_in;
+  float* x_out; float* x_in;
+  const float* bm; const float* cond_out;
+  const float* z;           // noise tape: draw 0 is x_T, step i uses draw 1 + i (none for the last step)
+  long long z_stride;
+  const int* idx_ptr;       // device scalar: current step index (graph-replay friendly)
+  int nsteps;
+  const float* coefs;       // device [nsteps][5]
+  int mask_x, ood_uses_cond;
+  float lo, hi;
+  long long n;
+  unsigned int* counters;   // [2]=#(eps_out*m==0), [3]=#(eps_in*(1-m)==0) at the fusion step
+};
+int launch_ddim_step(const DdimP& p, cudaStream_t s);
+// idx += 1; t = times[idx] (when in range)
+int launch_ddim_advance(int* idx_ptr, const int* times, int nsteps, int* t_ptr, cudaStream_t s);
 int launch_dec_t(int* t_ptr, cudaStream_t s);
 
 int launch_nhwc_to_nchw_f32(const void* in, float* out, int N, int HW, int C, bool bf, cudaStream_t s);

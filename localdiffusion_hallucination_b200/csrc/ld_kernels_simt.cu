@@ -905,6 +905,79 @@ int launch_step(const StepP& p, cudaStream_t s) {
   step_kernel<<<cdiv(p.n, 256), 256, 0, s>>>(p);
   return 1;
 }
+// ---- DDIM (ddpm.py:979-1075): every product and sum is rounded separately, in the reference's evaluation order ----
+// predict_noise_from_start (ddpm.py:637-641)
+__device__ __forceinline__ float eps_from(float sr, float srm1, float xt, float x0) {
+  return __fdiv_rn(__fsub_rn(__fmul_rn(sr, xt), x0), srm1);
+}
+// x_start * alpha_next.sqrt() + c * pred_noise + sigma * noise (ddpm.py:1041-1043, 1068-1070)
+__device__ __forceinline__ float ddim_next(float san, float c, float sg, float x0, float eps, float z) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(x0, san), __fmul_rn(c, eps)), __fmul_rn(sg, z));
+}
+__global__ void __launch_bounds__(256) ddim_step_kernel(DdimP p) {
+  const int idx = *p.idx_ptr;
+  const bool last = idx >= p.nsteps - 1;   // time_next < 0 (ddpm.py:1009-1012, 1053-1056)
+  const float* cf = p.coefs + (size_t)idx * 5;
+  const float sr = cf[0], srm1 = cf[1], san = cf[2], c = cf[3], sg = cf[4];
+  const float* z = (!last && p.z) ? p.z + (size_t)(1 + idx) * p.z_stride : nullptr;
+  unsigned int zo = 0, zi = 0;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < p.n) {
+    const float zz = z ? z[i] : 0.0f;
+    if (p.kind == 2) {
+      const float x0 = clampf(p.o_out[i], p.lo, p.hi);
+      const float xt = p.x_out[i];
+      p.x_out[i] = last ? x0 : ddim_next(san, c, sg, x0, eps_from(sr, srm1, xt, x0), zz);
+    } else {
+      const float bm = p.bm[i];
+      float v;
+      if (p.mask_x) {   // ddpm.py:697-708
+        if (p.ood_uses_cond) v = p.cond_out[i];
+        else v = (bm == 0.0f) ? p.lo : __fmul_rn(p.o_out[i], bm);
+      } else {
+        v = p.o_out[i];
+      }
+      const float x0o = clampf(v, p.lo, p.hi), x0i = clampf(p.o_in[i], p.lo, p.hi);
+      const float xo = p.x_out[i], xi = p.x_in[i];
+      if (last) {                         // img = [x_start_out, x_start_in]: never fused on the last step
+        p.x_out[i] = x0o; p.x_in[i] = x0i;
+      } else {
+        const float eo = eps_from(sr, srm1, xo, x0o), ei = eps_from(sr, srm1, xi, x0i);
+        if (p.kind == 0) {
+          p.x_out[i] = ddim_next(san, c, sg, x0o, eo, zz);
+          p.x_in[i] = ddim_next(san, c, sg, x0i, ei, zz);
+        } else {                          // fusion: select on x_start_out == 0, composite of the noise predictions
+          const float x0 = clampf(x0o == 0.0f ? x0i : x0o, p.lo, p.hi);
+          const float a = __fmul_rn(eo, bm), b = __fmul_rn(ei, __fsub_rn(1.0f, bm));
+          zo = a == 0.0f; zi = b == 0.0f;
+          const float eps = (a == 0.0f) ? b : a;
+          p.x_out[i] = ddim_next(san, c, sg, x0, eps, zz);
+        }
+      }
+    }
+  }
+  if (p.kind == 1) {
+    zo = __reduce_add_sync(0xffffffffu, zo);
+    zi = __reduce_add_sync(0xffffffffu, zi);
+    if ((threadIdx.x & 31) == 0) {
+      if (zo) atomicAdd(p.counters + 2, zo);
+      if (zi) atomicAdd(p.counters + 3, zi);
+    }
+  }
+}
+int launch_ddim_step(const DdimP& p, cudaStream_t s) {
+  ddim_step_kernel<<<cdiv(p.n, 256), 256, 0, s>>>(p);
+  return 1;
+}
+__global__ void ddim_advance_kernel(int* idx, const int* times, int nsteps, int* t) {
+  const int i = *idx + 1;
+  *idx = i;
+  if (i < nsteps) *t = times[i];
+}
+int launch_ddim_advance(int* idx_ptr, const int* times, int nsteps, int* t_ptr, cudaStream_t s) {
+  ddim_advance_kernel<<<1, 1, 0, s>>>(idx_ptr, times, nsteps, t_ptr);
+  return 1;
+}
 __global__ void dec_t_kernel(int* t) { *t = *t - 1; }
 int launch_dec_t(int* t_ptr, cudaStream_t s) {
   dec_t_kernel<<<1, 1, 0, s>>>(t_ptr);

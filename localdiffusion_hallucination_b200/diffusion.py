@@ -76,6 +76,74 @@ class GaussianDiffusion(nn.Module):
             tape[i] = torch.randn(shape, device=device)
         return tape
 
+    # ---------------------------------------------------------------------------------------
+    def ddim_schedule(self):
+        """(times, coefs, fuse_step) of `ddim_sample` (ddpm.py:982-987, 1013-1018), built with the reference's own fp32
+        tensor expressions so the coefficients are bit-identical.  coefs[i] = (sqrt_recip_alphas_cumprod[t],
+        sqrt_recipm1_alphas_cumprod[t], sqrt(alpha_next), c, sigma); the last step has no successor."""
+        T, Ssteps, eta = self.num_timesteps, self.sampling_timesteps, self.ddim_sampling_eta
+        times = torch.linspace(-1, T - 1, steps=Ssteps + 1)
+        times = list(reversed(times.int().tolist()))
+        pairs = list(zip(times[:-1], times[1:]))
+        self.start_timestep_ddim = times[-self.config["start_timestep"] - 2]
+        ac = self.alphas_cumprod.detach().cpu()
+        sr, srm1 = self.sqrt_recip_alphas_cumprod.detach().cpu(), self.sqrt_recipm1_alphas_cumprod.detach().cpu()
+        coefs = torch.zeros(len(pairs), 5, dtype=torch.float32)
+        for i, (t, tn) in enumerate(pairs):
+            coefs[i, 0], coefs[i, 1] = sr[t], srm1[t]
+            if tn < 0:
+                continue
+            alpha, alpha_next = ac[t], ac[tn]
+            sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+            c = (1 - alpha_next - sigma ** 2).sqrt()
+            coefs[i, 2], coefs[i, 3], coefs[i, 4] = alpha_next.sqrt(), c, sigma
+        fuse = -1
+        if self.config["start_intermediate"]:
+            for i, (t, _) in enumerate(pairs):
+                if t <= self.start_timestep_ddim:  # ddpm.py:1022
+                    fuse = i
+                    break
+        return [t for t, _ in pairs], coefs, fuse
+
+    def _ddim_sample(self, h, dev, cond_img, mask, min_max_val, shape, noise):
+        """ddpm.py:979-1075 on the device loop `ld_sample_ddim`.  The reference draws x_T and one `randn_like` per step
+        (none for the last) from the global generator WITHOUT re-seeding; `noise=` replaces those draws."""
+        cfg = self.config
+        B, Cc, S, _ = shape
+        times, coefs, fuse = self.ddim_schedule()
+        n = len(times)
+        if noise is None:
+            noise = torch.stack([torch.randn(shape, device=dev) for _ in range(n)])
+        noise = noise.to(dev, torch.float32).contiguous()
+        assert noise.shape[0] >= n and tuple(noise.shape[1:]) == tuple(shape)
+        cond = cond_img.to(dev, torch.float32).contiguous()
+        assert tuple(cond.shape) == tuple(shape)
+        mk = mask.to(dev, torch.float32).contiguous() if mask is not None else None
+        sd = _lib.SampleDesc()
+        sd.batch, sd.height, sd.width, sd.num_timesteps = B, S, S, n
+        sd.branch_out = int(bool(cfg["branch_out"]))
+        sd.start_intermediate = int(bool(cfg["start_intermediate"]))
+        sd.start_timestep = int(cfg["start_timestep"])
+        sd.mask_x = int(bool(cfg["mask_x"]))
+        data = cfg["data"]
+        sd.ood_uses_cond = int(any(s in data for s in _NON_MRI) and "mri" not in data)
+        sd.cond_in_floor = 0.5 if data == "mnist" else 0.95
+        sd.min_val, sd.max_val = float(min_max_val[0]), float(min_max_val[1])
+        will_fuse = bool(sd.branch_out) and 0 <= fuse < n - 1
+        pair = bool(sd.branch_out) and not will_fuse  # the reference returns the list [x_out, x_in] (ddpm.py:1010, 1073)
+        sd.return_pair = int(pair)
+        out = torch.empty((2,) + tuple(shape) if pair else tuple(shape), device=dev)
+        tt = torch.tensor(times, dtype=torch.int32)
+        rc = _lib.lib().ld_sample_ddim(h, C.byref(sd), cond.data_ptr(), mk.data_ptr() if mk is not None else None,
+                                       noise.data_ptr(), out.data_ptr(), tt.data_ptr(), coefs.data_ptr(), n,
+                                       fuse if cfg["start_intermediate"] else -1,
+                                       C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        if will_fuse:  # ddpm.py:1023-1024
+            cfg["branch_out"] = False
+            cfg["mask_x"] = False
+        _lib.check(rc)
+        return [out[0], out[1]] if pair else out
+
     @torch.inference_mode()
     def sample(self, cond_img, gt, batch_size=16, return_all_timesteps=False, return_all_outputs=False, mask=None,
                ood_confidence_ad=False, min_max_val=None, instance=0, noise=None):
@@ -98,8 +166,6 @@ class GaussianDiffusion(nn.Module):
             u = torch.unique(mask)
             if len(u) == 1 and u == 1:
                 cfg["mask_cond"] = cfg["mask_x"] = cfg["branch_out"] = cfg["start_intermediate"] = False
-        if self.is_ddim_sampling:
-            raise NotImplementedError("DDIM branch sampling (ddpm.py:979-1075) is a 'next' row (SURVEY.md §8f)")
         if return_all_timesteps:
             raise NotImplementedError("return_all_timesteps stacks branch lists and fails in the reference (ddpm.py:964)")
         if cfg["branch_out"] and self.objective != "pred_x0":
@@ -113,6 +179,8 @@ class GaussianDiffusion(nn.Module):
         dev = self.model._handle_device
         self._push_schedule(h)
         B, Cc, S = batch_size, self.channels, self.image_size
+        if self.is_ddim_sampling:  # ddpm.py:1122-1124: return_all_outputs is not forwarded to ddim_sample
+            return self._ddim_sample(h, dev, cond_img, mask, min_max_val, (B, Cc, S, S), noise)
         steps = self.num_timesteps
         use_gt = bool(self.start_intermediate and cfg.get("use_gt", False))
         if use_gt:

@@ -376,6 +376,88 @@ class Sampler:
         return img
 
 
+def ddim_sample(smp: "Sampler", cond: Tensor, mask: Tensor, min_max_val, noise_tape: Sequence[Tensor], sampling_timesteps: int,
+                eta: float = 0.0):
+    """Restatement of `GaussianDiffusion.sample` -> `ddim_sample` (ddpm.py:1078-1124, 979-1075) for objective pred_x0.
+
+    `noise_tape[0]` is x_T, then one draw per step that has a successor (the reference draws `randn_like` only after its
+    `time_next < 0` early-out, ddpm.py:1009-1020).  Returns a tensor, or the list [x_out, x_in] when the branches were
+    never composited (the reference returns `img` as it is, ddpm.py:1073-1076)."""
+    cfg = smp.config
+    if cfg["branch_out"] is False:
+        cfg["branch_out"] = smp.ctor_branch_out
+    if cfg["start_intermediate"] is False:
+        cfg["start_intermediate"] = smp.ctor_start_intermediate
+    smp.ctor_start_intermediate = bool(cfg["start_intermediate"])
+    if cfg["ood_AD"] or cfg["ood_confidence"]:
+        cfg["mask_cond"] = True
+        cfg["mask_x"] = True
+    if cfg["branch_out"]:
+        u = torch.unique(mask)
+        if len(u) == 1 and float(u[0]) == 1.0:
+            cfg["mask_cond"] = cfg["mask_x"] = cfg["branch_out"] = cfg["start_intermediate"] = False
+    lo, hi = float(min_max_val[0]), float(min_max_val[1])
+    T = smp.num_timesteps
+    times = torch.linspace(-1, T - 1, steps=sampling_timesteps + 1)  # ddpm.py:984
+    times = list(reversed(times.int().tolist()))
+    pairs = list(zip(times[:-1], times[1:]))
+    start_ddim = times[-cfg["start_timestep"] - 2]  # ddpm.py:987
+    ac, sr, srm1 = smp.buf["alphas_cumprod"], smp.buf["sqrt_recip_alphas_cumprod"], smp.buf["sqrt_recipm1_alphas_cumprod"]
+    it = iter(noise_tape)
+    draw = lambda: next(it).clone()
+    img = draw()
+    eps_of = lambda xt, t, x0: (sr[t] * xt - x0) / srm1[t]  # ddpm.py:637-641
+    for time, time_next in pairs:
+        tt = torch.full((cond.shape[0],), time, dtype=torch.long)
+        if cfg["branch_out"]:
+            if time == T - 1:
+                img = [img, img]  # ddpm.py:1003-1004
+            # model_predictions(clip_x_start=True, rederive_pred_noise=True), ddpm.py:668-766
+            bm = (mask >= 1.0).float()
+            cond_out = cond * bm
+            floor = 0.5 if cfg["data"] == "mnist" else 0.95
+            cond_in = (cond * torch.clip(1.0 - bm, floor, 1.0)).float()
+            o_out = smp._model(img[0], cond_out, tt)
+            o_in = smp._model(img[1], cond_in, tt)
+            if cfg["mask_x"]:
+                assert len(torch.unique(bm)) == 2, "mask should be binary"
+                o_out = torch.where(bm == 0.0, torch.tensor(lo), o_out * bm)
+                d = cfg["data"]
+                if any(s in d for s in _NON_MRI) and "mri" not in d:
+                    o_out = cond_out
+            x0_out, x0_in = o_out.clamp(lo, hi), o_in.clamp(lo, hi)
+            e_out, e_in = eps_of(img[0], time, x0_out), eps_of(img[1], time, x0_in)
+            if time_next < 0:
+                img = [x0_out, x0_in]
+                continue
+            alpha, alpha_next = ac[time], ac[time_next]
+            sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+            c = (1 - alpha_next - sigma ** 2).sqrt()
+            noise = draw()
+            if time <= start_ddim and cfg["start_intermediate"]:  # ddpm.py:1022-1043
+                cfg["branch_out"] = False
+                cfg["mask_x"] = False
+                x0 = torch.where(x0_out == 0.0, x0_in, x0_out).clamp(lo, hi)
+                xo, xi = e_out * bm, e_in * (1.0 - bm)
+                assert bool((xo == 0).any()) and bool((xi == 0).any()), "x_out and x_in should be masked"
+                eps = torch.where(xo == 0.0, xi, xo)
+                img = x0 * alpha_next.sqrt() + c * eps + sigma * noise
+            else:
+                img = [x0_out * alpha_next.sqrt() + c * e_out + sigma * noise, x0_in * alpha_next.sqrt() + c * e_in + sigma * noise]
+        else:
+            x0 = smp._model(img, cond, tt).clamp(lo, hi)  # ddpm.py:716, clip_x_start (and the idempotent re-clamp of 1050-1051)
+            eps = eps_of(img, time, x0)
+            if time_next < 0:
+                img = x0
+                continue
+            alpha, alpha_next = ac[time], ac[time_next]
+            sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+            c = (1 - alpha_next - sigma ** 2).sqrt()
+            noise = draw()
+            img = x0 * alpha_next.sqrt() + c * eps + sigma * noise
+    return img
+
+
 def psnr(a: Tensor, b: Tensor, peak: float) -> float:
     mse = float(((a.double() - b.double()) ** 2).mean())
     return float("inf") if mse == 0 else 10.0 * math.log10(peak * peak / mse)
