@@ -474,10 +474,10 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
     mbar_init(w_full, 1);
     for (int i = 0; i < K::XS; ++i) { mbar_init(x_full + 8 * i, 4); mbar_init(x_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(d1_full + 8 * i, 1); mbar_init(d1_empty + 8 * i, 128);
+      mbar_init(d1_full + 8 * i, 1); mbar_init(d1_empty + 8 * i, 4);     // one arrival per transform warp
       mbar_init(d2_full + 8 * i, 1); mbar_init(d2_empty + 8 * i, 128);
     }
-    for (int i = 0; i < K::NP; ++i) { mbar_init(p_full + 8 * i, 128); mbar_init(p_empty + 8 * i, 1); }
+    for (int i = 0; i < K::NP; ++i) { mbar_init(p_full + 8 * i, 4); mbar_init(p_empty + 8 * i, 1); }
     for (int i = 0; i < K::RS; ++i) { mbar_init(raw_full + 8 * i, 1); mbar_init(raw_empty + 8 * i, 4); }
     fence_barrier_init();
   }
@@ -565,12 +565,8 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
       mbar_wait(d1_full + 8 * g, u & 1);
       tc_fence_after();
       mbar_wait(p_empty + 8 * pi, ppar(i) ^ 1);     // the MMA2 that last read this P buffer is complete
-#pragma unroll 1
-      for (int h = 0; h < 4; ++h) {
-        uint32_t qr[32];
-        tmem_ld32(lane_base + (uint32_t)(g * 128 + h * 32), qr);
-        tmem_ld_wait();
-        if (h == 3) { tc_fence_before(); mbar_arrive(d1_empty + 8 * g); }
+      // one head = 32 TMEM columns of this pixel row; the next head's columns are in flight while this one is exponentiated
+      auto head = [&](const uint32_t (&qr)[32], int h) {
         // q arrives pre-multiplied by log2(e) (folded into W_q): softmax_d(q) = 2^(q' - max) / sum
         float mx = 0.f;
         if (p.use_max) {
@@ -578,10 +574,10 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
 #pragma unroll
           for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(qr[j]));
         }
-        float e[32], su = 0.f;
+        float e[32], s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { e[j] = ex2_approx(__uint_as_float(qr[j]) - mx); su += e[j]; }
-        const float sc = 1.0f / su;   // softmax(dim=-2) (ddpm.py:242); the dim_head^-0.5 of ddpm.py:245 is folded into Mn
+        for (int j = 0; j < 32; ++j) { e[j] = ex2_approx(__uint_as_float(qr[j]) - mx); s4[j & 3] += e[j]; }
+        const float sc = 1.0f / ((s4[0] + s4[1]) + (s4[2] + s4[3]));   // softmax(dim=-2) (ddpm.py:242); dim_head^-0.5 (ddpm.py:245) is in Mn
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t o4[4];
@@ -589,19 +585,42 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
           for (int j = 0; j < 4; ++j) o4[j] = pack_bf16x2(e[8 * c + 2 * j] * sc, e[8 * c + 2 * j + 1] * sc);
           *reinterpret_cast<uint4*>(pbuf + (size_t)(h * 4 + c) * 2048) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
         }
-      }
+      };
+      const uint32_t qbase = lane_base + (uint32_t)(g * 128);
+      uint32_t qa[32], qb[32];
+      tmem_ld32(qbase, qa);
+      tmem_ld_wait();
+      tmem_ld32(qbase + 32, qb);
+      head(qa, 0);
+      tmem_ld_wait();
+      tmem_ld32(qbase + 64, qa);
+      head(qb, 1);
+      tmem_ld_wait();
+      tmem_ld32(qbase + 96, qb);
+      head(qa, 2);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d1_empty + 8 * g);
+      head(qb, 3);
       fence_proxy_async();
-      mbar_arrive(p_full + 8 * pi);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full + 8 * pi);
     };
     auto epilogue = [&](int i) {
       const int u = i >> 1;
-      mbar_wait(d2_full + 8 * g, u & 1);
-      tc_fence_after();
       const int px = (t0 + i) * 128 + m;
       const __nv_bfloat16* xr = ximg + (size_t)px * C;
       __nv_bfloat16* orow = p.out + ((size_t)n * p.HW + px) * C;
       if constexpr (C <= 64) {
-        // one sweep: the whole row stays in registers
+        // one sweep: the whole row stays in registers; the residual row of x is requested before the accumulator is read
+        uint4 xv[C / 8];
+        if (px < p.HW) {
+#pragma unroll
+          for (int j = 0; j < C / 8; ++j) xv[j] = __ldg(reinterpret_cast<const uint4*>(xr) + j);
+        }
+        mbar_wait(d2_full + 8 * g, u & 1);
+        tc_fence_after();
         float o[C];
         float ss = 0.f;
 #pragma unroll
@@ -618,8 +637,7 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
           const float inv = rsqrtf(fmaxf(ss, 1e-24f));            // to_out RMSNorm (ddpm.py:231,251)
 #pragma unroll
           for (int j0 = 0; j0 < C; j0 += 8) {
-            const uint4 xv = *reinterpret_cast<const uint4*>(xr + j0);
-            const uint32_t xi[4] = {xv.x, xv.y, xv.z, xv.w};
+            const uint32_t xi[4] = {xv[j0 / 8].x, xv[j0 / 8].y, xv[j0 / 8].z, xv[j0 / 8].w};
             uint32_t o4[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -631,6 +649,8 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
         }
       } else {
         // two sweeps over the TMEM row (sum of squares, then normalise + store)
+        mbar_wait(d2_full + 8 * g, u & 1);
+        tc_fence_after();
         float ss = 0.f;
 #pragma unroll 1
         for (int j0 = 0; j0 < C; j0 += 32) {
