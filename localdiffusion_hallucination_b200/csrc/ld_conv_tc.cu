@@ -87,6 +87,7 @@ struct alignas(64) KParams {
   long long M;
   int resident, nb_stages, coef_floats;
   int tma_in, tma_out, sa;           // TMA activation loads / TMA output store / number of activation stages
+  int xf;                            // lean kernel: warps 8-11 normalise the TMA-loaded patch in place (pro_ab) instead of draining tiles
   int ds, ds_cs;                     // 2x2 stride-2 (pixel-unshuffle) conv run as a 1x1 over four strided TMA gathers; ds_cs = source channels
   int a_stage, lbo16;                // activation stage pitch (bytes) and chunk stride (16-byte units)
   int off_a, off_b, off_coef;        // shared memory carve-up (bytes)
@@ -227,14 +228,15 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
   float* sacc_all = coef + p.coef_floats;             // [2][256] GroupNorm partial sums of each epilogue warp-group
   float* bias_s = sacc_all + 512;                         // [NT] bias of this CTA's output channels
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 2 * NT);   // bias_s[NT..2NT): bias of the fused 1x1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA_MAX + 2 * SB + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * SA_MAX + 2 * SB + 4);
   const uint32_t a_full = smem_u32(bars), a_empty = a_full + 8 * SA_MAX, b_full = a_empty + 8 * SA_MAX, b_empty = b_full + 8 * SB,
-                 acc_full = b_empty + 8 * SB, acc_empty = acc_full + 16;
+                 acc_full = b_empty + 8 * SB, acc_empty = acc_full + 16, raw_full = acc_empty + 16;
+  const bool xf = LEAN && p.xf;      // TMA -> raw_full -> transform warps -> a_full -> MMA
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int SA = p.sa;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < SA; ++i) { mbar_init(a_full + 8 * i, p.tma_in ? 1 : 4); mbar_init(a_empty + 8 * i, 1); }
+    for (int i = 0; i < SA; ++i) { mbar_init(a_full + 8 * i, (p.tma_in && !xf) ? 1 : 4); mbar_init(a_empty + 8 * i, 1); mbar_init(raw_full + 8 * i, 1); }
     for (int i = 0; i < SB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 128); }
     fence_barrier_init();
@@ -268,18 +270,19 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
             const void* map = (p.ds || cbase < p.C0) ? (const void*)&p.map_a0 : (const void*)&p.map_a1;
             const int cb8 = (cbase < p.C0 ? cbase : cbase - p.C0) >> 3;
             const uint32_t dst = smem_u32(a_s + (size_t)ra.s * p.a_stage);
-            mbar_arrive_expect_tx(a_full + 8 * ra.s, stage_bytes);
+            const uint32_t fbar = (xf ? raw_full : a_full) + 8 * ra.s;
+            mbar_arrive_expect_tx(fbar, stage_bytes);
             if (!(p.dbg & 1)) {
-              if (KS == 3) tma_load_5d(dst, map, 0, tw.tx * G::TW - 1, tw.ty * G::TH - 1, cb8, tw.img, a_full + 8 * ra.s);
+              if (KS == 3) tma_load_5d(dst, map, 0, tw.tx * G::TW - 1, tw.ty * G::TH - 1, cb8, tw.img, fbar);
               else if (p.ds) {
                 // chunk c covers channels [cbase % Cs, +KC) of unshuffle tap q = cbase / Cs = (p1, p2): every other pixel
                 // of the source starting at (2 ty + p1, 2 tx + p2) -- one strided TMA gather of 16 x 8 pixels
                 const int q = cbase / p.ds_cs, cq = cbase - q * p.ds_cs;
-                tma_load_5d(dst, map, 0, 2 * (tw.tx * 8) + (q & 1), 2 * (tw.ty * 16) + (q >> 1), cq >> 3, tw.img, a_full + 8 * ra.s);
-              } else tma_load_3d(dst, map, 0, tw.tile * 128, cb8, a_full + 8 * ra.s);
+                tma_load_5d(dst, map, 0, 2 * (tw.tx * 8) + (q & 1), 2 * (tw.ty * 16) + (q >> 1), cq >> 3, tw.img, fbar);
+              } else tma_load_3d(dst, map, 0, tw.tile * 128, cb8, fbar);
             } else {
               // development aid: complete the transaction without data
-              asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(a_full + 8 * ra.s), "r"(stage_bytes) : "memory");
+              asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(fbar), "r"(stage_bytes) : "memory");
             }
             ra.advance(SA);
           }
@@ -363,8 +366,51 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
         }
       }
     }
+  } else if (xf && warp >= kEpiWarp0 + 4 && warp < kEpiWarp0 + 8) {
+    // ================================================================== in-place transform ============
+    // "normalise on load" for TMA-fed launches: the raw patch landed in the operand layout; every warp owns the 8-channel
+    // groups c8 = xw, xw + 4, .. (coefficients in registers), lanes walk the patch pixels (conflict-free 16-byte accesses).
+    // Padding pixels (hardware zero fill) stay exactly zero, like the reference's conv padding of the normalised tensor.
+    const int xw = warp - (kEpiWarp0 + 4);
+    Ring ra;
+    TileWalk tw;
+    tw.init(p, true);
+    for (; tw.tile < tw.end; tw.next(p)) {
+      const int img = tw.img, ty0 = tw.ty * G::TH, tx0 = tw.tx * G::TW;
+      const bool interior = ty0 > 0 && tx0 > 0 && ty0 + G::TH < p.H && tx0 + G::TW < p.W;
+      for (int c = 0; c < p.nchunks; ++c) {
+        mbar_wait(raw_full + 8 * ra.s, ra.ph);
+        uint8_t* stage = a_s + (size_t)ra.s * p.a_stage;
+        for (int c8 = xw; c8 < G::CH; c8 += 4) {
+          const float4* ab = reinterpret_cast<const float4*>(p.pro_ab + ((size_t)img * 2) * p.C0 + c * KC + c8 * 8);
+          const float4 a0 = __ldg(ab), a1 = __ldg(ab + 1);
+          const float4* bb = reinterpret_cast<const float4*>(p.pro_ab + ((size_t)img * 2 + 1) * p.C0 + c * KC + c8 * 8);
+          const float4 b0 = __ldg(bb), b1 = __ldg(bb + 1);
+          const float pa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          const float pb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          uint8_t* col = stage + (size_t)c8 * G::LBO_TMA;
+#pragma unroll 2
+          for (int hp = lane; hp < G::HPIX; hp += 32) {
+            bool ok = interior;
+            if (!ok) {
+              const int hy = hp / G::PITCH, hx = hp - hy * G::PITCH;
+              ok = (unsigned)(ty0 + hy - 1) < (unsigned)p.H && (unsigned)(tx0 + hx - 1) < (unsigned)p.W;
+            }
+            if (ok) {
+              uint4* q = reinterpret_cast<uint4*>(col + hp * 16);
+              *q = pro_apply(*q, pa, pb, p.pro_act);
+            }
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full + 8 * ra.s);
+        ra.advance(SA);
+      }
+    }
   } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4 * R::kEpiGroups) {
     // ================================================================== epilogue ======================
+    const bool two_groups = R::kEpiGroups == 2 && !xf;
     // warp-group eg drains the tiles whose accumulator stage is eg (every tile when there is one group)
     const int eg = (warp - kEpiWarp0) >> 2;
     const int ew = warp & 3, etid = threadIdx.x - (kEpiWarp0 + 4 * eg) * 32;
@@ -393,7 +439,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
     };
     for (; tw.tile < tw.end; tw.next(p), ++it_tile) {
       const int as = it_tile & 1;
-      if (R::kEpiGroups == 2 && as != eg) continue;
+      if (two_groups && as != eg) continue;
       const int img = tw.img;
       if (p.stats && img != stat_img) {
         if (stat_img >= 0) flush_stats(stat_img);
@@ -415,7 +461,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
       const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)as * acc_cols;
       // TMA store path: the store that read this staging buffer two tiles ago must have finished reading it
       if (NT <= 64 && p.tma_out) {
-        if (etid == 0) { if (R::kEpiGroups == 2) bulk_wait_group_read<0>(); else bulk_wait_group_read<1>(); }
+        if (etid == 0) { if (two_groups) bulk_wait_group_read<0>(); else bulk_wait_group_read<1>(); }
         named_bar(ebar, 128);
       }
       // staged output row: MX tiles are 8 x 14 pixels dense (patch columns 14, 15 of every row produce nothing)
@@ -772,7 +818,7 @@ size_t layout(KParams& p, int sa, int nb_stages) {
   p.off_b = (int)off;
   off += (size_t)nb_stages * (MX ? 3 * NT : NT) * KC * 2;
   p.off_coef = (int)off;
-  off += (size_t)(p.coef_floats + 512 + 2 * NT) * 4 + (2 * SA_MAX + 2 * SB + 4) * 8 + 16;
+  off += (size_t)(p.coef_floats + 512 + 2 * NT) * 4 + (3 * SA_MAX + 2 * SB + 4) * 8 + 16;
   return off;
 }
 
@@ -980,11 +1026,15 @@ static bool build_params(const ConvTcW& w, const ConvTcArgs& a, KParams& p) {
   p.tma_in = 0;
   if (a.ds) {
     p.tma_in = map_in_ds(&p.map_a0, a.src0, a.N, a.Hin, a.Win, a.C0, kc) ? 1 : 0;
-  } else if (!a.up && !a.pro_ab) {
+  } else if (!a.up) {
     bool ok = w.ks == 3 ? map_in_3x3(&p.map_a0, a.src0, a.N, a.Hin, a.Win, a.C0, kc, mx ? 16 : 10, mx ? 10 : 18) : map_in_1x1(&p.map_a0, a.src0, p.M, a.C0, kc);
     if (ok && a.src1)
       ok = w.ks == 3 ? map_in_3x3(&p.map_a1, a.src1, a.N, a.Hin, a.Win, a.C1, kc, mx ? 16 : 10, mx ? 10 : 18) : map_in_1x1(&p.map_a1, a.src1, p.M, a.C1, kc);
     p.tma_in = ok ? 1 : 0;
+    static int noxf = -1;   // env LD_CONV_NO_XF=1: normalise-on-load through the register-staging kernel (A/B aid)
+    if (noxf < 0) { const char* e = getenv("LD_CONV_NO_XF"); noxf = e ? atoi(e) : 0; }
+    if (a.pro_ab && noxf) p.tma_in = 0;
+    p.xf = (a.pro_ab && p.tma_in) ? 1 : 0;
   }
   p.tma_out = map_out(&p.map_out, a.dst, a.N, a.H, a.W, w.Cout, w.ntile, a.ds ? 3 : w.ks, mx) ? 1 : 0;
   if (mx) {

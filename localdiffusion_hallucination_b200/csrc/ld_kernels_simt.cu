@@ -760,6 +760,7 @@ __global__ void time_embed_kernel(TimeP p) {
   extern __shared__ float sh[];  // emb[dim], h1[4dim]
   const int n = blockIdx.x, dim = p.dim, td = 4 * dim, half = dim / 2;
   float* emb = sh; float* h1 = sh + dim;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const float tf = p.t_scalar ? (float)(*p.t_scalar) : (float)p.t[n];
   for (int i = threadIdx.x; i < half; i += blockDim.x) {
     const float f = expf((float)i * p.neg_step);
@@ -767,16 +768,23 @@ __global__ void time_embed_kernel(TimeP p) {
     emb[i] = sinf(a); emb[half + i] = cosf(a);
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < td; j += blockDim.x) {
-    float a = p.b1[j];
-    for (int k = 0; k < dim; ++k) a = fmaf(p.w1[(size_t)j * dim + k], emb[k], a);
-    h1[j] = 0.5f * a * (1.0f + erff(a * 0.70710678118654752f));  // exact GELU (nn.GELU default)
+  // one warp per output row: coalesced weight reads, shuffle reduction (rows are too few for a thread each to hide latency)
+  for (int j = warp; j < td; j += nwarps) {
+    float a = 0.f;
+    for (int k = lane; k < dim; k += 32) a = fmaf(p.w1[(size_t)j * dim + k], emb[k], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    a += p.b1[j];
+    if (lane == 0) h1[j] = 0.5f * a * (1.0f + erff(a * 0.70710678118654752f));  // exact GELU (nn.GELU default)
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < td; j += blockDim.x) {
-    float a = p.b2[j];
-    for (int k = 0; k < td; ++k) a = fmaf(p.w2[(size_t)j * td + k], h1[k], a);
-    p.st[(size_t)n * td + j] = a / (1.0f + expf(-a));  // SiLU in front of every block MLP (ddpm.py:192)
+  for (int j = warp; j < td; j += nwarps) {
+    float a = 0.f;
+    for (int k = lane; k < td; k += 32) a = fmaf(p.w2[(size_t)j * td + k], h1[k], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    a += p.b2[j];
+    if (lane == 0) p.st[(size_t)n * td + j] = a / (1.0f + expf(-a));  // SiLU in front of every block MLP (ddpm.py:192)
   }
 }
 // all block MLPs at once (ddpm.py:191-194): one warp per output row j, coalesced weight reads, every image of the batch
@@ -800,7 +808,7 @@ __global__ void film_kernel(TimeP p) {
 }
 int launch_time_film(const TimeP& p, cudaStream_t s) {
   // the sampler shares one timestep across the batch (t_scalar): a single row is computed and consumers use stride 0
-  time_embed_kernel<<<p.N, 128, (size_t)5 * p.dim * sizeof(float), s>>>(p);
+  time_embed_kernel<<<p.N, 512, (size_t)5 * p.dim * sizeof(float), s>>>(p);
   int launches = 1;
   for (int n0 = 0; n0 < p.N; n0 += 16) {   // 16 images per launch keep the staged embeddings inside 48 KB
     TimeP q = p;
