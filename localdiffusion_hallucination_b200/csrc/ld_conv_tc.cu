@@ -87,7 +87,9 @@ struct alignas(64) KParams {
   long long M;
   int resident, nb_stages, coef_floats;
   int tma_in, tma_out, sa;           // TMA activation loads / TMA output store / number of activation stages
-  int xf;                            // lean kernel: warps 8-11 normalise the TMA-loaded patch in place (pro_ab) instead of draining tiles
+  int xf;                            // lean kernel, warps 8-11 transform instead of draining tiles: 1 normalise the TMA-loaded patch in
+                                     // place (pro_ab), 2 expand the low-resolution patch of a nearest x2 up-sampled source
+  int off_raw, raw_stage;            // xf == 2: ring of raw low-resolution patches (bytes)
   int ds, ds_cs;                     // 2x2 stride-2 (pixel-unshuffle) conv run as a 1x1 over four strided TMA gathers; ds_cs = source channels
   int a_stage, lbo16;                // activation stage pitch (bytes) and chunk stride (16-byte units)
   int off_a, off_b, off_coef;        // shared memory carve-up (bytes)
@@ -116,6 +118,7 @@ struct Geo {
   static constexpr int LBO_TMA = HPIX * 16;                            // TMA path: dense box image
   static constexpr int ITEMS = (HPIX * CH + kTeamThreads - 1) / kTeamThreads;
   static constexpr int SBO = MX ? 128 : (KS == 3 ? PITCH : 8) * 16;    // stride between 8-pixel core-matrix groups
+  static constexpr int RP = TW / 2 + 2, RR = TH / 2 + 2;               // low-resolution patch behind an up-sampled halo patch
 };
 
 // walks tile = blockIdx.x + k * gridDim.x and keeps its (image, tile row, tile column) without integer divisions
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
         Ring ra;
         TileWalk tw;
         tw.init(p, KS == 3 || p.ds);
-        const uint32_t stage_bytes = (uint32_t)(G::CH * G::LBO_TMA);
+        const uint32_t stage_bytes = p.xf == 2 ? (uint32_t)(G::CH * G::RP * G::RR * 16) : (uint32_t)(G::CH * G::LBO_TMA);
         for (; tw.tile < tw.end; tw.next(p)) {
           for (int c = 0; c < p.nchunks; ++c) {
             mbar_wait(a_empty + 8 * ra.s, ra.ph ^ 1);
@@ -273,7 +276,10 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
             const uint32_t fbar = (xf ? raw_full : a_full) + 8 * ra.s;
             mbar_arrive_expect_tx(fbar, stage_bytes);
             if (!(p.dbg & 1)) {
-              if (KS == 3) tma_load_5d(dst, map, 0, tw.tx * G::TW - 1, tw.ty * G::TH - 1, cb8, tw.img, fbar);
+              if (KS == 3 && p.xf == 2)   // nearest x2 source (ddpm.py:116): the (TH/2+2) x (TW/2+2) low-resolution pixels under the halo patch
+                tma_load_5d(smem_u32(smem + p.off_raw + (size_t)ra.s * p.raw_stage), map, 0, tw.tx * (G::TW / 2) - 1, tw.ty * (G::TH / 2) - 1, cb8,
+                            tw.img, fbar);
+              else if (KS == 3) tma_load_5d(dst, map, 0, tw.tx * G::TW - 1, tw.ty * G::TH - 1, cb8, tw.img, fbar);
               else if (p.ds) {
                 // chunk c covers channels [cbase % Cs, +KC) of unshuffle tap q = cbase / Cs = (p1, p2): every other pixel
                 // of the source starting at (2 ty + p1, 2 tx + p2) -- one strided TMA gather of 16 x 8 pixels
@@ -381,6 +387,22 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
       for (int c = 0; c < p.nchunks; ++c) {
         mbar_wait(raw_full + 8 * ra.s, ra.ph);
         uint8_t* stage = a_s + (size_t)ra.s * p.a_stage;
+        if (p.xf == 2) {
+          // halo pixel (hy, hx) of the up-sampled image <- low-resolution pixel ((ty0-1+hy) >> 1, (tx0-1+hx) >> 1); the raw patch
+          // starts at (ty0/2 - 1, tx0/2 - 1), so (hy+1) >> 1 and (hx+1) >> 1 index it (tile origins are even); pixels outside the
+          // up-sampled image map to rows / columns the TMA unit zero-filled
+          const uint8_t* raw = smem + p.off_raw + (size_t)ra.s * p.raw_stage;
+          for (int c8 = xw; c8 < G::CH; c8 += 4) {
+            const uint8_t* rc = raw + (size_t)c8 * (G::RP * G::RR * 16);
+            uint8_t* col = stage + (size_t)c8 * G::LBO_TMA;
+#pragma unroll 2
+            for (int hp = lane; hp < G::HPIX; hp += 32) {
+              const int hy = hp / G::PITCH, hx = hp - hy * G::PITCH;
+              *reinterpret_cast<uint4*>(col + hp * 16) =
+                  *reinterpret_cast<const uint4*>(rc + (((hy + 1) >> 1) * G::RP + ((hx + 1) >> 1)) * 16);
+            }
+          }
+        } else
         for (int c8 = xw; c8 < G::CH; c8 += 4) {
           const float4* ab = reinterpret_cast<const float4*>(p.pro_ab + ((size_t)img * 2) * p.C0 + c * KC + c8 * 8);
           const float4 a0 = __ldg(ab), a1 = __ldg(ab + 1);
@@ -819,6 +841,10 @@ size_t layout(KParams& p, int sa, int nb_stages) {
   off += (size_t)nb_stages * (MX ? 3 * NT : NT) * KC * 2;
   p.off_coef = (int)off;
   off += (size_t)(p.coef_floats + 512 + 2 * NT) * 4 + (3 * SA_MAX + 2 * SB + 4) * 8 + 16;
+  off = (off + 127) & ~(size_t)127;
+  p.off_raw = (int)off;
+  p.raw_stage = p.xf == 2 ? ((G::CH * G::RP * G::RR * 16 + 127) & ~127) : 0;
+  off += (size_t)sa * p.raw_stage;
   return off;
 }
 
@@ -1026,7 +1052,13 @@ static bool build_params(const ConvTcW& w, const ConvTcArgs& a, KParams& p) {
   p.tma_in = 0;
   if (a.ds) {
     p.tma_in = map_in_ds(&p.map_a0, a.src0, a.N, a.Hin, a.Win, a.C0, kc) ? 1 : 0;
-  } else if (!a.up) {
+  } else if (a.up) {
+    // nearest x2 source: TMA fetches the low-resolution pixels under the halo patch, transform warps replicate them
+    static int noup = -1;   // env LD_CONV_NO_XF=1: register-staging kernel instead (A/B aid)
+    if (noup < 0) { const char* e = getenv("LD_CONV_NO_XF"); noup = e ? atoi(e) : 0; }
+    const int rp = (mx ? 14 : 8) / 2 + 2, rr = (mx ? 8 : 16) / 2 + 2;
+    if (!noup && a.H == 2 * a.Hin && a.W == 2 * a.Win && map_in_3x3(&p.map_a0, a.src0, a.N, a.Hin, a.Win, a.C0, kc, rp, rr)) { p.tma_in = 1; p.xf = 2; }
+  } else {
     bool ok = w.ks == 3 ? map_in_3x3(&p.map_a0, a.src0, a.N, a.Hin, a.Win, a.C0, kc, mx ? 16 : 10, mx ? 10 : 18) : map_in_1x1(&p.map_a0, a.src0, p.M, a.C0, kc);
     if (ok && a.src1)
       ok = w.ks == 3 ? map_in_3x3(&p.map_a1, a.src1, a.N, a.Hin, a.Win, a.C1, kc, mx ? 16 : 10, mx ? 10 : 18) : map_in_1x1(&p.map_a1, a.src1, p.M, a.C1, kc);

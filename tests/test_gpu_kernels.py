@@ -22,6 +22,9 @@ CONV_CASES = [
     (256, 256, 256, 3, 1, 8, 8, 0, False),    # conv_fusion block1 shape (ddpm.py:380)
     (32, 0, 32, 3, 1, 20, 12, 0, False),      # H, W not multiples of the tile
     (96 - 32, 32, 64, 1, 1, 8, 8, 0, False),  # res_conv over a concat
+    (128, 0, 64, 3, 3, 24, 40, 1, False),     # up-sampling conv, two 64-channel chunks, ragged tiles (H, W = 24, 40)
+    (256, 0, 128, 3, 1, 16, 16, 1, False),    # up-sampling conv of the deepest level (four chunks, direct stores)
+    (32, 0, 32, 3, 2, 20, 12, 1, False),      # up-sampling conv, 32-channel chunk, H, W not multiples of the tile
 ]
 
 
