@@ -281,7 +281,7 @@ def dominant_kernel_roofline(lib, dev, B, S, hbm, src):
     byts = N * S * S * (32 + 32) * 2 + 9 * 32 * 32 * 2
     ach = byts / (ms.value / 1000.0) / 1e9
     traffic, tsrc = None, None
-    tp = os.path.join(ROOT, "profiles", "r1h_conv32_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r1v_conv32_traffic.json")
     if N == 32 and S == 256 and os.path.isfile(tp):  # the ncu capture was taken on exactly this launch shape
         t = json.load(open(tp))
         traffic, tsrc = t["traffic_bytes_per_launch"], t["source"]
