@@ -90,6 +90,8 @@ struct alignas(64) KParams {
   int xf;                            // lean kernel, warps 8-11 transform instead of draining tiles: 1 normalise the TMA-loaded patch in
                                      // place (pro_ab), 2 expand the low-resolution patch of a nearest x2 up-sampled source
   int off_raw, raw_stage;            // xf == 2: ring of raw low-resolution patches (bytes)
+  int mt, nacc;                      // mt = 2: every streamed weight stage serves TWO consecutive tiles of the CTA (two accumulators);
+                                     // nacc = accumulator stages (2, or 1 when two NT-wide accumulators already fill TMEM)
   int ds, ds_cs;                     // 2x2 stride-2 (pixel-unshuffle) conv run as a 1x1 over four strided TMA gathers; ds_cs = source channels
   int a_stage, lbo16;                // activation stage pitch (bytes) and chunk stride (16-byte units)
   int off_a, off_b, off_coef;        // shared memory carve-up (bytes)
@@ -209,7 +211,7 @@ __device__ __forceinline__ void stats_chunk(const float (&f)[16], bool valid, fl
   if ((lane & ((32 >> LOG) - 1)) == 0) atomicAdd(sacc + 2 * grp0 + (lane >> (5 - LOG)), v[0]);
 }
 
-template <int NT, int KS, int KC, bool LEAN>
+template <int NT, int KS, int KC, bool LEAN, int MT = 1>
 __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) conv_tc_kernel(const __grid_constant__ KParams p) {
   constexpr bool MX = kUseMX && KS == 3 && NT == 32;
   using G = Geo<KS, KC, MX>;
@@ -219,7 +221,9 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
   constexpr int NMMA = MX ? 3 * NT : NT;  // UMMA N
   constexpr int B_STAGE = NMMA * KC * 2;
   // two accumulator stages of NT (dual: 2 NT) fp32 columns; NT in {32,64,128,256} -> power of two >= 64
-  const uint32_t acc_cols = MX ? 4 * NT : (p.dual ? 2 * NT : NT), TM_COLS = 2 * acc_cols;   // MX: 96 + 32 (fused 1x1)
+  const int NACC = MT == 2 ? p.nacc : 2;   // MT (template): tiles per streamed weight stage, see KParams::mt
+  const uint32_t acc_cols = MX ? 4 * NT : (p.dual ? 2 * NT : NT);   // MX: 96 + 32 (fused 1x1)
+  const uint32_t acc_stride = (uint32_t)MT * acc_cols, TM_COLS = (uint32_t)NACC * acc_stride;
   const int TAPSW = TAPS + (p.dual ? 1 : 0);   // weight stages per channel chunk
   constexpr int O_ROW = NT * 2;          // bytes of one staged output row (TMA store path, NT <= 64)
   constexpr int DUALC = MX ? 3 * NT : NT; // first TMEM column of the fused-1x1 accumulator inside a stage
@@ -241,7 +245,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
   if (threadIdx.x == 0) {
     for (int i = 0; i < SA; ++i) { mbar_init(a_full + 8 * i, (p.tma_in && !xf) ? 1 : 4); mbar_init(a_empty + 8 * i, 1); mbar_init(raw_full + 8 * i, 1); }
     for (int i = 0; i < SB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, (MT == 2 && R::kEpiGroups == 2 && !xf) ? 256 : 128); }
     fence_barrier_init();
     if (p.tma_in) { tma_prefetch_desc(&p.map_a0); if (p.C1) tma_prefetch_desc(&p.map_a1); }
     if (p.tma_out) tma_prefetch_desc(&p.map_out);
@@ -263,11 +267,20 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
       // ================================================================ TMA producer (one thread) =======
       if (warp == 0 && lane == 0) {
         Ring ra;
-        TileWalk tw;
-        tw.init(p, KS == 3 || p.ds);
+        TileWalk tw0;
+        tw0.init(p, KS == 3 || p.ds);
         const uint32_t stage_bytes = p.xf == 2 ? (uint32_t)(G::CH * G::RP * G::RR * 16) : (uint32_t)(G::CH * G::LBO_TMA);
-        for (; tw.tile < tw.end; tw.next(p)) {
-          for (int c = 0; c < p.nchunks; ++c) {
+        // mt == 2: stages are filled in the order the MMA warp consumes them: (tile A, chunk c), (tile B, chunk c), ...
+        // (two named walkers + scalar selects: an indexed pair would live in local memory)
+        TileWalk twA = tw0, twB = tw0;
+        while (twA.tile < twA.end) {
+          int nm = 1;
+          if (MT == 2) { twB = twA; twB.next(p); if (twB.tile < twB.end) nm = 2; }
+          for (int cm = 0; cm < p.nchunks * nm; ++cm) {
+            const int c = nm == 2 ? (cm >> 1) : cm;
+            const bool second = nm == 2 && (cm & 1);
+            struct { int tile, img, ty, tx; } tw = {second ? twB.tile : twA.tile, second ? twB.img : twA.img, second ? twB.ty : twA.ty,
+                                                    second ? twB.tx : twA.tx};
             mbar_wait(a_empty + 8 * ra.s, ra.ph ^ 1);
             const int cbase = c * KC;
             const void* map = (p.ds || cbase < p.C0) ? (const void*)&p.map_a0 : (const void*)&p.map_a1;
@@ -292,6 +305,8 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
             }
             ra.advance(SA);
           }
+          if (nm == 2) twA = twB;
+          twA.next(p);
         }
       }
     } else if constexpr (!LEAN) {
@@ -379,12 +394,17 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
     // Padding pixels (hardware zero fill) stay exactly zero, like the reference's conv padding of the normalised tensor.
     const int xw = warp - (kEpiWarp0 + 4);
     Ring ra;
-    TileWalk tw;
-    tw.init(p, true);
-    for (; tw.tile < tw.end; tw.next(p)) {
-      const int img = tw.img, ty0 = tw.ty * G::TH, tx0 = tw.tx * G::TW;
-      const bool interior = ty0 > 0 && tx0 > 0 && ty0 + G::TH < p.H && tx0 + G::TW < p.W;
-      for (int c = 0; c < p.nchunks; ++c) {
+    TileWalk twA, twB;
+    twA.init(p, true);
+    twB = twA;
+    while (twA.tile < twA.end) {
+      int nm = 1;
+      if (MT == 2) { twB = twA; twB.next(p); if (twB.tile < twB.end) nm = 2; }
+      for (int cm = 0; cm < p.nchunks * nm; ++cm) {
+        const int c = nm == 2 ? (cm >> 1) : cm;
+        const bool second = nm == 2 && (cm & 1);
+        const int img = second ? twB.img : twA.img, ty0 = (second ? twB.ty : twA.ty) * G::TH, tx0 = (second ? twB.tx : twA.tx) * G::TW;
+        const bool interior = ty0 > 0 && tx0 > 0 && ty0 + G::TH < p.H && tx0 + G::TW < p.W;
         mbar_wait(raw_full + 8 * ra.s, ra.ph);
         uint8_t* stage = a_s + (size_t)ra.s * p.a_stage;
         if (p.xf == 2) {
@@ -429,6 +449,8 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
         if (lane == 0) mbar_arrive(a_full + 8 * ra.s);
         ra.advance(SA);
       }
+      if (nm == 2) twA = twB;
+      twA.next(p);
     }
   } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4 * R::kEpiGroups) {
     // ================================================================== epilogue ======================
@@ -459,9 +481,16 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
       }
       named_bar(ebar, 128);
     };
+    const int my_tiles = my_tile_count(p);
     for (; tw.tile < tw.end; tw.next(p), ++it_tile) {
-      const int as = it_tile & 1;
-      if (two_groups && as != eg) continue;
+      // accumulator of this tile: pair q = it_tile / MT, member mi; stage as = q % NACC, completion parity of its use
+      const int q = MT == 2 ? it_tile >> 1 : it_tile, mi = MT == 2 ? (it_tile & 1) : 0;
+      const int as = NACC == 2 ? (q & 1) : 0;
+      const uint32_t aph = (uint32_t)(NACC == 2 ? (q >> 1) : q) & 1u;
+      // two warp-groups: group eg drains accumulator stage eg (mt == 1) or member eg of every pair (mt == 2)
+      if (two_groups && (MT == 2 ? mi : as) != eg) continue;
+      // mt == 2 with one warp-group: the stage goes back to the MMA warp after the last member of the pair
+      const bool arrive_here = MT == 1 || two_groups || mi == 1 || it_tile == my_tiles - 1;
       const int img = tw.img;
       if (p.stats && img != stat_img) {
         if (stat_img >= 0) flush_stats(stat_img);
@@ -478,9 +507,9 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
         const long long gp = (long long)tw.tile * 128 + m;
         if (gp < p.M) opix = gp;
       }
-      mbar_wait(acc_full + 8 * as, (it_tile >> 1) & 1);
+      mbar_wait(acc_full + 8 * as, aph);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)as * acc_cols;
+      const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)as * acc_stride + (uint32_t)mi * acc_cols;
       // TMA store path: the store that read this staging buffer two tiles ago must have finished reading it
       if (NT <= 64 && p.tma_out) {
         if (etid == 0) { if (two_groups) bulk_wait_group_read<0>(); else bulk_wait_group_read<1>(); }
@@ -495,7 +524,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
         if (!MX) {
           tmem_ld32(trow + j1, r32);
           tmem_ld_wait();
-          if (j1 + 32 == NT && !p.dual) {   // every TMEM read of this thread is complete: hand the stage back
+          if (j1 + 32 == NT && !p.dual && arrive_here) {   // every TMEM read of this thread is complete: hand the stage back
             tc_fence_before();
             mbar_arrive(acc_empty + 8 * as);
           }
@@ -598,6 +627,12 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
         }
       }
     }
+    if (MT == 2 && two_groups && eg == 1 && (my_tiles & 1)) {
+      // the last pair has one member (drained by group 0): this group still owes its 128 arrivals on the stage
+      const int q = my_tiles >> 1, as = NACC == 2 ? (q & 1) : 0;
+      mbar_wait(acc_full + 8 * as, (uint32_t)(NACC == 2 ? (q >> 1) : q) & 1u);
+      mbar_arrive(acc_empty + 8 * as);
+    }
     if (p.stats && stat_img >= 0) flush_stats(stat_img);
     if (NT <= 64 && p.tma_out && etid == 0) bulk_wait_group<0>();
   } else if (warp == kMmaWarp) {
@@ -615,16 +650,22 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
       int it_tile = 0;
       if (p.resident) { mbar_wait(b_full, 0); tc_fence_after(); }
       const int my_tiles = my_tile_count(p);
-      for (; it_tile < my_tiles; ++it_tile) {
-        const int as = it_tile & 1;
-        mbar_wait(acc_empty + 8 * as, ((it_tile >> 1) & 1) ^ 1);
+      for (int q = 0; it_tile < my_tiles; it_tile += MT, ++q) {
+        // one iteration = one tile, or (mt == 2) a pair of consecutive tiles that share every streamed weight stage
+        const int nm = (MT == 2 && it_tile + 1 < my_tiles) ? 2 : 1;
+        const int as = NACC == 2 ? (q & 1) : 0;
+        mbar_wait(acc_empty + 8 * as, ((uint32_t)(NACC == 2 ? (q >> 1) : q) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t dcol = tmem_base + (uint32_t)as * acc_cols;
+        const uint32_t dcol = tmem_base + (uint32_t)as * acc_stride;
         uint32_t acc = 0;
         for (int c = 0; c < p.nchunks; ++c) {
+          Ring ra1 = ra;                       // stage of the pair's second tile
+          if (nm == 2) ra1.advance(SA);
           mbar_wait(a_full + 8 * ra.s, ra.ph);
+          if (nm == 2) mbar_wait(a_full + 8 * ra1.s, ra1.ph);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + (uint32_t)ra.s * a_stage16;
+          const uint32_t a_lo1 = a_lo0 + (uint32_t)ra1.s * a_stage16;
           if (p.resident) {
             const uint32_t b_lo = b_lo0 + (uint32_t)(c * TAPSW * (B_STAGE >> 4));
             if (elect_one()) {
@@ -670,14 +711,21 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
                                  (c > 0 || k > 0) ? 1u : 0u);
                 } else {
 #pragma unroll
-                  for (int k = 0; k < KC / 16; ++k) {
-                    umma_bf16_lh(dcol, a_t + (uint32_t)(2 * k) * lbo16, a_hi, b_lo + (uint32_t)(2 * k * NMMA), b_hi, idesc, acc);
-                    acc = 1;
+                  for (int k = 0; k < KC / 16; ++k)
+                    umma_bf16_lh(dcol, a_t + (uint32_t)(2 * k) * lbo16, a_hi, b_lo + (uint32_t)(2 * k * NMMA), b_hi, idesc, (acc | (uint32_t)k) ? 1u : 0u);
+                  if (nm == 2) {   // same weight stage, second tile of the pair, second accumulator
+                    const uint32_t a_t1 = a_lo1 + (uint32_t)(ky * G::PITCH + kx);
+#pragma unroll
+                    for (int k = 0; k < KC / 16; ++k)
+                      umma_bf16_lh(dcol + acc_cols, a_t1 + (uint32_t)(2 * k) * lbo16, a_hi, b_lo + (uint32_t)(2 * k * NMMA), b_hi, idesc,
+                                   (acc | (uint32_t)k) ? 1u : 0u);
                   }
+                  acc = 1;
                 }
                 umma_commit(b_empty + 8 * rb.s);
                 if (tap == TAPSW - 1) {
                   umma_commit(a_empty + 8 * ra.s);
+                  if (nm == 2) umma_commit(a_empty + 8 * ra1.s);
                   if (c == p.nchunks - 1) umma_commit(acc_full + 8 * as);
                 }
               }
@@ -687,6 +735,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
             }
           }
           ra.advance(SA);
+          if (nm == 2) ra.advance(SA);
         }
       }
     }
@@ -701,7 +750,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
       } else {
         Ring rb;
         const int my_tiles = my_tile_count(p);
-        for (int it = 0; it < my_tiles; ++it) {
+        for (int it = 0; it < my_tiles; it += MT) {
           for (int i = 0; i < total; ++i) {
             mbar_wait(b_empty + 8 * rb.s, rb.ph ^ 1);
             mbar_arrive_expect_tx(b_full + 8 * rb.s, B_STAGE);
@@ -811,6 +860,9 @@ bool map_out(CUtensorMap* m, void* ptr, int N, int H, int W, int Cout, int nt, i
 template <int NT, int KS, int KC>
 int configure_one() {
   if (cudaFuncSetAttribute(conv_tc_kernel<NT, KS, KC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg().max_smem) != cudaSuccess) return -1;
+  if constexpr (NT >= 128) {
+    if (cudaFuncSetAttribute(conv_tc_kernel<NT, KS, KC, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg().max_smem) != cudaSuccess) return -1;
+  }
   return cudaFuncSetAttribute(conv_tc_kernel<NT, KS, KC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg().max_smem) == cudaSuccess ? 0 : -1;
 }
 template <int KS, int KC>
@@ -852,14 +904,22 @@ template <int NT, int KS, int KC>
 int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
   constexpr bool MX = kUseMX && KS == 3 && NT == 32;
   const int total = p.nchunks * ((MX ? 3 : KS * KS) + (p.dual ? 1 : 0));
-  const int tm_cols = MX ? 8 * NT : (p.dual ? 4 : 2) * NT;   // TMEM columns per CTA (two accumulator stages)
   const size_t limit = (size_t)cfg().max_smem < kResidentBudget ? (size_t)cfg().max_smem : kResidentBudget;
   // weights resident in shared memory when everything fits; more activation stages when fed by TMA
   int sa = p.tma_in ? 4 : 3;
   p.resident = layout<NT, KS, KC>(p, sa, total) <= limit ? 1 : 0;
   p.nb_stages = p.resident ? total : SB;
+  // Streamed weights: a stage (NT x KC) feeds KC/16 MMAs of NT/2 clocks each, i.e. the ring must take in 64 B/clk per SM and its
+  // four stages cover ~1 us of MMA work -- less than the L2 latency under load (tensor pipe 58 % busy, ncu).  With mt = 2 every
+  // stage serves two consecutive tiles of the CTA (two accumulators): half the weight traffic per FLOP, twice the cover.
+  static int mt_env = -1;   // env LD_CONV_MT=1 disables (A/B aid)
+  if (mt_env < 0) { const char* e = getenv("LD_CONV_MT"); mt_env = e ? atoi(e) : 2; }
+  // (not with the in-place normalise mode: its single epilogue warp-group would drain both accumulators back to back -- measured slower)
+  p.mt = (p.tma_in && !p.resident && NT >= 128 && KS == 3 && !p.dual && p.xf != 1 && mt_env == 2) ? 2 : 1;
   size_t smem = layout<NT, KS, KC>(p, sa, p.nb_stages);
-  if (smem > (size_t)cfg().max_smem) { sa = 3; smem = layout<NT, KS, KC>(p, sa, p.nb_stages); }
+  if (smem > (size_t)cfg().max_smem) { sa = 3; p.mt = 1; smem = layout<NT, KS, KC>(p, sa, p.nb_stages); }   // pairs need four activation stages
+  p.nacc = (p.mt == 2 && NT == 256) ? 1 : 2;
+  const int tm_cols = MX ? 8 * NT : (p.mt == 2 ? p.nacc * 2 * NT : (p.dual ? 4 : 2) * NT);   // TMEM columns per CTA
   if (smem > (size_t)cfg().max_smem) return -1;
   if (p.tma_in && sa == 4) {   // a third co-resident CTA is worth more than a fourth activation stage
     const size_t smem3 = layout<NT, KS, KC>(p, 3, p.nb_stages);
@@ -890,6 +950,9 @@ int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
     p.step_img = gx / tpi;
     const int r = gx - p.step_img * tpi;
     p.step_ty = r / p.tiles_x; p.step_tx = r - p.step_ty * p.tiles_x;
+  }
+  if constexpr (NT >= 128) {
+    if (lean && p.mt == 2) { conv_tc_kernel<NT, KS, KC, true, 2><<<dim3((unsigned)gx, (unsigned)ntiles_y), Roles<true>::kThreads, smem, s>>>(p); return 1; }
   }
   if (lean) conv_tc_kernel<NT, KS, KC, true><<<dim3((unsigned)gx, (unsigned)ntiles_y), Roles<true>::kThreads, smem, s>>>(p);
   else conv_tc_kernel<NT, KS, KC, false><<<dim3((unsigned)gx, (unsigned)ntiles_y), Roles<false>::kThreads, smem, s>>>(p);
