@@ -122,6 +122,9 @@ struct Engine {
   int64_t launches = 0;
   int64_t opt_micro_batch = 0, opt_use_graph = 1, opt_debug_keep = 0, opt_la_exact = 0, opt_attn_simt = 0;
   unsigned int* la_flag = nullptr;        // soft-max underflow counter of the fused LinearAttention
+  // sampler: FiLM rows of every timestep [film_tab_T][film_total] -- time MLP + block MLPs depend on t only (ddpm.py:339-344,191-194),
+  // so the loop gathers a row instead of running them
+  float* film_tab = nullptr; int film_tab_T = 0;
   std::map<std::string, std::unique_ptr<Plan>> plans;
   std::map<std::string, Staged> staged;   // stand-alone entry points (ld_unet_forward / ld_cond_encode)
   // sampler-owned state
@@ -146,6 +149,7 @@ struct Engine {
     for (auto& kv : attn) linattn_tc_free(&kv.second.la);
     conv7_tc_free(&init_tc);
     if (la_flag) cudaFree(la_flag);
+    if (film_tab) cudaFree(film_tab);
     if (coef1) cudaFree(coef1);
     if (coef2) cudaFree(coef2);
     if (sigma) cudaFree(sigma);
@@ -749,7 +753,12 @@ static int build_unet_plan(Engine& E, Plan& P, int N, int H, int W, const float*
     tp.neg_step = (float)(-(std::log((double)E.d.sinusoidal_theta) / (double)(E.d.dim / 2 - 1)));
     tp.w1 = E.tw1; tp.b1 = E.tb1; tp.w2 = E.tw2; tp.b2 = E.tb2; tp.st = (float*)st.p;
     tp.wf = E.film_w; tp.bf_ = E.film_b; tp.total = E.film_total; tp.film = (float*)fl.p;
-    B.op([tp](cudaStream_t s) { return launch_time_film(tp, s); });
+    Engine* Ep = &E;
+    B.op([tp, Ep](cudaStream_t s) {
+      // sampler loop: one shared timestep whose row was precomputed (ensure_film_table); else run the two MLPs
+      if (tp.t_scalar && Ep->film_tab && (Ep->film_total & 3) == 0) return launch_film_gather(Ep->film_tab, tp.total, tp.t_scalar, tp.film, s);
+      return launch_time_film(tp, s);
+    });
   }
   Ten h = B.act(N, H, W, E.d.init_dim);
   {
@@ -1086,6 +1095,32 @@ static int prepare_sampler(Engine& E, const ld_sample_desc& sd) {
   return 0;
 }
 
+// FiLM rows for t = 0 .. T-1 (once per handle and T): the same two kernels the per-step path runs, on T "images"
+static int ensure_film_table(Engine& E, int T, cudaStream_t s) {
+  if (E.film_tab && E.film_tab_T >= T) return 0;
+  if (E.film_tab) { cudaFree(E.film_tab); E.film_tab = nullptr; E.film_tab_T = 0; }
+  if (E.film_total & 3) return 0;   // (row gathers are 16-byte vectors)
+  float* tab = nullptr; float* st = nullptr; int64_t* tt = nullptr;
+  const int td = 4 * E.d.dim;
+  CK(cudaMalloc(&tab, (size_t)T * E.film_total * sizeof(float)));
+  CK(cudaMalloc(&st, (size_t)T * td * sizeof(float)));
+  CK(cudaMalloc(&tt, (size_t)T * sizeof(int64_t)));
+  std::vector<int64_t> th(T);
+  for (int i = 0; i < T; ++i) th[i] = i;
+  CK(cudaMemcpyAsync(tt, th.data(), (size_t)T * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  TimeP tp{};
+  tp.t = tt; tp.t_scalar = nullptr; tp.N = T; tp.dim = E.d.dim; tp.theta = E.d.sinusoidal_theta;
+  tp.neg_step = (float)(-(std::log((double)E.d.sinusoidal_theta) / (double)(E.d.dim / 2 - 1)));
+  tp.w1 = E.tw1; tp.b1 = E.tb1; tp.w2 = E.tw2; tp.b2 = E.tb2; tp.st = st;
+  tp.wf = E.film_w; tp.bf_ = E.film_b; tp.total = E.film_total; tp.film = tab;
+  E.launches += launch_time_film(tp, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  cudaFree(st); cudaFree(tt);
+  if (e != cudaSuccess) { cudaFree(tab); return fail(LD_ERR_CUDA, "FiLM table failed: %s", cudaGetErrorString(e)); }
+  E.film_tab = tab; E.film_tab_T = T;
+  return 0;
+}
+
 static StepP make_step(Engine& E, const ld_sample_desc& sd, int kind, const float* noise, float* x0_trace) {
   auto& S = E.ss;
   const long long n = (long long)sd.batch * sd.height * sd.width;
@@ -1126,6 +1161,7 @@ int ld_sample(ld_handle* h, const ld_sample_desc* sdp, const float* cond, const 
   if (sd.branch_out && !mask) return fail(LD_ERR_INVALID, "branch mode needs a mask");
   if ((rc = check_shape(E, sd.height, sd.width))) return rc;
   if ((rc = prepare_sampler(E, sd))) return rc;
+  if ((rc = ensure_film_table(E, E.T, E.own_stream))) return rc;
   auto& S = E.ss;
   cudaStream_t cs = (cudaStream_t)stream, s = E.own_stream;
   const long long n = (long long)sd.batch * sd.height * sd.width;
@@ -1229,6 +1265,7 @@ int ld_sample_ddim(ld_handle* h, const ld_sample_desc* sdp, const float* cond, c
   if (sd.branch_out && !mask) return fail(LD_ERR_INVALID, "branch mode needs a mask");
   if ((rc = check_shape(E, sd.height, sd.width))) return rc;
   if ((rc = prepare_sampler(E, sd))) return rc;
+  if (E.T && (rc = ensure_film_table(E, E.T, E.own_stream))) return rc;
   auto& S = E.ss;
   cudaStream_t cs = (cudaStream_t)stream, s = E.own_stream;
   const long long n = (long long)sd.batch * sd.height * sd.width;

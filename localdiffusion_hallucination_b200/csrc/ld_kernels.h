@@ -61,6 +61,8 @@ struct TimeP {
   float* film;        // [N][total]
 };
 int launch_time_film(const TimeP& p, cudaStream_t s);
+// film[0][:] = table[*t][:] (the sampler's per-timestep FiLM rows are precomputed once: they depend on t only)
+int launch_film_gather(const float* table, int total, const int* t_scalar, float* film, cudaStream_t s);
 
 // sampler elementwise kernels (ddpm.py:672-690, 697-708, 775-810, 852-858)
 struct PrepP {

@@ -820,6 +820,16 @@ int launch_time_film(const TimeP& p, cudaStream_t s) {
   return launches;
 }
 
+__global__ void film_gather_kernel(const float* __restrict__ table, int total, const int* __restrict__ t_scalar, float* __restrict__ film) {
+  const float4* src = reinterpret_cast<const float4*>(table + (size_t)(*t_scalar) * total);
+  float4* dst = reinterpret_cast<float4*>(film);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total / 4; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+int launch_film_gather(const float* table, int total, const int* t_scalar, float* film, cudaStream_t s) {
+  film_gather_kernel<<<cdiv(total / 4, 256), 256, 0, s>>>(table, total, t_scalar, film);
+  return 1;
+}
+
 // =================================================================================================
 // sampler elementwise kernels
 // =================================================================================================
