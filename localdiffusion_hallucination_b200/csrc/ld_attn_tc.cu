@@ -100,9 +100,9 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const AttnParams p
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < KV_STAGES; ++i) { mbar_init(kv_full + 8 * i, 1); mbar_init(kv_empty + 8 * i, 1); }
-    mbar_init(s_full, 1); mbar_init(s_empty, 128);
-    mbar_init(p_full, 128); mbar_init(p_empty, 1);
-    mbar_init(o_full, 1); mbar_init(o_empty, 128);
+    mbar_init(s_full, 1); mbar_init(s_empty, 4);      // one arrival per soft-max warp
+    mbar_init(p_full, 4); mbar_init(p_empty, 1);
+    mbar_init(o_full, 1); mbar_init(o_empty, 4);
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), 256);
@@ -171,43 +171,46 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const AttnParams p
       const int kvalid = p.n - j * 128;               // keys of this block that exist
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row max
-      float mx = m;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t sr[32];
-        tmem_ld32(lane_base + (uint32_t)c0, sr);
-        tmem_ld_wait();
+      // the whole 128-key row of S goes to registers ONCE (TMEM reads run at 64 B/clk per SM and each costs a round trip);
+      // the stage is handed back to the MMA warp right after
+      uint32_t sr[128];
+      tmem_ld32(lane_base, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
+      tmem_ld32(lane_base + 32u, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
+      tmem_ld32(lane_base + 64u, *reinterpret_cast<uint32_t(*)[32]>(&sr[64]));
+      tmem_ld32(lane_base + 96u, *reinterpret_cast<uint32_t(*)[32]>(&sr[96]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);
+      if (kvalid < 128) {                              // ragged last block: keys past n carry no weight
 #pragma unroll
-        for (int c = 0; c < 32; ++c) if (c0 + c < kvalid) mx = fmaxf(mx, __uint_as_float(sr[c]));
+        for (int c = 0; c < 128; ++c) if (c >= kvalid) sr[c] = 0xff800000u;   // -inf
       }
+      float mx4[4] = {m, m, m, m};
+#pragma unroll
+      for (int c = 0; c < 128; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], __uint_as_float(sr[c]));
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float alpha = ex2_approx(m - mx);          // m = -inf on the first block: alpha = 0, o = l = 0 anyway
       m = mx;
       mbar_wait(p_empty, (j & 1) ^ 1);                 // the previous P has been consumed
-      // pass 2: p = exp2(s - m), row sum, P -> smem
-      float su = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t sr[32];
-        tmem_ld32(lane_base + (uint32_t)c0, sr);
-        tmem_ld_wait();
-        if (c0 == 96) { tc_fence_before(); mbar_arrive(s_empty); }
-        uint32_t pk[16];
+      // p = exp2(s - m), row sum, P -> smem
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          float e0 = ex2_approx(__uint_as_float(sr[2 * c]) - mx), e1 = ex2_approx(__uint_as_float(sr[2 * c + 1]) - mx);
-          if (c0 + 2 * c >= kvalid) e0 = 0.f;
-          if (c0 + 2 * c + 1 >= kvalid) e1 = 0.f;
-          su += e0 + e1;
+      for (int c8 = 0; c8 < 16; ++c8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float e0 = ex2_approx(__uint_as_float(sr[8 * c8 + 2 * c]) - mx), e1 = ex2_approx(__uint_as_float(sr[8 * c8 + 2 * c + 1]) - mx);
+          s4[c] += e0 + e1;
           pk[c] = pack_bf16x2(e0, e1);
         }
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          *reinterpret_cast<uint4*>(p_s + (size_t)(c0 / 8 + c) * 2048 + row * 16) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        *reinterpret_cast<uint4*>(p_s + (size_t)c8 * 2048 + row * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
+      const float su = (s4[0] + s4[1]) + (s4[2] + s4[3]);
       l = l * alpha + su;
       fence_proxy_async();
-      mbar_arrive(p_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
       // consume O_blk of the PREVIOUS block while the tensor core works on this one's P V
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1);
@@ -216,7 +219,8 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const AttnParams p
         tmem_ld32(lane_base + 128u, orr);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(o_empty);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_empty);
 #pragma unroll
         for (int d = 0; d < 32; ++d) o[d] = fmaf(o[d], alpha_prev, __uint_as_float(orr[d]));
       }
