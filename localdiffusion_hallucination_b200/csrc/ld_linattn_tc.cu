@@ -313,6 +313,9 @@ __global__ void __launch_bounds__(kThreads, CtxCfg<C>::CTAS) la_ctx_kernel(const
     for (int i = 0; i < K::NB && i < nh; ++i) mma1(i);
     for (int j = 0; j < nh; ++j) {      // Z += P(j) . xhat(j)
       const int b = j & (K::NB - 1), sj = j % K::XS;
+      // K^T of the tile that reuses this buffer first: its transform group released the buffer right after reading it, long before
+      // it delivers P(j) -- issuing it here (not after MMA2(j)) keeps that group's next tile ready when it comes back
+      if (j + K::NB < nh) mma1(j + K::NB);
       mbar_wait(p_full + 8 * b, (j >> K::LOGNB) & 1);
       tc_fence_after();
       if (elect_one()) {
@@ -325,7 +328,6 @@ __global__ void __launch_bounds__(kThreads, CtxCfg<C>::CTAS) la_ctx_kernel(const
         umma_commit(x_empty + 8 * sj);
       }
       __syncwarp();
-      if (j + K::NB < nh) mma1(j + K::NB);
     }
     if (elect_one()) umma_commit(z_full);
     __syncwarp();
@@ -350,22 +352,18 @@ __global__ void __launch_bounds__(kThreads, CtxCfg<C>::CTAS) la_ctx_kernel(const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(d1_empty + 8 * b);
+      // exponentiate in registers first (packed in place), then wait for the P buffer: the MMA2 round trip of the tile that
+      // last used it hides behind the ex2 work
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        kr0[j] = pack_bf16x2(ex2_approx(__uint_as_float(kr0[2 * j])), ex2_approx(__uint_as_float(kr0[2 * j + 1])));
+        kr1[j] = pack_bf16x2(ex2_approx(__uint_as_float(kr1[2 * j])), ex2_approx(__uint_as_float(kr1[2 * j + 1])));
+      }
       mbar_wait(p_empty + 8 * b, par ^ 1);                   // MMA2 of the tile that last used this P buffer has consumed it
 #pragma unroll
       for (int c = 0; c < 4; ++c) {     // chunks of 8 pixels along K
-        uint32_t pk[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          pk[j] = pack_bf16x2(ex2_approx(__uint_as_float(kr0[8 * c + 2 * j])), ex2_approx(__uint_as_float(kr0[8 * c + 2 * j + 1])));
-        *reinterpret_cast<uint4*>(pbuf + (size_t)c * 2048) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          pk[j] = pack_bf16x2(ex2_approx(__uint_as_float(kr1[8 * c + 2 * j])), ex2_approx(__uint_as_float(kr1[8 * c + 2 * j + 1])));
-        *reinterpret_cast<uint4*>(pbuf + (size_t)(4 + c) * 2048) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(pbuf + (size_t)c * 2048) = make_uint4(kr0[4 * c], kr0[4 * c + 1], kr0[4 * c + 2], kr0[4 * c + 3]);
+        *reinterpret_cast<uint4*>(pbuf + (size_t)(4 + c) * 2048) = make_uint4(kr1[4 * c], kr1[4 * c + 1], kr1[4 * c + 2], kr1[4 * c + 3]);
       }
       fence_proxy_async();
       __syncwarp();
@@ -534,7 +532,7 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
       }
       __syncwarp();
     };
-    for (int i = 0; i < nt; ++i) {
+    auto mma1 = [&](int i) {
       const int s = i % K::XS, g = i & 1, u = i >> 1;
       mbar_wait(x_full + 8 * s, (i / K::XS) & 1);
       mbar_wait(d1_empty + 8 * g, (u & 1) ^ 1);
@@ -549,6 +547,12 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
         umma_commit(d1_full + 8 * g);
       }
       __syncwarp();
+    };
+    // Q of tile i+1 before the second MMA of tile i-1: its group frees the Q buffer three quarters into the soft-max of tile i-1
+    // and delivers P(i-1) only at the end -- this order has Q(i+1) waiting when the group comes back
+    mma1(0);
+    for (int i = 0; i < nt; ++i) {
+      if (i + 1 < nt) mma1(i + 1);
       if (i >= 1) mma2(i - 1);
     }
     mma2(nt - 1);
