@@ -90,6 +90,7 @@ struct alignas(64) KParams {
   int xf;                            // lean kernel, warps 8-11 transform instead of draining tiles: 1 normalise the TMA-loaded patch in
                                      // place (pro_ab), 2 expand the low-resolution patch of a nearest x2 up-sampled source
   int off_raw, raw_stage;            // xf == 2: ring of raw low-resolution patches (bytes)
+  int obuf;                          // output staging buffers (TMA store path): 2, or 4 = two per epilogue warp-group
   int mt, nacc;                      // mt = 2: every streamed weight stage serves TWO consecutive tiles of the CTA (two accumulators);
                                      // nacc = accumulator stages (2, or 1 when two NT-wide accumulators already fill TMEM)
   int ds, ds_cs;                     // 2x2 stride-2 (pixel-unshuffle) conv run as a 1x1 over four strided TMA gathers; ds_cs = source channels
@@ -463,7 +464,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
     const int m = ew * 32 + lane;
     const int nbase = n_tile * NT;
     const int cpg = p.stats ? p.Cout / p.stats_G : 1;
-    int it_tile = 0;
+    int it_tile = 0, n_mine = 0;
     TileWalk tw;
     const bool tile2d = KS == 3 || p.ds;
     tw.init(p, tile2d);
@@ -511,13 +512,17 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)as * acc_stride + (uint32_t)mi * acc_cols;
       // TMA store path: the store that read this staging buffer two tiles ago must have finished reading it
+      // (ncu source view: with ONE staging buffer per warp-group 31 % of the stall samples sat here, waiting for the previous tile's
+      // store to drain; every group now alternates between two buffers)
+      const int ob = two_groups ? (p.obuf == 4 ? 2 * eg + (n_mine & 1) : eg) : as;
+      ++n_mine;
       if (NT <= 64 && p.tma_out) {
-        if (etid == 0) { if (two_groups) bulk_wait_group_read<0>(); else bulk_wait_group_read<1>(); }
+        if (etid == 0) { if (two_groups && p.obuf != 4) bulk_wait_group_read<0>(); else bulk_wait_group_read<1>(); }
         named_bar(ebar, 128);
       }
       // staged output row: MX tiles are 8 x 14 pixels dense (patch columns 14, 15 of every row produce nothing)
       const int orow_i = MX ? (m >> 4) * G::TW + (m & 15) : m;
-      uint8_t* orow = o_s + (size_t)as * (128 * O_ROW) + (size_t)orow_i * O_ROW;
+      uint8_t* orow = o_s + (size_t)ob * (128 * O_ROW) + (size_t)orow_i * O_ROW;
 #pragma unroll 1
       for (int j1 = 0; j1 < NT; j1 += 32) {
         uint32_t r32[32];
@@ -618,7 +623,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
         named_bar(ebar, 128);
         if (etid == 0) {
           if (!(p.dbg & 4)) {
-            const uint32_t src = smem_u32(o_s + (size_t)as * (128 * O_ROW));
+            const uint32_t src = smem_u32(o_s + (size_t)ob * (128 * O_ROW));
             if (MX) tma_store_4d(&p.map_out, nbase, tw.tx * G::TW, tw.ty * G::TH, img, src);
             else if (tile2d) tma_store_4d(&p.map_out, nbase, tw.tx * 8, tw.ty * 16, img, src);
             else tma_store_2d(&p.map_out, nbase, tw.tile * 128, src);
@@ -882,7 +887,8 @@ size_t layout(KParams& p, int sa, int nb_stages) {
   constexpr bool MX = kUseMX && KS == 3 && NT == 32;
   using G = Geo<KS, KC, MX>;
   size_t off = 0;
-  if (p.tma_out) off += 2 * 128 * NT * 2;                      // output staging (1024-byte aligned, first)
+  // output staging (1024-byte aligned, first): two buffers per epilogue warp-group
+  if (p.tma_out) off += (size_t)(p.obuf == 4 ? 4 : 2) * 128 * NT * 2;
   p.off_a = (int)off;
   p.a_stage = p.tma_in ? G::CH * G::LBO_TMA : G::CH * G::LBO_REG;
   p.a_stage = (p.a_stage + 127) & ~127;
@@ -907,6 +913,7 @@ int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
   const size_t limit = (size_t)cfg().max_smem < kResidentBudget ? (size_t)cfg().max_smem : kResidentBudget;
   // weights resident in shared memory when everything fits; more activation stages when fed by TMA
   int sa = p.tma_in ? 4 : 3;
+  p.obuf = 2;
   p.resident = layout<NT, KS, KC>(p, sa, total) <= limit ? 1 : 0;
   p.nb_stages = p.resident ? total : SB;
   // Streamed weights: a stage (NT x KC) feeds KC/16 MMAs of NT/2 clocks each, i.e. the ring must take in 64 B/clk per SM and its
@@ -928,6 +935,17 @@ int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
     else layout<NT, KS, KC>(p, sa, p.nb_stages);
   }
   p.sa = sa;
+  if (p.tma_out && p.tma_in && !p.xf && LD_CONV_EG == 2) {
+    // a second staging buffer per epilogue warp-group (the store of the previous tile drains while the next tile is staged) --
+    // unless the extra shared memory costs a co-resident CTA
+    const int occ2 = (int)((size_t)cfg().max_smem_sm / (smem + 1024));
+    p.obuf = 4;
+    const size_t smem4 = layout<NT, KS, KC>(p, sa, p.nb_stages);
+    const int occ4 = (int)((size_t)cfg().max_smem_sm / (smem4 + 1024));
+    const int cap = Roles<true>::kMinCtas < 512 / tm_cols ? Roles<true>::kMinCtas : 512 / tm_cols;
+    if (smem4 <= (size_t)cfg().max_smem && (occ4 >= occ2 || occ4 >= cap)) smem = smem4;
+    else { p.obuf = 2; layout<NT, KS, KC>(p, sa, p.nb_stages); }
+  }
   // persistent grid: as many CTAs as are co-resident (registers allow two per SM; 2*NT of 512 TMEM columns each)
   const bool lean = p.tma_in != 0;
   int occ = (int)((size_t)cfg().max_smem_sm / (smem + 1024));

@@ -23,6 +23,7 @@
 #include <cuda_bf16.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -155,12 +156,19 @@ __device__ __forceinline__ void produce_x(const __nv_bfloat16* __restrict__ ximg
 // Same producer fed by the bulk-copy engine: a stage of x is ROWS*C*2 contiguous bytes in global memory, so one lane
 // issues cp.async.bulk copies RS stages ahead into a raw ring (no registers, no scoreboards tied up: the register
 // FIFO above cannot keep more than ~6 load batches in flight per warp), and the four warps normalise smem -> smem.
+// Thread = pixel: the whole channel row (C * 2 bytes) is summed and scaled by one thread -- no shuffles, C/8 independent 16-byte
+// items in flight -- and for 64-pixel stages the four warps split into two teams that normalise alternate stages concurrently
+// (ncu source view: with four lanes per pixel and one stage at a time the MMA warp waited on x_full > 50 % of the time in both
+// passes; the producers, not the exponentials, bounded LinearAttention).  kXArrivals = warps that arrive per stage.
+template <int ROWS> struct XTeams { static constexpr int TEAMS = 128 / ROWS, kArrivals = ROWS / 32; };
 template <int C, int ROWS, int XS, int RS, bool EXT = false>
 __device__ __forceinline__ void produce_x_raw(const __nv_bfloat16* __restrict__ ximg, int first, int count, int HW, uint8_t* x_s,
                                               int x_stage_bytes, uint32_t x_full, uint32_t x_empty, uint8_t* raw_s, uint32_t raw_full,
                                               uint32_t raw_empty, int tid, int lane) {
-  constexpr int LP = C / 8, ITEMS = ROWS * LP / 128, RAWB = ROWS * C * 2;
-  const int c8 = tid % LP;
+  constexpr int LPX = C / 8, RAWB = ROWS * C * 2, TEAMS = XTeams<ROWS>::TEAMS;
+  static_assert(RS % TEAMS == 0 && XS % TEAMS == 0 || TEAMS == 1, "a team must own fixed ring slots (it has to observe every barrier phase)");
+  const int team = tid / ROWS, p = tid - team * ROWS;
+  int issued = 0;
   auto issue = [&](int j) {
     const int slot = j % RS;
     mbar_wait(raw_empty + 8 * slot, ((j / RS) & 1) ^ 1);
@@ -170,39 +178,52 @@ __device__ __forceinline__ void produce_x_raw(const __nv_bfloat16* __restrict__ 
     mbar_arrive_expect_tx(raw_full + 8 * slot, bytes);
     bulk_g2s(smem_u32(raw_s + (size_t)slot * RAWB), ximg + (size_t)px0 * C, bytes, raw_full + 8 * slot);
   };
-  if (tid == 0)
-    for (int j = 0; j < RS - 1 && j < count; ++j) issue(j);
-  for (int i = 0; i < count; ++i) {
-    if (tid == 0 && i + RS - 1 < count) issue(i + RS - 1);
+  for (int i = team; i < count; i += TEAMS) {
+    if (tid == 0)   // one lane keeps RS raw stages in flight for both teams
+      while (issued < count && issued < i + RS) issue(issued++);
     const int slot = i % RS, s = i % XS;
     const int valid = HW - (first + i) * ROWS;               // pixels of this stage that exist (may exceed ROWS)
     mbar_wait(raw_full + 8 * slot, (i / RS) & 1);
-    mbar_wait(x_empty + 8 * s, ((i / XS) & 1) ^ 1);
-    const uint8_t* raw = raw_s + (size_t)slot * RAWB;
-    uint8_t* stage = x_s + (size_t)s * x_stage_bytes;
+    const uint8_t* raw = raw_s + (size_t)slot * RAWB + (size_t)p * (C * 2);
+    constexpr bool KEEP = LPX <= 4;                          // wider rows are read twice instead of held in registers
+    uint4 v[KEEP ? LPX : 1];
+    float ssp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-      const int p = (k * 128 + tid) / LP;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (p < valid) v = *reinterpret_cast<const uint4*>(raw + (size_t)p * (C * 2) + c8 * 16);
-      const uint32_t in[4] = {v.x, v.y, v.z, v.w};
-      float f[8];
-      float ss = 0.f;
+    for (int j = 0; j < LPX; ++j) {
+      const int cj = (j + p) & (LPX - 1);                    // rotated chunk order: 64/128-byte row strides would conflict 4-way
+      uint4 w = make_uint4(0u, 0u, 0u, 0u);
+      if (p < valid) w = *reinterpret_cast<const uint4*>(raw + cj * 16);
+      if (KEEP) v[j] = w;
+      const uint32_t in[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 t = unpack_bf16x2(in[j]);
-        f[2 * j] = t.x; f[2 * j + 1] = t.y;
-        ss = fmaf(t.x, t.x, ss); ss = fmaf(t.y, t.y, ss);
+      for (int e = 0; e < 4; ++e) {
+        const float2 t = unpack_bf16x2(in[e]);
+        ssp[e] = fmaf(t.x, t.x, ssp[e]); ssp[e] = fmaf(t.y, t.y, ssp[e]);
       }
+    }
+    const float ss = (ssp[0] + ssp[1]) + (ssp[2] + ssp[3]);
+    const float inv = rsqrtf(fmaxf(ss, 1e-24f));             // 1 / max(|x|, 1e-12): F.normalize(x, dim=1) (ddpm.py:132)
+    mbar_wait(x_empty + 8 * s, ((i / XS) & 1) ^ 1);
+    uint8_t* stage = x_s + (size_t)s * x_stage_bytes + p * 16;
 #pragma unroll
-      for (int o = 1; o < LP; o <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      const float inv = rsqrtf(fmaxf(ss, 1e-24f));           // 1 / max(|x|, 1e-12): F.normalize(x, dim=1) (ddpm.py:132)
+    for (int j = 0; j < LPX; ++j) {
+      const int cj = (j + p) & (LPX - 1);
+      uint4 w = make_uint4(0u, 0u, 0u, 0u);
+      if (KEEP) w = v[j];
+      else if (p < valid) w = *reinterpret_cast<const uint4*>(raw + cj * 16);
+      const uint32_t in[4] = {w.x, w.y, w.z, w.w};
       uint32_t o4[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o4[j] = pack_bf16x2(f[2 * j] * inv, f[2 * j + 1] * inv);
-      *reinterpret_cast<uint4*>(stage + (size_t)c8 * (ROWS * 16) + p * 16) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+      for (int e = 0; e < 4; ++e) {
+        const float2 t = unpack_bf16x2(in[e]);
+        o4[e] = pack_bf16x2(t.x * inv, t.y * inv);
+      }
+      *reinterpret_cast<uint4*>(stage + (size_t)cj * (ROWS * 16)) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
     }
-    if (EXT) write_ext<ROWS>(stage, C / 8, valid, tid);
+    if (EXT) {   // ones channel (0 past the end of the image) + 7 zero channels, then a zero chunk: see write_ext
+      *reinterpret_cast<uint4*>(stage + (size_t)LPX * (ROWS * 16)) = make_uint4(p < valid ? 0x3F80u : 0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(stage + (size_t)(LPX + 1) * (ROWS * 16)) = make_uint4(0u, 0u, 0u, 0u);
+    }
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) { mbar_arrive(x_full + 8 * s); mbar_arrive(raw_empty + 8 * slot); }
@@ -218,11 +239,13 @@ struct CtxCfg {
   static constexpr int CTAS = C >= 128 ? 1 : 2;       // co-resident CTAs per SM (C <= 64: 256 TMEM columns and < 113 KB each)
   static constexpr int NB = C >= 128 ? 4 : 2;         // K^T (TMEM) and P (smem) buffers: NB / 2 per transform warp-group
   static constexpr int LOGNB = C >= 128 ? 2 : 1;
-  static constexpr int XS = C >= 128 ? 6 : (C >= 64 ? 5 : 6);   // xhat stages: released only after MMA2
+  static constexpr int XS = C >= 128 ? 6 : (C >= 64 ? 4 : 6);   // xhat stages: released only after MMA2 (even, like RS: producer teams)
   static constexpr int X_STAGE = 64 * CE * 2;         // xhat [CE/8][64 px][16 B]: K-major for MMA1, MN-major for MMA2
   static constexpr int W_BYTES = 128 * CE * 2;
   static constexpr int P_BYTES = 128 * 64 * 2;        // one P buffer
-  static constexpr int RS = C >= 128 ? 0 : (C >= 64 ? 2 : 3);   // raw x ring fed by cp.async.bulk (C = 128: register FIFO)
+  // raw x ring fed by cp.async.bulk (C = 128: register FIFO).  EVEN: the two producer teams take alternate stages, and a team must see
+  // every phase of the raw_full barriers it waits on (with 3 slots a team met each slot every other use and could pass a stale phase)
+  static constexpr int RS = C >= 128 ? 0 : (C >= 64 ? 2 : 4);
   static constexpr int RAW_STAGE = 64 * C * 2;
   static constexpr int ZCOL = NB * 64;                // TMEM: K^T buffer b at b*64 (64 pixels each); Z at ZCOL .. ZCOL+CE
   static constexpr int TMEM_COLS = C >= 128 ? 512 : 256;
@@ -250,13 +273,13 @@ __global__ void __launch_bounds__(kThreads, CtxCfg<C>::CTAS) la_ctx_kernel(const
 
   if (threadIdx.x == 0) {
     mbar_init(w_full, 1);
-    for (int i = 0; i < K::XS; ++i) { mbar_init(x_full + 8 * i, 4); mbar_init(x_empty + 8 * i, 1); }
+    for (int i = 0; i < K::XS; ++i) { mbar_init(x_full + 8 * i, K::RS > 0 ? XTeams<64>::kArrivals : 4); mbar_init(x_empty + 8 * i, 1); }
     for (int i = 0; i < K::NB; ++i) {
       mbar_init(d1_full + 8 * i, 1); mbar_init(d1_empty + 8 * i, 4);
       mbar_init(p_full + 8 * i, 4); mbar_init(p_empty + 8 * i, 1);
     }
     mbar_init(z_full, 1);
-    for (int i = 0; i < K::RS; ++i) { mbar_init(raw_full + 8 * i, 1); mbar_init(raw_empty + 8 * i, 4); }
+    for (int i = 0; i < K::RS; ++i) { mbar_init(raw_full + 8 * i, 1); mbar_init(raw_empty + 8 * i, XTeams<64>::kArrivals); }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), K::TMEM_COLS);
@@ -727,11 +750,12 @@ int launch_c(const LinAttnTcW& w, const LinAttnTcArgs& a, cudaStream_t s) {
   int slA = CtxCfg<C>::CTAS * sms() / a.N; if (slA > HT / 4) slA = HT / 4; if (slA < 1) slA = 1;
   int slB = sl; if (slB > NTL / 2) slB = NTL / 2; if (slB < 1) slB = 1;
   CtxParams cp{(const __nv_bfloat16*)a.x, (const __nv_bfloat16*)w.wk, w.kb2, a.Z, a.ksum, a.HW, slA};
-  la_ctx_kernel<C><<<dim3(slA, a.N), kThreads, CtxCfg<C>::SMEM, s>>>(cp);
+  static int only = -1; if (only < 0) { const char* e = getenv("LD_LA_ONLY"); only = e ? atoi(e) : 0; }   // debug: 1 = pass A only, 2 = pass B only
+  if (only != 2) la_ctx_kernel<C><<<dim3(slA, a.N), kThreads, CtxCfg<C>::SMEM, s>>>(cp);
   la_fold_kernel<<<dim3(4, a.N), 256, 32 * C * sizeof(float), s>>>(a.Z, a.ksum, w.Ut, (__nv_bfloat16*)a.Mn, C, a.flag);
   OutParams op{(const __nv_bfloat16*)a.x, (const __nv_bfloat16*)w.wq, (const __nv_bfloat16*)a.Mn, w.bout, w.g2,
                (__nv_bfloat16*)a.out, a.HW, slB, w.q_use_max};
-  la_out_kernel<C><<<dim3(slB, a.N), kThreads, OutCfg<C>::SMEM, s>>>(op);
+  if (only != 1) la_out_kernel<C><<<dim3(slB, a.N), kThreads, OutCfg<C>::SMEM, s>>>(op);
   return 3;
 }
 
