@@ -944,7 +944,13 @@ int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
     const int occ4 = (int)((size_t)cfg().max_smem_sm / (smem4 + 1024));
     const int cap = Roles<true>::kMinCtas < 512 / tm_cols ? Roles<true>::kMinCtas : 512 / tm_cols;
     if (smem4 <= (size_t)cfg().max_smem && (occ4 >= occ2 || occ4 >= cap)) smem = smem4;
-    else { p.obuf = 2; layout<NT, KS, KC>(p, sa, p.nb_stages); }
+    else {
+      // next best: give up the fourth activation stage for it (the staging wait was 23 % of the stall samples of the dual launch)
+      const size_t smem43 = sa == 4 && p.mt == 1 ? layout<NT, KS, KC>(p, 3, p.nb_stages) : 0;
+      const int occ43 = smem43 ? (int)((size_t)cfg().max_smem_sm / (smem43 + 1024)) : 0;
+      if (smem43 && (occ43 >= occ2 || occ43 >= cap)) { sa = 3; p.sa = 3; smem = smem43; }
+      else { p.obuf = 2; layout<NT, KS, KC>(p, sa, p.nb_stages); }
+    }
   }
   // persistent grid: as many CTAs as are co-resident (registers allow two per SM; 2*NT of 512 TMEM columns each)
   const bool lean = p.tma_in != 0;
