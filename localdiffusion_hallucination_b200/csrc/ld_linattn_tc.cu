@@ -62,6 +62,7 @@ struct OutParams {
   __nv_bfloat16* out;
   int HW, slices;
   int use_max;              // 0: |q| is provably small, soft-max over d needs no max subtraction
+  int flat, N;              // flat: the CTAs split the N * tiles-per-image tile list evenly (a CTA may cross ONE image boundary)
 };
 
 // Producer side: ROWS pixels of x/|x| staged as a K-major operand (16-byte chunk (pixel p, channels 8*c8..) at
@@ -465,7 +466,8 @@ struct OutCfg {
   static constexpr int P_BYTES = 128 * 128 * 2;
   static constexpr int NP = C >= 128 ? 2 : 4;         // P buffers: two per transform warp-group (one when smem is full)
   static constexpr int RS = C >= 128 ? 0 : (C >= 64 ? 2 : 3);   // raw x ring fed by cp.async.bulk
-  static constexpr int SMEM_MIN = WQ_BYTES + MN_BYTES + XS * X_STAGE + NP * P_BYTES + RS * X_STAGE + 2 * C * 4 + 32 * 8 + 16;
+  static constexpr int MN2 = C <= 32 ? MN_BYTES : 0;   // second Mn buffer (flat tile lists cross one image boundary); no room at C >= 64
+  static constexpr int SMEM_MIN = WQ_BYTES + MN_BYTES + MN2 + XS * X_STAGE + NP * P_BYTES + RS * X_STAGE + 2 * C * 4 + 32 * 8 + 16;
   static constexpr int SMEM = SMEM_MIN > 117 * 1024 ? SMEM_MIN : 117 * 1024;   // one CTA per SM: it owns all 512 TMEM columns
 };
 
@@ -476,7 +478,7 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* wq_s = smem;
   uint8_t* mn_s = wq_s + K::WQ_BYTES;
-  uint8_t* x_s = mn_s + K::MN_BYTES;
+  uint8_t* x_s = mn_s + K::MN_BYTES + K::MN2;           // Mn of the CTA's first image and (flat mode) of the next one
   uint8_t* p_s = x_s + K::XS * K::X_STAGE;
   uint8_t* raw_s = p_s + K::NP * K::P_BYTES;
   float* bg_s = reinterpret_cast<float*>(raw_s + K::RS * K::X_STAGE);   // bias[C], g2*sqrt(C)[C]
@@ -486,10 +488,20 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
                  d1_empty = d1_full + 16, p_full = d1_empty + 16, p_empty = p_full + 32, d2_full = p_empty + 32,
                  d2_empty = d2_full + 16, raw_full = d2_empty + 16, raw_empty = raw_full + 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.y;
   const int NTL = (p.HW + 127) / 128;
-  const int t0 = (int)((long long)NTL * blockIdx.x / p.slices), t1 = (int)((long long)NTL * (blockIdx.x + 1) / p.slices);
-  const int nt = t1 - t0;
+  // per-image slices (grid.y = image), or -- HW a multiple of 128 -- one flat tile list split evenly over ALL CTAs: with 32 images
+  // and 148 SMs per-image slicing leaves 20 SMs idle.  In flat mode tile indices / pixels simply run on into image n + 1.
+  int n, t0, nt, hw_lim;
+  if (p.flat) {
+    const long long T = (long long)p.N * NTL;
+    const int f0 = (int)(T * blockIdx.x / gridDim.x), f1 = (int)(T * (blockIdx.x + 1) / gridDim.x);
+    n = f0 / NTL; t0 = f0 - n * NTL; nt = f1 - f0; hw_lim = (p.N - n) * p.HW;
+  } else {
+    n = blockIdx.y;
+    t0 = (int)((long long)NTL * blockIdx.x / p.slices);
+    nt = (int)((long long)NTL * (blockIdx.x + 1) / p.slices) - t0;
+    hw_lim = p.HW;
+  }
 
   if (threadIdx.x == 0) {
     mbar_init(w_full, 1);
@@ -521,16 +533,18 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
   if (warp < 4) {
     // ---------------------------------------------------------------- producers ------------------
     if constexpr (K::RS > 0)
-      produce_x_raw<C, 128, K::XS, (K::RS > 0 ? K::RS : 1)>(ximg, t0, nt, p.HW, x_s, K::X_STAGE, x_full, x_empty, raw_s, raw_full, raw_empty,
+      produce_x_raw<C, 128, K::XS, (K::RS > 0 ? K::RS : 1)>(ximg, t0, nt, hw_lim, x_s, K::X_STAGE, x_full, x_empty, raw_s, raw_full, raw_empty,
                                                            threadIdx.x, lane);
     else
-      produce_x<C, 128, K::XS, false>(ximg, t0, nt, p.HW, x_s, K::X_STAGE, x_full, x_empty, threadIdx.x, lane);
+      produce_x<C, 128, K::XS, false>(ximg, t0, nt, hw_lim, x_s, K::X_STAGE, x_full, x_empty, threadIdx.x, lane);
   } else if (warp == kMmaWarp) {
     // ---------------------------------------------------------------- MMA issue ------------------
     if (lane == 0) {
-      mbar_arrive_expect_tx(w_full, K::WQ_BYTES + K::MN_BYTES);
+      mbar_arrive_expect_tx(w_full, K::WQ_BYTES + K::MN_BYTES + K::MN2);
       bulk_g2s(smem_u32(wq_s), p.wq, K::WQ_BYTES, w_full);
       bulk_g2s(smem_u32(mn_s), p.Mn + (size_t)n * 128 * C, K::MN_BYTES, w_full);
+      const int n2 = (p.flat && n + 1 < p.N) ? n + 1 : n;
+      if (K::MN2) bulk_g2s(smem_u32(mn_s + K::MN_BYTES), p.Mn + (size_t)n2 * 128 * C, K::MN_BYTES, w_full);
     }
     __syncwarp();
     mbar_wait(w_full, 0);
@@ -548,7 +562,8 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
         const uint32_t p_lo = p_lo0 + (uint32_t)(pi * (K::P_BYTES >> 4));
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // K = 128 (h,d) = 8 x 16
-          umma_bf16_lh(tmem_base + 256u + (uint32_t)(g * C), p_lo + (uint32_t)(2 * k * 128), hi128, mn_lo + (uint32_t)(2 * k * C), hi128,
+          umma_bf16_lh(tmem_base + 256u + (uint32_t)(g * C), p_lo + (uint32_t)(2 * k * 128), hi128,
+                       mn_lo + (uint32_t)((K::MN2 && t0 + j >= NTL) ? (K::MN_BYTES >> 4) : 0) + (uint32_t)(2 * k * C), hi128,
                        idesc2, k > 0 ? 1u : 0u);
         umma_commit(p_empty + 8 * pi);
         umma_commit(d2_full + 8 * g);
@@ -642,7 +657,7 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
       if constexpr (C <= 64) {
         // one sweep: the whole row stays in registers; the residual row of x is requested before the accumulator is read
         uint4 xv[C / 8];
-        if (px < p.HW) {
+        if (px < hw_lim) {
 #pragma unroll
           for (int j = 0; j < C / 8; ++j) xv[j] = __ldg(reinterpret_cast<const uint4*>(xr) + j);
         }
@@ -660,7 +675,7 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
         }
         tc_fence_before();
         mbar_arrive(d2_empty + 8 * g);
-        if (px < p.HW) {
+        if (px < hw_lim) {
           const float inv = rsqrtf(fmaxf(ss, 1e-24f));            // to_out RMSNorm (ddpm.py:231,251)
 #pragma unroll
           for (int j0 = 0; j0 < C; j0 += 8) {
@@ -694,7 +709,7 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
           tmem_ld32(lane_base + 256u + (uint32_t)(g * C + j0), rr);
           tmem_ld_wait();
           if (j0 + 32 == C) { tc_fence_before(); mbar_arrive(d2_empty + 8 * g); }
-          if (px < p.HW) {
+          if (px < hw_lim) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const uint4 xv = *reinterpret_cast<const uint4*>(xr + j0 + 8 * c);
@@ -749,13 +764,18 @@ int launch_c(const LinAttnTcW& w, const LinAttnTcArgs& a, cudaStream_t s) {
   int sl = sms() / a.N; if (sl < 1) sl = 1;
   int slA = CtxCfg<C>::CTAS * sms() / a.N; if (slA > HT / 4) slA = HT / 4; if (slA < 1) slA = 1;
   int slB = sl; if (slB > NTL / 2) slB = NTL / 2; if (slB < 1) slB = 1;
+  // pass B: when tiles never straddle images, all SMs share one flat tile list (a CTA crosses at most one image boundary)
+  static int flat_env = -1; if (flat_env < 0) { const char* e = getenv("LD_LA_FLAT"); flat_env = e ? atoi(e) : 1; }   // LD_LA_FLAT=0: per-image slices (A/B aid)
+  const long long Tb = (long long)a.N * NTL;
+  int ctasB = sms(); if (ctasB > Tb / 2) ctasB = (int)(Tb / 2);
+  const bool flatB = flat_env && OutCfg<C>::MN2 > 0 && a.HW % 128 == 0 && ctasB >= 1 && Tb / ctasB + 1 <= NTL;
   CtxParams cp{(const __nv_bfloat16*)a.x, (const __nv_bfloat16*)w.wk, w.kb2, a.Z, a.ksum, a.HW, slA};
   static int only = -1; if (only < 0) { const char* e = getenv("LD_LA_ONLY"); only = e ? atoi(e) : 0; }   // debug: 1 = pass A only, 2 = pass B only
   if (only != 2) la_ctx_kernel<C><<<dim3(slA, a.N), kThreads, CtxCfg<C>::SMEM, s>>>(cp);
   la_fold_kernel<<<dim3(4, a.N), 256, 32 * C * sizeof(float), s>>>(a.Z, a.ksum, w.Ut, (__nv_bfloat16*)a.Mn, C, a.flag);
   OutParams op{(const __nv_bfloat16*)a.x, (const __nv_bfloat16*)w.wq, (const __nv_bfloat16*)a.Mn, w.bout, w.g2,
-               (__nv_bfloat16*)a.out, a.HW, slB, w.q_use_max};
-  if (only != 1) la_out_kernel<C><<<dim3(slB, a.N), kThreads, OutCfg<C>::SMEM, s>>>(op);
+               (__nv_bfloat16*)a.out, a.HW, slB, w.q_use_max, flatB ? 1 : 0, a.N};
+  if (only != 1) la_out_kernel<C><<<flatB ? dim3(ctasB, 1) : dim3(slB, a.N), kThreads, OutCfg<C>::SMEM, s>>>(op);
   return 3;
 }
 
