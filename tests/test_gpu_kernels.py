@@ -174,7 +174,9 @@ def test_conv_dual_block1_and_res_conv(case):
 
 
 # (C, N, HW)
-LINATTN_CASES = [(32, 2, 1024), (64, 1, 784), (128, 2, 256), (32, 3, 4096), (64, 5, 1000)]
+LINATTN_CASES = [(32, 2, 1024), (64, 1, 784), (128, 2, 256), (32, 3, 4096), (64, 5, 1000),
+                 (32, 6, 65536),   # 256 x 256: ~20 stages per CTA, every ring wraps several times (a 3-deep raw ring hung here)
+                 (64, 20, 4096)]   # many images: flat / sliced tile lists cross image boundaries
 
 
 @pytest.mark.parametrize("C_,N,HW", LINATTN_CASES)
@@ -189,14 +191,17 @@ def test_fused_linear_attention_matches_torch(C_, N, HW):
     wout = torch.randn(C_, 128, generator=g) / 128 ** 0.5
     bout = torch.randn(C_, generator=g) * 0.1
     g2 = torch.rand(C_, generator=g) + 0.5
-    xd = x.double()
-    xn = F.normalize(xd, dim=-1) * gn.double() * C_ ** 0.5
-    q, k, v = (xn @ wqkv.double().T).view(N, HW, 3, 4, 32).unbind(dim=2)
+    rd = dev if N * HW > 200000 else torch.device("cpu")   # plain torch fp64 reference (on the GPU for the big cases)
+    xd = x.double().to(rd)
+    xn = F.normalize(xd, dim=-1) * gn.double().to(rd) * C_ ** 0.5
+    q, k, v = (xn @ wqkv.double().to(rd).T).view(N, HW, 3, 4, 32).unbind(dim=2)
     q = q.softmax(dim=-1) * 32 ** -0.5
     k = k.softmax(dim=1)
     ctx = torch.einsum("nphd,nphe->nhde", k, v)
-    o = torch.einsum("nhde,nphd->nphe", ctx, q).reshape(N, HW, 128) @ wout.double().T + bout.double()
-    attn = F.normalize(o, dim=-1) * g2.double() * C_ ** 0.5
+    o = torch.einsum("nhde,nphd->nphe", ctx, q).reshape(N, HW, 128) @ wout.double().to(rd).T + bout.double().to(rd)
+    attn = (F.normalize(o, dim=-1) * g2.double().to(rd) * C_ ** 0.5).cpu()
+    xd = xd.cpu()
+    del q, k, v, o, xn
     out = torch.empty(N, HW, C_, device=dev)
     rc = lib.ld_debug_linattn(x.to(dev).data_ptr(), C_, N, HW, wqkv.contiguous().data_ptr(), gn.data_ptr(), wout.contiguous().data_ptr(),
                               bout.data_ptr(), g2.data_ptr(), out.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
