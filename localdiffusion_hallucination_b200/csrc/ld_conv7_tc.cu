@@ -1,10 +1,12 @@
 // init_conv (ddpm.py:319): 7x7, pad 3, ONE fp32 input channel -> 32..64 bf16 channels, on tcgen05 for sm_100a.
 //
 // The sampler state x_t is fp32 and stays fp32 in HBM; the im2col operand is built on the fly in shared memory:
-//   builders (4 warps, thread = output pixel of a 16 x 8 tile) read the 22 x 14 halo patch of x from a shared
-//   staging buffer, split every tap into bf16 hi + bf16 lo (x = hi + lo to ~2^-17, so the fp32 state is not
-//   rounded to 8 bits on its way into the network) and write their row of the K-major A operand
-//   [K = 64 (49 hi taps + pad) | 64 (49 lo taps + pad)];
+//   builders (4 warps) stage the 22 x 14 halo patch of x ONCE per tile as two bf16 patches, hi and lo (x = hi + lo to
+//   ~2^-17, so the fp32 state is not rounded to 8 bits on its way into the network); then thread = output pixel
+//   copies, per filter row ky, the 8-element window [px, px+8) of patch row py+ky (five 32-bit loads + funnel
+//   shifts, one 16-byte store) into its row of the K-major A operand: K chunk ky = taps (ky, 0..6) + one zero-weight
+//   slot, chunk 7 = padding; [K = 64 hi | 64 lo].  (The first version split all 49 taps per pixel: 6272 splits and
+//   scalar loads per tile instead of 308 -- the builders, not the tensor pipe, set the pace.)
 //   one lane issues 8 tcgen05.mma (M = 128 pixels, N = Cout, K = 16) against the resident weights [w | w];
 //   4 epilogue warps add the bias and store bf16 NHWC.  Persistent CTAs, 2 A stages, 2 TMEM accumulators.
 #include <cuda_bf16.h>
@@ -25,6 +27,7 @@ constexpr int kThreads = 9 * 32;     // warps 0-3 builders, 4-7 epilogue, 8 MMA
 constexpr int kMmaWarp = 8;
 constexpr int PH = 22, PW = 14;      // halo patch of a 16 x 8 tile
 constexpr int A_STAGE = 16 * 2048;   // [16 chunks of 8 K][128 rows][16 B]
+constexpr int PATCH_W = PH * 8;      // 32-bit words of one bf16 patch (row pitch 16 elements)
 
 struct Params {
   const float* x; const __nv_bfloat16* w; const float* bias; __nv_bfloat16* out;
@@ -37,8 +40,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv7_tc_kernel(const Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* a_s = smem;                                // 2 stages
   uint8_t* w_s = a_s + 2 * A_STAGE;
-  float* patch = reinterpret_cast<float*>(w_s + W_BYTES);   // [2][PH*PW] (+ pad)
-  float* bias_s = patch + 2 * 320;
+  uint32_t* patch = reinterpret_cast<uint32_t*>(w_s + W_BYTES);   // [2 stages][hi, lo][PH rows][8 words = 16 bf16]
+  float* bias_s = reinterpret_cast<float*>(patch + 4 * PATCH_W);
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + NT);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
   const uint32_t w_full = smem_u32(bars), a_full = w_full + 8, a_empty = a_full + 16, acc_full = a_empty + 16, acc_empty = acc_full + 16;
@@ -64,42 +67,59 @@ __global__ void __launch_bounds__(kThreads, 2) conv7_tc_kernel(const Params p) {
     const int m = threadIdx.x;                         // output pixel of the tile: (m >> 3, m & 7)
     const int py = m >> 3, px = m & 7;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const int s = it & 1;
+    // the patch values of the NEXT tile are requested before this tile's window copies: the global-load latency (the patch is
+    // read straight from HBM/L2, 176 element pairs per tile) otherwise sits on every tile's critical path
+    float pv[4];
+    auto load_patch = [&](int tile, float (&v)[4]) {
       const int img = tile / tpi, r = tile - img * tpi;
       const int ty0 = (r / p.tiles_x) * 16, tx0 = (r % p.tiles_x) * 8;
-      float* pb = patch + s * 320;
-      // stage the halo patch (zero outside the image = the conv's zero padding)
       const float* ximg = p.x + (size_t)img * p.H * p.W;
-      for (int i = m; i < PH * PW; i += 128) {
-        const int hy = i / PW, hx = i - hy * PW;
-        const int gy = ty0 + hy - 3, gx = tx0 + hx - 3;
-        pb[i] = ((unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W) ? __ldg(ximg + (size_t)gy * p.W + gx) : 0.f;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int i = m + 128 * k;
+        v[2 * k] = v[2 * k + 1] = 0.f;
+        if (i < PH * 8) {
+          const int hy = i >> 3, hx = (i & 7) * 2;
+          const int gy = ty0 + hy - 3, gx = tx0 + hx - 3;
+          if ((unsigned)gy < (unsigned)p.H) {
+            if (hx < PW && (unsigned)gx < (unsigned)p.W) v[2 * k] = __ldg(ximg + (size_t)gy * p.W + gx);
+            if (hx + 1 < PW && (unsigned)(gx + 1) < (unsigned)p.W) v[2 * k + 1] = __ldg(ximg + (size_t)gy * p.W + gx + 1);
+          }
+        }
       }
+    };
+    if ((int)blockIdx.x < p.ntiles) load_patch(blockIdx.x, pv);
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      uint32_t* ph = patch + s * 2 * PATCH_W;          // hi patch, then lo patch
+      uint32_t* pl = ph + PATCH_W;
+      // halo patch split into bf16 hi + lo (zero outside the image = the conv's zero padding)
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int i = m + 128 * k;
+        if (i < PH * 8) {
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[2 * k], pv[2 * k + 1]);
+          const float2 hf = __bfloat1622float2(h2);
+          ph[i] = *reinterpret_cast<const uint32_t*>(&h2);
+          pl[i] = pack_bf16x2(pv[2 * k] - hf.x, pv[2 * k + 1] - hf.y);
+        }
+      }
+      if (tile + (int)gridDim.x < p.ntiles) load_patch(tile + gridDim.x, pv);
       named_bar(1, 128);                               // patch complete (and the previous tile's readers are done: 2 patch buffers)
       mbar_wait(a_empty + 8 * s, ((it >> 1) & 1) ^ 1);
       uint8_t* row = a_s + s * A_STAGE + m * 16;
-      const float* src = pb + py * PW + px;
+      const int sh = (px & 1) * 16;                    // odd px: the window starts in the upper half of its first word
 #pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {                 // 8 taps per 16-byte chunk; taps 49..63 are zero
-        uint32_t hi[4], lo[4];
+      for (int ky = 0; ky < 7; ++ky) {                 // K chunk ky = taps (ky, kx = 0..6) + one slot whose weight is zero
+        const uint32_t* rh = ph + (py + ky) * 8 + (px >> 1);
+        const uint32_t* rl = pl + (py + ky) * 8 + (px >> 1);
+        uint32_t a[5], b[5];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float v[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int tap = c8 * 8 + 2 * j + e;
-            v[e] = tap < 49 ? src[(tap / 7) * PW + (tap % 7)] : 0.f;
-          }
-          const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[0], v[1]);
-          const float2 hf = __bfloat1622float2(h2);
-          hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
-          lo[j] = pack_bf16x2(v[0] - hf.x, v[1] - hf.y);
-        }
-        if (c8 < 7) {                                  // chunk 7 (taps 56..63) is all padding: written once below
-          *reinterpret_cast<uint4*>(row + c8 * 2048) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(row + (8 + c8) * 2048) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
+        for (int j = 0; j < 5; ++j) { a[j] = rh[j]; b[j] = rl[j]; }
+        *reinterpret_cast<uint4*>(row + ky * 2048) = make_uint4(__funnelshift_r(a[0], a[1], sh), __funnelshift_r(a[1], a[2], sh),
+                                                                __funnelshift_r(a[2], a[3], sh), __funnelshift_r(a[3], a[4], sh));
+        *reinterpret_cast<uint4*>(row + (8 + ky) * 2048) = make_uint4(__funnelshift_r(b[0], b[1], sh), __funnelshift_r(b[1], b[2], sh),
+                                                                      __funnelshift_r(b[2], b[3], sh), __funnelshift_r(b[3], b[4], sh));
       }
       if (it < 2) {                                    // the padding chunks of a stage never change
         *reinterpret_cast<uint4*>(row + 7 * 2048) = make_uint4(0u, 0u, 0u, 0u);
@@ -177,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv7_tc_kernel(const Params p) {
 }
 
 template <int NT>
-constexpr int smem_bytes() { return 2 * A_STAGE + 16 * NT * 16 + (2 * 320 + NT) * 4 + 9 * 8 + 16; }
+constexpr int smem_bytes() { return 2 * A_STAGE + 16 * NT * 16 + (4 * PATCH_W + NT) * 4 + 9 * 8 + 16; }
 
 int g_sms = 0;
 
@@ -186,13 +206,15 @@ int g_sms = 0;
 int conv7_tc_pack(const float* w_tap_cout, const float* bias, int Cout, Conv7TcW* out) {
   out->ready = false;
   if (Cout != 32 && Cout != 64) return 0;
-  // B operand [Cout rows][K = 128]: K index k < 64 -> tap k (hi part), k >= 64 -> tap k - 64 (lo part); same weights
+  // B operand [Cout rows][K = 128]: K chunk c8 < 7 = filter row ky = c8 (hi part), elements kx = 0..6, element 7 zero; chunk 7 zero;
+  // chunks 8..15 repeat the same weights for the lo part
   std::vector<__nv_bfloat16> pk((size_t)16 * Cout * 8);
   for (int c8 = 0; c8 < 16; ++c8)
     for (int n = 0; n < Cout; ++n)
       for (int e = 0; e < 8; ++e) {
-        const int tap = (c8 & 7) * 8 + e;
-        pk[((size_t)c8 * Cout + n) * 8 + e] = __float2bfloat16_rn(tap < 49 ? w_tap_cout[(size_t)tap * Cout + n] : 0.f);
+        const int ky = c8 & 7;
+        const bool live = ky < 7 && e < 7;
+        pk[((size_t)c8 * Cout + n) * 8 + e] = __float2bfloat16_rn(live ? w_tap_cout[(size_t)(ky * 7 + e) * Cout + n] : 0.f);
       }
   if (cudaMalloc(&out->w, pk.size() * 2) != cudaSuccess) return -1;
   if (cudaMemcpy(out->w, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
