@@ -1,13 +1,16 @@
 #!/usr/bin/env python
-"""Benchmark of the B200-native LocalDiffusion sampler (driver contract: see DESIGN.md §Measurement).
+"""Benchmark of the B200-native LocalDiffusion sampler (driver contract: see DESIGN.md §6).
 
     python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun for N>1)
     python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm (oracle port) on host cores
+    python bench.py --config c4|c5 [--start-timestep s]       # the other BASELINE configurations (development / SCALE runs)
 
-A "step" is one pass of the hot path over one batch: the full T=1000-timestep local-diffusion
-sampling (IND/OOD branches, fusion at start_timestep=2, 1998 UNet image-forwards per image) of
-B=16 synthetic 256x256 conditional images per GPU (BASELINE.json configs[1]; weak scaling:
-global batch 16*N, which at N=8 is configs[2]).
+A "step" is one pass of the hot path over one batch: the full T-timestep local-diffusion sampling (IND/OOD branches, fusion at
+`start_timestep`, `2(T-s)+s` UNet image-forwards per image) of B synthetic conditional images per GPU.  Default = BASELINE.json
+configs[1]: 256x256, T=1000, s=2, B=16 per GPU (weak scaling: global batch 16*N, which at N=8 is configs[2]).
+
+The product arm imports only the package (`localdiffusion_hallucination_b200`); `oracle/` is imported by the `cpu_baseline`
+leg and by `--impl reference` alone, after the GPU measurements are complete.
 """
 import argparse
 import json
@@ -21,9 +24,18 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "local_diffusion_sampling_256x256_T1000_images_per_sec"
 UNIT = "img/s"
-GF_PER_IMAGE_FORWARD = 75.35  # BASELINE.md §3, un-hoisted reference count (UNet 69.53 + cond encoder 5.81)
+# BASELINE.json configs: (model, image size, T, start_timestep, images per GPU)
+CONFIGS = {
+    "c2": dict(model="mri", size=256, timesteps=1000, start_timestep=2, batch=16,
+               label="BASELINE configs[1]: 256x256 single-channel conditional translation (synthetic T1-like + OOD blob), mri Unet(dim=32)"),
+    "c4": dict(model="mri_attn8", size=256, timesteps=1000, start_timestep=2, batch=8,
+               label="BASELINE configs[3]: attention-heavy Unet(full_attn=(F,F,T,T), attn_heads=8), 256x256 (64x64 and 32x32 token grids)"),
+    "c4s": dict(model="mri_attn8", size=128, timesteps=1000, start_timestep=2, batch=16,
+                label="BASELINE configs[3]: attention-heavy Unet(full_attn=(F,F,T,T), attn_heads=8), 128x128 (32x32 and 16x16 token grids)"),
+    "c5": dict(model="mri", size=512, timesteps=1000, start_timestep=500, batch=4,
+               label="BASELINE configs[4]: branching-timestep sweep point, 512x512, mri Unet(dim=32), 4 images per GPU (batch 32 on 8 GPUs)"),
+}
 
 
 def parse():
@@ -32,14 +44,26 @@ def parse():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="images per GPU (development override)")
-    ap.add_argument("--size", type=int, default=256)
-    ap.add_argument("--timesteps", type=int, default=1000)
-    ap.add_argument("--start-timestep", type=int, default=2)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (development override)")
+    ap.add_argument("--size", type=int, default=None)
+    ap.add_argument("--timesteps", type=int, default=None)
+    ap.add_argument("--start-timestep", type=int, default=None)
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    c = CONFIGS[a.config]
+    a.model = c["model"]
+    for k in ("batch", "size", "timesteps", "start_timestep"):
+        if getattr(a, k) is None:
+            setattr(a, k, c[k])
+    a.label = c["label"]
+    return a
+
+
+def metric_name(a):
+    return f"local_diffusion_sampling_{a.size}x{a.size}_T{a.timesteps}_images_per_sec"
 
 
 class ClockSampler:
@@ -89,83 +113,99 @@ def measured_peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
-# ------------------------------------------------------------------------------------------------
-# CPU leg: the reference's algorithm (oracle port, torch CPU fp32) on the host cores, bounded sample
-# ------------------------------------------------------------------------------------------------
-def cpu_sample_rate(args, cores, sample_batch=8):
-    """img/s of the reference's CPU algorithm for the bench workload, extrapolated from one branched
-    step + one fused-phase step at `sample_batch` images (a full run is hours)."""
-    import torch
-
-    from oracle import ld_oracle as lo
-    from tests import util
-    from tests.golden import cases
-
-    torch.set_num_threads(cores)
-    S, T, s = args.size, args.timesteps, args.start_timestep
-    sd = util.cpu_state_dict(util.make_model("mri"))
-    hp = util.hp_of("mri")
-    cond, mask = cases.mri_like(sample_batch, S)
-    x = cases.noise_tape(sample_batch, S, 1)[0]
-    cfg = cases.base_config("mri", s)
-    smp = lo.Sampler(cfg, sd, hp, image_size=S, timesteps=T)
-    z = lambda: x.clone()
-    with torch.no_grad():
-        t0 = time.perf_counter()
-        smp._p_sample([x, x], mask, cases.MRI_MIN_MAX, cond, T - 1, z)      # branched step (2 UNet forwards)
-        t_br = time.perf_counter() - t0
-        cfg["branch_out"] = False
-        t0 = time.perf_counter()
-        smp._p_sample(x, mask, cases.MRI_MIN_MAX, cond, 1, z)               # fused-phase step (1 UNet forward)
-        t_si = time.perf_counter() - t0
-    total = (T - s) * t_br + s * t_si
-    return sample_batch / total, f"extrapolated from 1 branched + 1 single step at B={sample_batch}, {S}x{S}: {t_br:.2f}s + {t_si:.2f}s"
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    cores = os.cpu_count() or 1
-    vals = []
-    sample = ""
-    for i in range(args.warmup + args.steps):
-        v, sample = cpu_sample_rate(args, cores)
-        if i >= args.warmup:
-            vals.append(v)
-        if i == 0 and 1.0 / max(v, 1e-12) > 0:  # keep the whole run within minutes: one warm-up is enough on CPU
-            pass
-    value = statistics.median(vals)
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * args.batch / value, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": workload_config(args, 1),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    print(json.dumps(line))
-
-
-def workload_config(args, world):
+def workload_config(a, world):
+    fwd = 2 * (a.timesteps - a.start_timestep) + a.start_timestep
     return {
-        "workload": f"BASELINE configs[1]: {args.size}x{args.size} single-channel conditional translation (synthetic T1-like + OOD blob), "
-                    f"mri Unet(dim=32), T={args.timesteps} DDPM steps, start_timestep={args.start_timestep}, batch {args.batch}/GPU",
-        "global_batch": args.batch * world, "image": args.size, "timesteps": args.timesteps,
-        "unet_forwards_per_image": 2 * (args.timesteps - args.start_timestep) + args.start_timestep,
+        "workload": f"{a.label}, T={a.timesteps} DDPM steps, start_timestep={a.start_timestep}, batch {a.batch}/GPU",
+        "config": a.config, "global_batch": a.batch * world, "image": a.size, "timesteps": a.timesteps,
+        "start_timestep": a.start_timestep, "unet_forwards_per_image": fwd,
         "parallelism": f"batch-sharded x{world}, final all-gather only",
         "l2": "working set (activations + noise tape) >> 126 MB L2, no flush needed",
     }
 
 
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+# CPU leg: the reference's algorithm (oracle port, torch CPU fp32) on the host cores, bounded sample
+# ------------------------------------------------------------------------------------------------
+class CpuLeg:
+    """The reference's CPU algorithm (oracle port, torch fp32 on all host cores) on a bounded sample of the bench workload at the
+    TRUE batch: `n_branched` branched steps (2 UNet forwards each) + 1 fused-phase step (1 forward), extrapolated with
+    (T-s)*t_branched + s*t_single (SURVEY.md §8d prescribes 3 + 1; a full run is hours)."""
+
+    def __init__(self, a, cores):
+        import torch
+
+        from localdiffusion_hallucination_b200 import workload as wl
+        from oracle import ld_oracle as lo
+
+        torch.set_num_threads(cores)
+        self.a, self.wl, self.lo, self.torch = a, wl, lo, torch
+        m = wl.make_model(a.model)
+        self.sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+        kw = wl.MODEL_KW[a.model]
+        self.hp = lo.UnetHP(dim=kw["dim"], init_dim=kw["init_dim"], dim_mults=kw.get("dim_mults", (1, 2, 4, 8)),
+                            full_attn=kw.get("full_attn", (False, False, False, True)), heads=kw.get("attn_heads", 4), mode=kw["mode"])
+        self.cond, self.mask = wl.mri_like(a.batch, a.size)
+        self.x = wl.noise_tape(a.batch, a.size, 1)[0]
+        self.t_single = None
+
+    def _one(self, kind):
+        a, wl, torch = self.a, self.wl, self.torch
+        cfg = wl.base_config("mri", a.start_timestep)
+        smp = self.lo.Sampler(cfg, self.sd, self.hp, image_size=a.size, timesteps=a.timesteps)
+        z = lambda: self.x.clone()
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            if kind == "branched":
+                smp._p_sample([self.x, self.x], self.mask, wl.MRI_MIN_MAX, self.cond, a.timesteps - 1, z)   # 2 UNet forwards
+            else:
+                cfg["branch_out"] = False
+                smp._p_sample(self.x, self.mask, wl.MRI_MIN_MAX, self.cond, 1, z)                           # 1 UNet forward
+        return time.perf_counter() - t0
+
+    def rate(self, n_branched=3):
+        a = self.a
+        t_br = statistics.median([self._one("branched") for _ in range(n_branched)])
+        fresh = self.t_single is None
+        if fresh:
+            self.t_single = self._one("single")
+        total = (a.timesteps - a.start_timestep) * t_br + a.start_timestep * self.t_single
+        return a.batch / total, (f"extrapolated from {n_branched} branched + {1 if fresh else 0} single step(s) at the bench batch B={a.batch}, "
+                                 f"{a.size}x{a.size}: {t_br:.2f}s / branched step, {self.t_single:.2f}s / single step, (T-s)*t_br + s*t_si")
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    leg = CpuLeg(a, cores)
+    leg.rate(1)   # one warm-up pass is enough on the CPU (keeps the whole run within minutes); it also times the single step
+    leg.t_single = None   # re-timed inside the first (3 + 1) step
+    vals, sample = [], ""
+    for i in range(a.steps):
+        # the first timed step is the prescribed 3 + 1 sample; later steps re-time one branched step (the single step is 0.1 % of a run)
+        v, sm = leg.rate(3 if i == 0 else 1)
+        sample = sample or sm
+        vals.append(v)
+    value = statistics.median(vals)
+    line = {
+        "metric": metric_name(a), "value": value, "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1000.0 * a.batch / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": workload_config(a, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + f"; median of {a.steps} such steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
     import torch
     import torch.distributed as dist
 
     from localdiffusion_hallucination_b200 import GaussianDiffusion, _lib, parallel
-    from tests import util
-    from tests.golden import cases
+    from localdiffusion_hallucination_b200 import workload as wl
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -174,15 +214,15 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    S, T, s, B = args.size, args.timesteps, args.start_timestep, args.batch
+    S, T, s, B = a.size, a.timesteps, a.start_timestep, a.batch
     GB = B * world
-    model = util.make_model("mri", args.precision, device=dev)
-    gd = GaussianDiffusion(cases.base_config("mri", s), model, image_size=S, timesteps=T, objective="pred_x0").to(dev)
-    cond_g, mask_g = cases.mri_like(GB, S)
+    model = wl.make_model(a.model, a.precision, device=dev)
+    gd = GaussianDiffusion(wl.base_config("mri", s), model, image_size=S, timesteps=T, objective="pred_x0").to(dev)
+    cond_g, mask_g = wl.mri_like(GB, S)
     lo_, hi_ = parallel.shard_bounds(GB, rank, world)
     cond_h, mask_h = cond_g[lo_:hi_].contiguous().pin_memory(), mask_g[lo_:hi_].contiguous().pin_memory()
     cond_d, mask_d = cond_h.to(dev), mask_h.to(dev)
-    mm = cases.MRI_MIN_MAX
+    mm = wl.MRI_MIN_MAX
     # device-resident noise tape in the reference's draw order (seed 10); the same tape is reused every step
     tape = gd.make_noise_tape((B, 1, S, S), T, dev)
     h = model.engine()
@@ -222,72 +262,92 @@ def run_ours(args):
         sync_all()
         return float(ms)
 
-    for _ in range(args.warmup):
+    for _ in range(a.warmup):
         step_resident()
     l0 = lib.ld_launch_count(h)
     with ClockSampler(local) as cs:
-        ms = timed(step_resident, args.steps)
+        ms = timed(step_resident, a.steps)
     launches = (lib.ld_launch_count(h) - l0) * world
     clocks = cs.summary()
-    value = GB * args.steps / (ms / 1000.0)
+    value = GB * a.steps / (ms / 1000.0)
     e2e = None
-    if not args.no_e2e:
+    if not a.no_e2e:
         step_e2e()
-        ke = min(args.steps, 2)
         t0 = time.perf_counter()
-        ms_e = timed(step_e2e, ke)
-        e2e = {"value": GB * ke / (ms_e / 1000.0), "unit": UNIT, "h2d_bytes_per_step": int(cond_h.numel() * 4 * 2 * world),
-               "d2h_bytes_per_step": int(host_out.numel() * 4 * world), "wall_ms_per_step": 1000.0 * (time.perf_counter() - t0) / ke,
+        ms_e = timed(step_e2e, a.steps)   # every one of the --steps steps, host buffers in and out
+        e2e = {"value": GB * a.steps / (ms_e / 1000.0), "unit": UNIT, "steps": a.steps, "h2d_bytes_per_step": int(cond_h.numel() * 4 * 2 * world),
+               "d2h_bytes_per_step": int(host_out.numel() * 4 * world), "wall_ms_per_step": 1000.0 * (time.perf_counter() - t0) / a.steps,
                "note": "pinned host cond+mask -> device, noise drawn on device (seed 10, reference order), result -> pinned host"}
 
     if rank == 0:
         hbm, tf_burst, tf_sus, src = measured_peaks()
         fwd = 2 * (T - s) + s
-        tflops = value * fwd * GF_PER_IMAGE_FORWARD / 1000.0
-        roof = dominant_kernel_roofline(lib, dev, B, S, hbm, src)
+        gf_fwd = wl.forward_gflop(a.model, S)   # reference count, cond encoder included (75.35 GF for the mri model at 256x256)
+        tflops = value * fwd * gf_fwd / 1000.0
+        # mixed roofline of SURVEY.md §8d: sum over layers of max(flops / tensor peak, min bytes / HBM bandwidth), measured peaks
+        ideal_us = wl.mixed_roofline_us(a.model, S, tf_sus, hbm)
+        us_per_fwd = 1e6 / (value / world * fwd)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.precision, "data": "synthetic", "config": workload_config(args, world),
+            "metric": metric_name(a), "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": a.precision, "data": "synthetic", "config": workload_config(a, world),
             "unet_tflops": tflops, "unet_tflops_frac_of_sustained_peak": tflops / (tf_sus * world),
-            "flop_count": f"{GF_PER_IMAGE_FORWARD} GF per image-forward (reference, cond encoder not hoisted) x {fwd} forwards/image",
-            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roof,
+            "flop_count": f"{gf_fwd:.2f} GF per image-forward (reference count, cond encoder not hoisted) x {fwd} forwards/image",
+            "mixed_roofline": {"ideal_us_per_image_forward": ideal_us, "achieved_us_per_image_forward": us_per_fwd, "frac": ideal_us / us_per_fwd,
+                               "ceiling_img_s_per_gpu": 1e6 / (ideal_us * fwd),
+                               "definition": "sum over layers of max(flops/sustained bf16 peak, min bytes/measured HBM bandwidth), "
+                                             "layer table in localdiffusion_hallucination_b200/workload.py (SURVEY.md 8d)"},
+            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
+            "roofline": dominant_kernel_roofline(lib, dev, a, hbm, src),
             "peaks": {"hbm_gbs": hbm, "bf16_tflops_burst": tf_burst, "bf16_tflops_sustained": tf_sus, "source": src},
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not a.no_cpu_baseline:
+            del gd, model
+            torch.cuda.empty_cache()
             cores = os.cpu_count() or 1
-            v, sample = cpu_sample_rate(args, cores)
+            v, sample = CpuLeg(a, cores).rate(3)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def dominant_kernel_roofline(lib, dev, B, S, hbm, src):
-    """Roofline of the dominant kernel, timed alone with CUDA events on its launch stream: the tcgen05
-    3x3 convolution at full resolution, 32->32 channels (16 of the 45 UNet convs, the HBM-bound ones).
-    Algorithmic bytes per launch = N*H*W*(Cin+Cout)*2 (bf16 in + out, each touched once) + weights."""
+def dominant_kernel_roofline(lib, dev, a, hbm, src):
+    """Roofline of the dominant kernel family -- the tcgen05 3x3 convolution with 32 output channels at full resolution
+    (the largest share of device time, profiles/*_launch_shares.md) -- timed alone with CUDA events on its launch stream, in every
+    variant the sampler launches it in, weighted by how often one UNet forward launches each at full resolution:
+      plain x1 (ups[-1] conv), +GroupNorm statistics x2 (block1 of the two down ResnetBlocks), +normalise-on-load and statistics x5
+      (every block2), dual 3x3 + 1x1 over a 64-channel virtual concat with statistics x3 (block1 + res_conv of the up / final blocks).
+    Algorithmic bytes per launch = N*H*W*(Cin+Cout_total)*2 (bf16 in + out, each touched once) + weights."""
     import ctypes as C
 
     import torch
 
-    if not hasattr(lib, "ld_debug_conv_time"):
+    if a.model != "mri":
         return None
-    N = 2 * B
-    ms = C.c_float(0)
-    rc = lib.ld_debug_conv_time(2, 32, 0, N, S, S, 0, 32, 3, 20, C.byref(ms), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
-    if rc != 0:
-        return None
-    byts = N * S * S * (32 + 32) * 2 + 9 * 32 * 32 * 2
-    ach = byts / (ms.value / 1000.0) / 1e9
+    N, S = 2 * a.batch, a.size
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    variants = [("plain", 0, 32, 0, 1, 1), ("stats", 1, 32, 0, 1, 2), ("normalise_on_load+stats", 2, 32, 0, 1, 5), ("dual+stats", 3, 32, 32, 2, 3)]
+    rows, tot_b, tot_t = [], 0.0, 0.0
+    for name, var, c0, c1, nout, weight in variants:
+        ms = C.c_float(0)
+        if lib.ld_debug_conv_variant_time(var, c0, c1, N, S, S, 32, 20, C.byref(ms), st) != 0:
+            return None
+        byts = N * S * S * (c0 + c1 + 32 * nout) * 2 + (9 + (1 if var == 3 else 0)) * (c0 + c1) * 32 * 2
+        rows.append({"variant": name, "launches_per_forward": weight, "ms_per_launch": ms.value, "bytes_per_launch": byts,
+                     "gbs": byts / (ms.value / 1e3) / 1e9, "frac": byts / (ms.value / 1e3) / 1e9 / hbm})
+        tot_b += weight * byts
+        tot_t += weight * ms.value / 1e3
+    ach = tot_b / tot_t / 1e9
     traffic, tsrc = None, None
-    tp = os.path.join(ROOT, "profiles", "r1v_conv32_traffic.json")
-    if N == 32 and S == 256 and os.path.isfile(tp):  # the ncu capture was taken on exactly this launch shape
+    tp = os.path.join(ROOT, "profiles", "conv32_traffic.json")
+    if N == 32 and S == 256 and os.path.isfile(tp):  # ncu captures taken on exactly these launch shapes
         t = json.load(open(tp))
-        traffic, tsrc = t["traffic_bytes_per_launch"], t["source"]
-    return {"kernel": "conv_tc_kernel<32,3,32> (3x3, 32->32 ch, %dx%dx%d; TMA in, tcgen05, TMA out)" % (N, S, S), "bound": "hbm",
-            "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic, "traffic_source": tsrc,
-            "ms_per_launch": ms.value, "peak_source": src, "algorithmic_bytes_per_launch": byts}
+        traffic, tsrc = t["traffic_bytes_per_launch_weighted"], t["source"]
+    return {"kernel": "conv_tc_kernel<32,3,32> (3x3 tcgen05 conv, 32 output channels, %dx%dx%d; TMA in, TMA out), launch-weighted over its "
+                      "four in-situ variants" % (N, S, S), "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+            "traffic": traffic, "traffic_source": tsrc, "variants": rows, "peak_source": src,
+            "algorithmic_bytes_per_launch": tot_b / sum(v[5] for v in variants)}
 
 
 if __name__ == "__main__":

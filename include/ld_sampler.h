@@ -12,10 +12,12 @@
  *     ABI; `ld_last_error()` returns a thread-local, NUL-terminated description.
  *   - tensors are plain pointers + sizes.  Images are dense NCHW fp32 with C == 1 (which is
  *     byte-identical to NHWC), exactly what the reference passes around (ddpm.py:1121-1125).
- *   - device pointers are borrowed for the duration of the call; all device work is enqueued on
- *     the caller's `stream` (a cudaStream_t passed as void*); host-pointer entry points
- *     (`*_host`) copy in/out themselves and synchronise the stream before returning.
- *   - one handle per device; a handle is not thread-safe.
+ *   - device pointers are borrowed for the duration of the call; device work is ordered after the
+ *     work already enqueued on the caller's `stream` (a cudaStream_t passed as void*), and the
+ *     stream is made to wait for the results; the sampler entry points run their loop on an
+ *     engine-owned stream joined to `stream` by events (see ld_sample for host synchronisation).
+ *   - one handle per device; a handle is not thread-safe (distinct handles may be used from
+ *     distinct threads concurrently).
  *   - there is no CPU fallback: every compute entry point fails with LD_ERR_NO_DEVICE when no
  *     sm_100 device is usable.
  */
@@ -136,6 +138,12 @@ LD_API int ld_cond_encode(ld_handle* h, const float* cond, float* feat, int N, i
  * x0_trace: optional device fp32 [num_timesteps, 2, B,1,H,W] (slot 1 unused after fusion). */
 LD_API int ld_sample(ld_handle* h, const ld_sample_desc* sd, const float* cond, const float* mask,
               const float* noise, float* out, float* x0_trace, void* stream);
+/* Host synchronisation: the loop itself never touches the host (t lives on the device, one CUDA graph per timestep).  By default
+ * ld_sample waits ONCE, at the end, for its internal stream, because the reference's asserts are synchronous: "mask should be
+ * binary" (ddpm.py:698) and "x_out and x_in should be masked" (ddpm.py:790) come back as LD_ERR_MASK from this very call.  With
+ * option "async" = 1 nothing waits: the call returns after enqueueing, `stream` is made to wait for the result, and
+ * ld_sample_finish(h) delivers the deferred status (it must be called before the next ld_sample on the handle). */
+LD_API int ld_sample_finish(ld_handle* h);
 
 /* --- `GaussianDiffusion.ddim_sample` (ddpm.py:979-1075): the DDIM variant of the branch sampler -----------------
  * times: host int32 [nsteps], the `time` of every step (ddpm.py:984-986 without the trailing -1).
@@ -162,7 +170,13 @@ LD_API int ld_posterior_step(ld_handle* h, int kind, int t, float* x_out, float*
 LD_API int64_t ld_launch_count(const ld_handle* h);
 /* Device workspace currently owned by the handle, bytes. */
 LD_API int64_t ld_workspace_bytes(const ld_handle* h);
-/* Tunables: "micro_batch" (images per UNet pass, 0 = all), "use_graph" (0/1). */
+/* Tunables (cached plans are dropped, the new value takes effect on the next call):
+ *   "use_graph" (default 1)  replay one CUDA graph per timestep instead of launching the ~100 kernels of a step one by one;
+ *   "async"     (default 0)  ld_sample / ld_sample_ddim return without synchronising: all work is enqueued, `stream` waits on it,
+ *                            and the reference's asserts (ddpm.py:698, 790) are reported by ld_sample_finish instead;
+ *   "la_exact"  (default 0)  LinearAttention through the exact-max kernels (the engine switches to them by itself when the fused
+ *                            kernels' analytic soft-max shift underflows, see ld_sample);
+ *   "attn_simt", "debug_keep", "use_tc" (before ld_finalize_weights): test aids. */
 LD_API int ld_set_option(ld_handle* h, const char* name, int64_t value);
 
 /* --- test hooks (used by tests/ only) ---------------------------------------------------------
@@ -203,6 +217,12 @@ LD_API int ld_debug_conv7(const float* x, int N, int H, int W, const float* w_ho
  * synthetic operands; used by bench.py for the roofline of the dominant kernel. */
 LD_API int ld_debug_conv_time(int kernel, int C0, int C1, int N, int H, int W, int up, int Cout, int ks,
                               int iters, float* ms_out, void* stream);
+
+/* Same for the dominant 3x3 tcgen05 convolution in the variants the sampler launches it in (ddpm.py:173-212):
+ * variant 0 plain; 1 + fused GroupNorm statistics of the output; 2 + normalise-on-load prologue of the source and statistics;
+ * 3 dual: 3x3 + 1x1 res_conv of the same virtual concat [C0 | C1] with statistics (two outputs). */
+LD_API int ld_debug_conv_variant_time(int variant, int C0, int C1, int N, int H, int W, int Cout, int iters, float* ms_out,
+                                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -49,6 +49,7 @@ SIGNATURES = {
     "ld_unet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ld_cond_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ld_sample": (C.c_int, [C.c_void_p, C.POINTER(SampleDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ld_sample_finish": (C.c_int, [C.c_void_p]),
     "ld_posterior_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.POINTER(SampleDesc), C.c_int64, C.c_void_p]),
     "ld_launch_count": (C.c_int64, [C.c_void_p]),
@@ -59,6 +60,8 @@ SIGNATURES = {
     "ld_debug_tap_fetch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ld_debug_conv_time": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.POINTER(C.c_float), C.c_void_p]),
+    "ld_debug_conv_variant_time": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                             C.c_void_p]),
     "ld_debug_conv_fused": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                       C.c_void_p]),

@@ -27,11 +27,18 @@ def extract_state_dict(ckpt, use_ema=True):
     return dict(ckpt["model"])
 
 
-def load_reference_checkpoint(diffusion, ckpt, use_ema=True, strict=True, map_location="cpu"):
+def load_reference_checkpoint(diffusion, ckpt, use_ema=True, strict=True, map_location="cpu", allow_pickle=False):
     """`Trainer.load` + `trainer.ema.ema_model` (ddpm.py:1509-1527, test.py:139-147) for the B200 `GaussianDiffusion`.
-    `ckpt` is a path to `model-<milestone>.pt` or the already loaded dict.  Returns the checkpoint's `step`."""
+    `ckpt` is a path to `model-<milestone>.pt` or the already loaded dict.  Returns the checkpoint's `step`.
+    Files are read with `weights_only=True`; `allow_pickle=True` falls back to full unpickling (the reference's `Trainer.save`
+    stores the optimiser and GradScaler state too, which older torch versions cannot load tensors-only) -- trusted files only."""
     if not isinstance(ckpt, dict):
-        ckpt = torch.load(ckpt, map_location=map_location, weights_only=False)
+        try:   # tensors-only unpickling first: a checkpoint file is untrusted input
+            ckpt = torch.load(ckpt, map_location=map_location, weights_only=True)
+        except Exception:
+            if not allow_pickle:
+                raise
+            ckpt = torch.load(ckpt, map_location=map_location, weights_only=False)
     sd = extract_state_dict(ckpt, use_ema)
     own = diffusion.state_dict()
     # buffers that only the training loss reads may be absent from / extra in older checkpoints: never block on them

@@ -78,6 +78,9 @@ struct GnApplyP {
   void* out;
   int N, HW, C;
   float eps;
+  // bf16 fast path only: instead of storing the C-channel result, reduce it with a 1x1 convolution to ONE fp32 channel
+  // (final_conv of the denoiser, ddpm.py:398, folded into the last ResnetBlock's output pass): dot_out[n*HW + p] = dot_b[0] + sum_c dot_w[c] y[p,c]
+  const float* dot_w; const float* dot_b; float* dot_out;
 };
 
 }  // namespace ld

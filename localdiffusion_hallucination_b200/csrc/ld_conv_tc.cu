@@ -33,7 +33,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 
-#include <string>
+#include <string.h>
+
+#include <mutex>
 #include <unordered_map>
 #include <vector>
 
@@ -1169,22 +1171,61 @@ static bool build_params(const ConvTcW& w, const ConvTcArgs& a, KParams& p) {
   return k64;
 }
 
+// The cache is shared by every handle of the process (plans of different handles may launch concurrently from different
+// threads): guarded by a mutex, keyed on an explicit field-by-field serialisation (no struct padding in the key).
+namespace {
+struct ParamKey {
+  uint64_t v[20];
+  bool operator==(const ParamKey& o) const { return memcmp(v, o.v, sizeof v) == 0; }
+};
+struct ParamKeyHash {
+  size_t operator()(const ParamKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t x : k.v) { h ^= x; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+ParamKey make_key(const ConvTcW& w, const ConvTcArgs& a) {
+  ParamKey k{};
+  int i = 0;
+  k.v[i++] = (uint64_t)(uintptr_t)a.src0; k.v[i++] = (uint64_t)(uintptr_t)a.src1; k.v[i++] = (uint64_t)(uintptr_t)a.dst;
+  k.v[i++] = (uint64_t)(uintptr_t)a.res; k.v[i++] = (uint64_t)(uintptr_t)a.dst2; k.v[i++] = (uint64_t)(uintptr_t)a.pro_ab;
+  k.v[i++] = (uint64_t)(uintptr_t)a.stats;
+  k.v[i++] = ((uint64_t)(uint32_t)a.C0 << 32) | (uint32_t)a.C1;
+  k.v[i++] = ((uint64_t)(uint32_t)a.N << 32) | (uint32_t)a.H;
+  k.v[i++] = ((uint64_t)(uint32_t)a.W << 32) | (uint32_t)a.Hin;
+  k.v[i++] = ((uint64_t)(uint32_t)a.Win << 32) | (uint32_t)((a.up & 1) | ((a.ds & 1) << 1) | ((a.pro_act & 3) << 2));
+  k.v[i++] = (uint64_t)(uint32_t)a.stats_G;
+  k.v[i++] = (uint64_t)(uintptr_t)w.w; k.v[i++] = (uint64_t)(uintptr_t)w.w32; k.v[i++] = (uint64_t)(uintptr_t)w.bias;
+  k.v[i++] = (uint64_t)(uintptr_t)w.bias2;
+  k.v[i++] = ((uint64_t)(uint32_t)w.Cin << 32) | (uint32_t)w.Cout;
+  k.v[i++] = ((uint64_t)(uint32_t)w.ks << 32) | (uint32_t)w.ntile;
+  int dev = 0; cudaGetDevice(&dev);
+  k.v[i++] = (uint64_t)dev;
+  return k;
+}
+}  // namespace
+
 int conv_tc_launch(const ConvTcW& w, const ConvTcArgs& a, cudaStream_t s) {
   if (!conv_tc_supports(w, a)) return -1;
   struct Cached { KParams p; bool k64; };
-  static std::unordered_map<std::string, Cached> cache;
-  std::string key(reinterpret_cast<const char*>(&a), sizeof(ConvTcArgs));
-  const void* wk[4] = {w.w, w.w32, w.bias, w.bias2};
-  key.append(reinterpret_cast<const char*>(wk), sizeof wk);
-  auto it = cache.find(key);
-  if (it == cache.end()) {
-    if (cache.size() > 4096) cache.clear();
-    Cached c;
-    c.k64 = build_params(w, a, c.p);
-    it = cache.emplace(std::move(key), c).first;
+  static std::unordered_map<ParamKey, Cached, ParamKeyHash> cache;
+  static std::mutex mu;
+  KParams p;
+  bool k64;
+  {
+    const ParamKey key = make_key(w, a);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+      if (cache.size() > 4096) cache.clear();
+      Cached c;
+      c.k64 = build_params(w, a, c.p);
+      it = cache.emplace(key, c).first;
+    }
+    p = it->second.p;
+    k64 = it->second.k64;
   }
-  KParams p = it->second.p;
-  const bool k64 = it->second.k64;
   if (a.ds && !p.tma_in) return -1;
   const int ny = w.Cout / w.ntile;
   if (w.ks == 3) return k64 ? launch_nt<3, 64>(w.ntile, p, ny, s) : launch_nt<3, 32>(w.ntile, p, ny, s);

@@ -120,7 +120,8 @@ struct Engine {
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   int64_t launches = 0;
-  int64_t opt_micro_batch = 0, opt_use_graph = 1, opt_debug_keep = 0, opt_la_exact = 0, opt_attn_simt = 0;
+  int64_t opt_use_graph = 1, opt_debug_keep = 0, opt_la_exact = 0, opt_attn_simt = 0, opt_async = 0;
+  bool pending = false; ld_sample_desc pend_sd{}; bool pend_fuse = false;   // opt_async: checks deferred to ld_sample_finish
   unsigned int* la_flag = nullptr;        // soft-max underflow counter of the fused LinearAttention
   // sampler: FiLM rows of every timestep [film_tab_T][film_total] -- time MLP + block MLPs depend on t only (ddpm.py:339-344,191-194),
   // so the loop gathers a row instead of running them
@@ -136,6 +137,7 @@ struct Engine {
     int* t_dev = nullptr;
     int64_t* t64 = nullptr;
     std::vector<void*> allocs;
+    void* ddim_blk = nullptr; size_t ddim_bytes = 0;   // DDIM: step index, times, coefficients
     cudaGraphExec_t g_branch = nullptr, g_single = nullptr;
     std::string key;
   } ss;
@@ -161,10 +163,18 @@ struct Engine {
     if (ss.g_branch) cudaGraphExecDestroy(ss.g_branch);
     if (ss.g_single) cudaGraphExecDestroy(ss.g_single);
     for (void* p : ss.allocs) cudaFree(p);
+    if (ss.ddim_blk) cudaFree(ss.ddim_blk);
     ss = SampState();
   }
   size_t esz() const { return bf ? 2 : 4; }
 };
+
+static void drop_plans(Engine& E) {
+  E.free_samp();
+  E.plans.clear();
+  for (auto& kv : E.staged) { kv.second.cond.reset(); kv.second.unet.reset(); kv.second.free_all(); }
+  E.staged.clear();
+}
 
 // -------------------------------------------------------------------------------------------------
 // spec generation (state_dict keys + shapes)
@@ -566,9 +576,11 @@ struct Builder {
   // out = act(GN(xa)*film) (+ xb variants), see GnApplyP
   Ten gn_apply(const Ten& xa, double* stA, const float* gA, const float* bA, int GA, int film_off, int act,
                const Ten* xb, int modeB, double* stB = nullptr, const float* gB = nullptr, const float* bB = nullptr,
-               int GB = 1) {
-    Ten o = act_t(xa);
+               int GB = 1, const ConvW* dot = nullptr, float* dot_out = nullptr) {
+    Ten o;
+    if (!dot) o = act_t(xa);
     GnApplyP p{};
+    if (dot) { p.dot_w = dot->w; p.dot_b = dot->bias; p.dot_out = dot_out; }
     p.xa = xa.p; p.statsA = stA; p.gA = gA; p.bA = bA; p.GA = GA;
     p.xb = xb ? xb->p : nullptr; p.statsB = stB; p.gB = gB; p.bB = bB; p.GB = GB; p.modeB = modeB;
     p.film = film_off >= 0 ? film + film_off : nullptr; p.film_stride = film_stride;
@@ -587,7 +599,9 @@ struct Builder {
   // ---- ResnetBlock (ddpm.py:200-212) -----------------------------------------------------------
   // block1: conv (+ statistics in its epilogue); block2: conv whose staging applies GN1 + FiLM + SiLU and whose
   // epilogue gathers the GN2 statistics; one elementwise pass: SiLU(GN2(h2)) + res_conv(x).
-  Ten resblock(const std::string& name, Ten& a, Ten* b) {
+  // `dot` / `dot_out`: fold the 1x1 convolution to one fp32 channel that consumes the block's output (final_conv, ddpm.py:398)
+  // into the output pass; the block's own output tensor is then never written
+  Ten resblock(const std::string& name, Ten& a, Ten* b, const ConvW* dot = nullptr, float* dot_out = nullptr) {
     const ResW& r = E.res[E.res_index.at(name)];
     const int G = E.d.resnet_groups;
     double* s1 = stats_alloc(a.N, G);
@@ -601,10 +615,10 @@ struct Builder {
     Ten o;
     if (r.has_res) {
       if (!dual) rs = conv_same(r.res, a, b);
-      o = gn_apply(h2, s2, r.g2, r.b2, G, -1, 1, &rs, 1);
+      o = gn_apply(h2, s2, r.g2, r.b2, G, -1, 1, &rs, 1, nullptr, nullptr, nullptr, 1, dot, dot_out);
       release(rs);
     } else {
-      o = gn_apply(h2, s2, r.g2, r.b2, G, -1, 1, &a, 1);
+      o = gn_apply(h2, s2, r.g2, r.b2, G, -1, 1, &a, 1, nullptr, nullptr, nullptr, 1, dot, dot_out);
     }
     release(h2);
     return o;
@@ -818,6 +832,13 @@ static int build_unet_plan(Engine& E, Plan& P, int N, int H, int W, const float*
     B.tag(p + ".3", cur);
     B.release(c);
   }
+  // final ResnetBlock + final_conv (ddpm.py:449-451): on the bf16 path the 1x1 convolution to the single output channel rides on the
+  // block's output pass (the 32-channel tensor is never written); debug taps and the fp32 parity path keep the two steps apart
+  if (gn_apply_can_dot(E.d.dim, bf) && !E.opt_debug_keep) {
+    B.resblock("final_res_block", cur, &r, &E.final_conv, out); B.release(cur); B.release(r);
+    if (B.err) return B.err;
+    return B.finish();
+  }
   Ten f = B.resblock("final_res_block", cur, &r); B.release(cur); B.release(r);
   B.tag("final_res_block", f);
   if (B.err) return B.err;
@@ -872,6 +893,18 @@ static int check_shape(const Engine& E, int H, int W) {
     return fail(LD_ERR_INVALID, "UNet bottleneck (S/%d) and conditional encoder (S/%d) resolutions differ", f, E.cond_div);
   return 0;
 }
+
+// device scratch that is released on every exit path
+struct Scratch {
+  std::vector<void*> ptrs;
+  ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+  template <typename T> cudaError_t get(T** p, size_t bytes) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e == cudaSuccess) { ptrs.push_back(q); *p = (T*)q; }
+    return e;
+  }
+};
 
 }  // namespace ld
 
@@ -1046,52 +1079,57 @@ static int dalloc(Engine& E, void** p, size_t bytes) {
   return 0;
 }
 
+// Sampler state of one (batch, height, width): buffers + the single-trajectory plans.  The branched plans are built on
+// demand and kept next to them, so alternating anomalous masks (branched) with all-ones masks (vanilla DDPM, ddpm.py:1110-1117),
+// as the reference's test loop does, re-uses everything.
 static int prepare_sampler(Engine& E, const ld_sample_desc& sd) {
   char k[128];
   const bool pair_unet = sd.branch_out && !(sd.mask_x && sd.ood_uses_cond);
-  snprintf(k, sizeof k, "%dx%dx%d/b%d/p%d", sd.batch, sd.height, sd.width, sd.branch_out, (int)pair_unet);
-  if (E.ss.key == k) return 0;
-  E.free_samp(); E.plans.clear();
+  snprintf(k, sizeof k, "%dx%dx%d", sd.batch, sd.height, sd.width);
   auto& S = E.ss;
-  S.B = sd.batch; S.H = sd.height; S.W = sd.width;
   const size_t n = (size_t)sd.batch * sd.height * sd.width;
-  const int fh = sd.height / E.cond_div, fw = sd.width / E.cond_div;
-  const size_t featB = (size_t)sd.batch * fh * fw * E.cond_C * E.esz();
-  int rc;
-  if ((rc = dalloc(E, (void**)&S.xs, 2 * n * 4))) return rc;
-  if ((rc = dalloc(E, (void**)&S.o, 2 * n * 4))) return rc;
-  if ((rc = dalloc(E, (void**)&S.bm, n * 4))) return rc;
-  if ((rc = dalloc(E, (void**)&S.cond, n * 4))) return rc;
-  if ((rc = dalloc(E, (void**)&S.cond_out, 2 * n * 4))) return rc;  // [cond_out; cond_in] contiguous
-  S.cond_in = S.cond_out + n;
-  if ((rc = dalloc(E, &S.feat_pair, 2 * featB))) return rc;
-  if ((rc = dalloc(E, &S.feat_full, featB))) return rc;
-  if ((rc = dalloc(E, (void**)&S.counters, 4 * sizeof(unsigned int)))) return rc;
-  if ((rc = dalloc(E, (void**)&S.t_dev, sizeof(int)))) return rc;
   const int B = sd.batch, H = sd.height, W = sd.width;
-  // conditional-feature plans (hoisted out of the loop: the encoder does not depend on t)
-  if (sd.branch_out) {
-    auto p = std::unique_ptr<Plan>(new Plan());
-    if (pair_unet) rc = build_cond_plan(E, *p, 2 * B, H, W, S.cond_out, S.feat_pair);
-    else rc = build_cond_plan(E, *p, B, H, W, S.cond_in, S.feat_pair);
-    if (rc) return rc;
-    E.plans["cond_pair"] = std::move(p);
-    p.reset(new Plan());
-    // branched UNet: x = [x_out; x_in] (or x_in only when the OOD output is discarded, ddpm.py:704-708)
-    if (pair_unet) rc = build_unet_plan(E, *p, 2 * B, H, W, S.xs, S.feat_pair, nullptr, S.t_dev, S.o);
-    else rc = build_unet_plan(E, *p, B, H, W, S.xs + n, S.feat_pair, nullptr, S.t_dev, S.o + n);
-    if (rc) return rc;
-    E.plans["unet_pair"] = std::move(p);
-  }
-  {
+  int rc;
+  if (S.key != k) {
+    E.free_samp(); E.plans.clear();
+    S.B = B; S.H = H; S.W = W;
+    const int fh = H / E.cond_div, fw = W / E.cond_div;
+    const size_t featB = (size_t)B * fh * fw * E.cond_C * E.esz();
+    if ((rc = dalloc(E, (void**)&S.xs, 2 * n * 4))) return rc;
+    if ((rc = dalloc(E, (void**)&S.o, 2 * n * 4))) return rc;
+    if ((rc = dalloc(E, (void**)&S.bm, n * 4))) return rc;
+    if ((rc = dalloc(E, (void**)&S.cond, n * 4))) return rc;
+    if ((rc = dalloc(E, (void**)&S.cond_out, 2 * n * 4))) return rc;  // [cond_out; cond_in] contiguous
+    S.cond_in = S.cond_out + n;
+    if ((rc = dalloc(E, &S.feat_pair, 2 * featB))) return rc;
+    if ((rc = dalloc(E, &S.feat_full, featB))) return rc;
+    if ((rc = dalloc(E, (void**)&S.counters, 8 * sizeof(unsigned int)))) return rc;   // [0..3] assertion counters, [4] step ticket
+    if ((rc = dalloc(E, (void**)&S.t_dev, sizeof(int)))) return rc;
     auto p = std::unique_ptr<Plan>(new Plan());
     if ((rc = build_cond_plan(E, *p, B, H, W, S.cond, S.feat_full))) return rc;
     E.plans["cond_full"] = std::move(p);
     p.reset(new Plan());
     if ((rc = build_unet_plan(E, *p, B, H, W, S.xs, S.feat_full, nullptr, S.t_dev, S.o))) return rc;
     E.plans["unet_full"] = std::move(p);
+    S.key = k;
   }
-  S.key = k;
+  if (sd.branch_out) {
+    // conditional-feature plans are hoisted out of the loop (the encoder does not depend on t);
+    // branched UNet: x = [x_out; x_in], or x_in only when the OOD output is discarded (ddpm.py:704-708)
+    const std::string ck = pair_unet ? "cond_pair/2" : "cond_pair/1", uk = pair_unet ? "unet_pair/2" : "unet_pair/1";
+    if (!E.plans.count(uk)) {
+      auto p = std::unique_ptr<Plan>(new Plan());
+      if (pair_unet) rc = build_cond_plan(E, *p, 2 * B, H, W, S.cond_out, S.feat_pair);
+      else rc = build_cond_plan(E, *p, B, H, W, S.cond_in, S.feat_pair);
+      if (rc) return rc;
+      E.plans[ck] = std::move(p);
+      p.reset(new Plan());
+      if (pair_unet) rc = build_unet_plan(E, *p, 2 * B, H, W, S.xs, S.feat_pair, nullptr, S.t_dev, S.o);
+      else rc = build_unet_plan(E, *p, B, H, W, S.xs + n, S.feat_pair, nullptr, S.t_dev, S.o + n);
+      if (rc) return rc;
+      E.plans[uk] = std::move(p);
+    }
+  }
   return 0;
 }
 
@@ -1133,6 +1171,7 @@ static StepP make_step(Engine& E, const ld_sample_desc& sd, int kind, const floa
   p.mask_x = sd.mask_x; p.ood_uses_cond = sd.ood_uses_cond; p.lo = sd.min_val; p.hi = sd.max_val;
   p.n = n; p.z_stride = n; p.tloop = sd.num_timesteps; p.counters = S.counters;
   p.x0_trace = x0_trace; p.trace_stride = 2 * n;
+  p.ticket = S.counters + 4;   // the step kernel also does `t -= 1` (ddpm.py:951)
   return p;
 }
 
@@ -1150,54 +1189,72 @@ static int capture(Engine& E, cudaGraphExec_t* exec, const std::function<int(cud
   return 0;
 }
 
-int ld_sample(ld_handle* h, const ld_sample_desc* sdp, const float* cond, const float* mask, const float* noise, float* out,
-              float* x0_trace, void* stream) {
-  if (!h || !sdp || !cond || !noise || !out) return fail(LD_ERR_INVALID, "null argument");
+// The asserts of the reference (ddpm.py:698, 790) and the soft-max shift check of the fused LinearAttention, from the counters
+// the loop left on the host.  *la_retry is set when the call has to be repeated on the exact-max LinearAttention path.
+static int finish_checks(Engine& E, const ld_sample_desc& sd, bool will_fuse, const unsigned int* cnt, unsigned int la_under, bool* la_retry) {
+  if (la_retry) *la_retry = false;
+  if (la_under) {
+    cudaMemset(E.la_flag, 0, sizeof(unsigned int));
+    if (la_retry && !E.opt_la_exact) { *la_retry = true; return 0; }
+    return fail(LD_ERR_STATE, "LinearAttention soft-max shift underflowed (%u rows)", la_under);
+  }
+  if (sd.branch_out && sd.mask_x && (cnt[0] == 0 || cnt[1] == 0)) return fail(LD_ERR_MASK, "mask should be binary");
+  if (will_fuse && !(cnt[2] > 0 && cnt[3] > 0)) return fail(LD_ERR_MASK, "x_out and x_in should be masked");
+  return 0;
+}
+
+// The fused LinearAttention shifts its soft-max over the pixels by an analytic bound instead of the true maximum (ld_linattn_tc.cu);
+// with extreme to_qkv weights a whole row of weights can underflow.  The kernels count such rows; the loop looks at the counter
+// after its first timestep and at its end, and on a hit the engine switches to the exact-max path for good (plans rebuilt) and
+// repeats the call -- no user action, no wrong result.
+static int switch_to_exact_linattn(Engine& E) {
+  E.opt_la_exact = 1;
+  drop_plans(E);
+  return 0;
+}
+
+static int sample_impl(ld_handle* h, const ld_sample_desc& sd, const float* cond, const float* mask, const float* noise, float* out,
+                       float* x0_trace, cudaStream_t cs, bool allow_retry) {
   Engine& E = h->E;
-  const ld_sample_desc sd = *sdp;
-  int rc = need_ready(E); if (rc) return rc;
-  if (!E.T) return fail(LD_ERR_STATE, "schedule not set");
-  if (sd.num_timesteps < 1 || sd.num_timesteps > E.T) return fail(LD_ERR_INVALID, "num_timesteps out of range");
-  if (sd.branch_out && !mask) return fail(LD_ERR_INVALID, "branch mode needs a mask");
-  if ((rc = check_shape(E, sd.height, sd.width))) return rc;
+  int rc;
   if ((rc = prepare_sampler(E, sd))) return rc;
   if ((rc = ensure_film_table(E, E.T, E.own_stream))) return rc;
   auto& S = E.ss;
-  cudaStream_t cs = (cudaStream_t)stream, s = E.own_stream;
+  cudaStream_t s = E.own_stream;
   const long long n = (long long)sd.batch * sd.height * sd.width;
   const bool pair_unet = sd.branch_out && !(sd.mask_x && sd.ood_uses_cond);
   // hand over from the caller's stream to the engine stream
   CK(cudaEventRecord(E.ev_in, cs));
   CK(cudaStreamWaitEvent(s, E.ev_in, 0));
-  CK(cudaMemsetAsync(S.counters, 0, 4 * sizeof(unsigned int), s));
+  CK(cudaMemsetAsync(S.counters, 0, 8 * sizeof(unsigned int), s));
   CK(cudaMemcpyAsync(S.cond, cond, n * 4, cudaMemcpyDeviceToDevice, s));
   CK(cudaMemcpyAsync(S.xs, noise, n * 4, cudaMemcpyDeviceToDevice, s));          // x_T (ddpm.py:935)
   const int t0 = sd.num_timesteps - 1;
   CK(cudaMemcpyAsync(S.t_dev, &t0, sizeof(int), cudaMemcpyHostToDevice, s));
   bool branched = sd.branch_out != 0;
+  Plan* up = branched ? E.plans[pair_unet ? "unet_pair/2" : "unet_pair/1"].get() : nullptr;
+  Plan* uf = E.plans["unet_full"].get();
   if (branched) {
     CK(cudaMemcpyAsync(S.xs + n, noise, n * 4, cudaMemcpyDeviceToDevice, s));    // img = [img, img] (ddpm.py:957)
     PrepP pp{}; pp.cond = S.cond; pp.mask = mask; pp.bm = S.bm; pp.cond_out = S.cond_out; pp.cond_in = S.cond_in;
     pp.floor = sd.cond_in_floor; pp.n = n; pp.counters = S.counters;
     E.launches += launch_prep_cond(pp, s);
-    if ((rc = run_plan(E, *E.plans["cond_pair"], s))) return rc;
+    if ((rc = run_plan(E, *E.plans[pair_unet ? "cond_pair/2" : "cond_pair/1"], s))) return rc;
   }
   const bool will_fuse = branched && sd.start_intermediate && sd.start_timestep >= 0;
   if (!branched || will_fuse) { if ((rc = run_plan(E, *E.plans["cond_full"], s))) return rc; }
 
-  Plan* up = branched ? E.plans["unet_pair"].get() : nullptr;
-  Plan* uf = E.plans["unet_full"].get();
   auto body_branch = [&](cudaStream_t st) -> int {
     int r = run_plan(E, *up, st); if (r) return r;
     StepP p = make_step(E, sd, 0, noise, x0_trace);
     if (!pair_unet) p.o_out = nullptr;
-    E.launches += launch_step(p, st); E.launches += launch_dec_t(S.t_dev, st);
+    E.launches += launch_step(p, st);
     return 0;
   };
   auto body_single = [&](cudaStream_t st) -> int {
     int r = run_plan(E, *uf, st); if (r) return r;
     StepP p = make_step(E, sd, 2, noise, x0_trace);
-    E.launches += launch_step(p, st); E.launches += launch_dec_t(S.t_dev, st);
+    E.launches += launch_step(p, st);
     return 0;
   };
   // graphs bake the tape / trace pointers: re-capture on every call (cheap next to T replays)
@@ -1213,6 +1270,7 @@ int ld_sample(ld_handle* h, const ld_sample_desc* sdp, const float* cond, const 
     per_single = E.launches - l0;
     E.launches -= per_branch + per_single;  // captured, not launched
   }
+  unsigned int la_under = 0;
   for (int t = sd.num_timesteps - 1; t >= 0; --t) {
     if (branched) {
       const bool fuse = sd.start_intermediate && t <= sd.start_timestep;  // ddpm.py:779
@@ -1220,7 +1278,7 @@ int ld_sample(ld_handle* h, const ld_sample_desc* sdp, const float* cond, const 
         if ((rc = run_plan(E, *up, s))) return rc;
         StepP p = make_step(E, sd, 1, noise, x0_trace);
         if (!pair_unet) p.o_out = nullptr;
-        E.launches += launch_step(p, s); E.launches += launch_dec_t(S.t_dev, s);
+        E.launches += launch_step(p, s);
         branched = false;  // config['branch_out'] = False (ddpm.py:780)
       } else if (use_graph) {
         CK(cudaGraphLaunch(S.g_branch, s)); E.launches += per_branch;
@@ -1229,84 +1287,124 @@ int ld_sample(ld_handle* h, const ld_sample_desc* sdp, const float* cond, const 
       if (use_graph) { CK(cudaGraphLaunch(S.g_single, s)); E.launches += per_single; }
       else if ((rc = body_single(s))) return rc;
     }
+    if (t == sd.num_timesteps - 1 && sd.num_timesteps > 8 && allow_retry && !E.opt_la_exact && !E.opt_async) {
+      // early look at the LinearAttention underflow counter: a long chain is not run to its end on a path that has to be repeated
+      CK(cudaMemcpyAsync(&la_under, E.la_flag, sizeof la_under, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      if (la_under) {
+        cudaMemset(E.la_flag, 0, sizeof(unsigned int));
+        if ((rc = switch_to_exact_linattn(E))) return rc;
+        return sample_impl(h, sd, cond, mask, noise, out, x0_trace, cs, false);
+      }
+    }
   }
   // result (ddpm.py:964-970)
-  if (sd.return_pair) {
-    CK(cudaMemcpyAsync(out, S.xs, n * 4, cudaMemcpyDeviceToDevice, s));
-    CK(cudaMemcpyAsync(out + n, branched ? S.xs + n : S.xs, n * 4, cudaMemcpyDeviceToDevice, s));
-  } else {
-    CK(cudaMemcpyAsync(out, S.xs, n * 4, cudaMemcpyDeviceToDevice, s));
-  }
-  unsigned int cnt[4], la_under = 0;
-  CK(cudaMemcpyAsync(cnt, S.counters, sizeof cnt, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(&la_under, E.la_flag, sizeof la_under, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(out, S.xs, n * 4, cudaMemcpyDeviceToDevice, s));
+  if (sd.return_pair) CK(cudaMemcpyAsync(out + n, branched ? S.xs + n : S.xs, n * 4, cudaMemcpyDeviceToDevice, s));
   CK(cudaEventRecord(E.ev_out, s));
   CK(cudaStreamWaitEvent(cs, E.ev_out, 0));
-  CK(cudaStreamSynchronize(s));
-  if (la_under) {
-    cudaMemset(E.la_flag, 0, sizeof(unsigned int));
-    return fail(LD_ERR_STATE, "LinearAttention soft-max shift underflowed (%u rows): set option la_exact=1 for the exact-max path", la_under);
+  if (E.opt_async) {   // no host synchronisation: the checks wait for ld_sample_finish
+    E.pending = true; E.pend_sd = sd; E.pend_fuse = will_fuse;
+    return 0;
   }
-  if (sd.branch_out && sd.mask_x && (cnt[0] == 0 || cnt[1] == 0)) return fail(LD_ERR_MASK, "mask should be binary");
-  if (sd.branch_out && will_fuse && sd.num_timesteps - 1 >= 0 && !(cnt[2] > 0 && cnt[3] > 0) && (sd.start_timestep >= 0))
-    return fail(LD_ERR_MASK, "x_out and x_in should be masked");
+  unsigned int cnt[4];
+  CK(cudaMemcpyAsync(cnt, S.counters, sizeof cnt, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&la_under, E.la_flag, sizeof la_under, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  bool retry = false;
+  if ((rc = finish_checks(E, sd, will_fuse, cnt, la_under, allow_retry ? &retry : nullptr))) return rc;
+  if (retry) {
+    if ((rc = switch_to_exact_linattn(E))) return rc;
+    return sample_impl(h, sd, cond, mask, noise, out, x0_trace, cs, false);
+  }
   return 0;
+}
+
+int ld_sample(ld_handle* h, const ld_sample_desc* sdp, const float* cond, const float* mask, const float* noise, float* out,
+              float* x0_trace, void* stream) {
+  if (!h || !sdp || !cond || !noise || !out) return fail(LD_ERR_INVALID, "null argument");
+  Engine& E = h->E;
+  const ld_sample_desc sd = *sdp;
+  int rc = need_ready(E); if (rc) return rc;
+  if (!E.T) return fail(LD_ERR_STATE, "schedule not set");
+  if (E.pending) return fail(LD_ERR_STATE, "a deferred call is pending: call ld_sample_finish first");
+  if (sd.num_timesteps < 1 || sd.num_timesteps > E.T) return fail(LD_ERR_INVALID, "num_timesteps out of range");
+  if (sd.branch_out && !mask) return fail(LD_ERR_INVALID, "branch mode needs a mask");
+  if ((rc = check_shape(E, sd.height, sd.width))) return rc;
+  return sample_impl(h, sd, cond, mask, noise, out, x0_trace, (cudaStream_t)stream, true);
+}
+
+// Deferred half of an "async" ld_sample / ld_sample_ddim: waits for the engine stream and reports what the synchronous call would have.
+int ld_sample_finish(ld_handle* h) {
+  if (!h) return fail(LD_ERR_INVALID, "null handle");
+  Engine& E = h->E;
+  int rc = need_ready(E); if (rc) return rc;
+  if (!E.pending) return 0;
+  E.pending = false;
+  unsigned int cnt[4], la_under = 0;
+  CK(cudaMemcpyAsync(cnt, E.ss.counters, sizeof cnt, cudaMemcpyDeviceToHost, E.own_stream));
+  CK(cudaMemcpyAsync(&la_under, E.la_flag, sizeof la_under, cudaMemcpyDeviceToHost, E.own_stream));
+  CK(cudaStreamSynchronize(E.own_stream));
+  return finish_checks(E, E.pend_sd, E.pend_fuse, cnt, la_under, nullptr);
 }
 
 // DDIM variant of the branch sampler (ddpm.py:979-1075): same UNet plans and masks, the schedule of (time, coefficient)
 // pairs comes from the host (diffusion.py builds it with the reference's own tensor ops), the step index lives on the device.
-int ld_sample_ddim(ld_handle* h, const ld_sample_desc* sdp, const float* cond, const float* mask, const float* noise, float* out,
-                   const int32_t* times, const float* coefs, int nsteps, int fuse_step, void* stream) {
-  if (!h || !sdp || !cond || !noise || !out || !times || !coefs) return fail(LD_ERR_INVALID, "null argument");
+static int ddim_impl(ld_handle* h, const ld_sample_desc& sd, const float* cond, const float* mask, const float* noise, float* out,
+                     const int32_t* times, const float* coefs, int nsteps, int fuse_step, cudaStream_t cs, bool allow_retry) {
   Engine& E = h->E;
-  const ld_sample_desc sd = *sdp;
-  int rc = need_ready(E); if (rc) return rc;
-  if (nsteps < 1) return fail(LD_ERR_INVALID, "nsteps out of range");
-  if (sd.branch_out && !mask) return fail(LD_ERR_INVALID, "branch mode needs a mask");
-  if ((rc = check_shape(E, sd.height, sd.width))) return rc;
+  int rc;
   if ((rc = prepare_sampler(E, sd))) return rc;
   if (E.T && (rc = ensure_film_table(E, E.T, E.own_stream))) return rc;
   auto& S = E.ss;
-  cudaStream_t cs = (cudaStream_t)stream, s = E.own_stream;
+  cudaStream_t s = E.own_stream;
   const long long n = (long long)sd.batch * sd.height * sd.width;
   const bool pair_unet = sd.branch_out && !(sd.mask_x && sd.ood_uses_cond);
-  // device copy of the schedule + step index (freed at the end of the call)
+  // device copy of the schedule + step index (owned by the sampler state: an async call outlives this function)
   int* times_d = nullptr; float* coefs_d = nullptr; int* idx_d = nullptr;
-  CK(cudaMalloc(&times_d, (size_t)nsteps * sizeof(int))); CK(cudaMalloc(&coefs_d, (size_t)nsteps * 5 * sizeof(float)));
-  CK(cudaMalloc(&idx_d, sizeof(int)));
-  auto cleanup = [&]() { cudaFree(times_d); cudaFree(coefs_d); cudaFree(idx_d); };
+  {
+    void* blk = nullptr;
+    const size_t bytes = (size_t)nsteps * 4 + (size_t)nsteps * 5 * 4 + 16;
+    if (S.ddim_blk && S.ddim_bytes >= bytes) blk = S.ddim_blk;
+    else {
+      if (S.ddim_blk) { CK(cudaStreamSynchronize(s)); cudaFree(S.ddim_blk); S.ddim_blk = nullptr; }
+      CK(cudaMalloc(&blk, bytes));
+      S.ddim_blk = blk; S.ddim_bytes = bytes;
+    }
+    idx_d = (int*)blk; times_d = idx_d + 4; coefs_d = (float*)(times_d + nsteps);
+  }
   CK(cudaEventRecord(E.ev_in, cs));
   CK(cudaStreamWaitEvent(s, E.ev_in, 0));
   CK(cudaMemcpyAsync(times_d, times, (size_t)nsteps * sizeof(int), cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(coefs_d, coefs, (size_t)nsteps * 5 * sizeof(float), cudaMemcpyHostToDevice, s));
   CK(cudaMemsetAsync(idx_d, 0, sizeof(int), s));
   CK(cudaMemcpyAsync(S.t_dev, times, sizeof(int), cudaMemcpyHostToDevice, s));
-  CK(cudaMemsetAsync(S.counters, 0, 4 * sizeof(unsigned int), s));
+  CK(cudaMemsetAsync(S.counters, 0, 8 * sizeof(unsigned int), s));
   CK(cudaMemcpyAsync(S.cond, cond, n * 4, cudaMemcpyDeviceToDevice, s));
   CK(cudaMemcpyAsync(S.xs, noise, n * 4, cudaMemcpyDeviceToDevice, s));          // img = randn(shape) (ddpm.py:989)
   bool branched = sd.branch_out != 0;
+  Plan* up = branched ? E.plans[pair_unet ? "unet_pair/2" : "unet_pair/1"].get() : nullptr;
+  Plan* uf = E.plans["unet_full"].get();
   if (branched) {
     CK(cudaMemcpyAsync(S.xs + n, noise, n * 4, cudaMemcpyDeviceToDevice, s));    // img = [img, img] (ddpm.py:1003-1004)
     PrepP pp{}; pp.cond = S.cond; pp.mask = mask; pp.bm = S.bm; pp.cond_out = S.cond_out; pp.cond_in = S.cond_in;
     pp.floor = sd.cond_in_floor; pp.n = n; pp.counters = S.counters;
     E.launches += launch_prep_cond(pp, s);
-    if ((rc = run_plan(E, *E.plans["cond_pair"], s))) { cleanup(); return rc; }
+    if ((rc = run_plan(E, *E.plans[pair_unet ? "cond_pair/2" : "cond_pair/1"], s))) return rc;
   }
   const bool will_fuse = branched && fuse_step >= 0 && fuse_step < nsteps - 1;   // the last step never fuses (ddpm.py:1009-1012)
-  if (!branched || will_fuse) { if ((rc = run_plan(E, *E.plans["cond_full"], s))) { cleanup(); return rc; } }
-  Plan* up = branched ? E.plans["unet_pair"].get() : nullptr;
-  Plan* uf = E.plans["unet_full"].get();
+  if (!branched || will_fuse) { if ((rc = run_plan(E, *E.plans["cond_full"], s))) return rc; }
   auto mk = [&](int kind) {
     DdimP p{};
     p.kind = kind; p.o_out = pair_unet || kind == 2 ? S.o : nullptr; p.o_in = S.o + n; p.x_out = S.xs; p.x_in = S.xs + n;
     p.bm = S.bm; p.cond_out = S.cond_out; p.z = noise; p.z_stride = n; p.idx_ptr = idx_d; p.nsteps = nsteps; p.coefs = coefs_d;
     p.mask_x = sd.mask_x; p.ood_uses_cond = sd.ood_uses_cond; p.lo = sd.min_val; p.hi = sd.max_val; p.n = n; p.counters = S.counters;
+    p.ticket = S.counters + 4; p.times = times_d; p.t_ptr = S.t_dev;   // the step kernel also advances (idx, t) (ddpm.py:996-998)
     return p;
   };
   auto body = [&](int kind, cudaStream_t st) -> int {
     int r = run_plan(E, kind == 2 ? *uf : *up, st); if (r) return r;
     E.launches += launch_ddim_step(mk(kind), st);
-    E.launches += launch_ddim_advance(idx_d, times_d, nsteps, S.t_dev, st);
     return 0;
   };
   if (S.g_branch) { cudaGraphExecDestroy(S.g_branch); S.g_branch = nullptr; }
@@ -1315,41 +1413,60 @@ int ld_sample_ddim(ld_handle* h, const ld_sample_desc* sdp, const float* cond, c
   int64_t per_branch = 0, per_single = 0;
   if (use_graph) {
     int64_t l0 = E.launches;
-    if (branched) { if ((rc = capture(E, &S.g_branch, [&](cudaStream_t st) { return body(0, st); }))) { cleanup(); return rc; } per_branch = E.launches - l0; }
+    if (branched) { if ((rc = capture(E, &S.g_branch, [&](cudaStream_t st) { return body(0, st); }))) return rc; per_branch = E.launches - l0; }
     l0 = E.launches;
-    if ((rc = capture(E, &S.g_single, [&](cudaStream_t st) { return body(2, st); }))) { cleanup(); return rc; }
+    if ((rc = capture(E, &S.g_single, [&](cudaStream_t st) { return body(2, st); }))) return rc;
     per_single = E.launches - l0;
     E.launches -= per_branch + per_single;
   }
   for (int i = 0; i < nsteps; ++i) {
     if (branched) {
       if (will_fuse && i >= fuse_step) {
-        if ((rc = body(1, s))) { cleanup(); return rc; }
+        if ((rc = body(1, s))) return rc;
         branched = false;   // config['branch_out'] = False (ddpm.py:1023)
       } else if (use_graph) {
         CK(cudaGraphLaunch(S.g_branch, s)); E.launches += per_branch;
-      } else if ((rc = body(0, s))) { cleanup(); return rc; }
+      } else if ((rc = body(0, s))) return rc;
     } else {
       if (use_graph) { CK(cudaGraphLaunch(S.g_single, s)); E.launches += per_single; }
-      else if ((rc = body(2, s))) { cleanup(); return rc; }
+      else if ((rc = body(2, s))) return rc;
     }
   }
   CK(cudaMemcpyAsync(out, S.xs, n * 4, cudaMemcpyDeviceToDevice, s));
   if (sd.return_pair) CK(cudaMemcpyAsync(out + n, branched ? S.xs + n : S.xs, n * 4, cudaMemcpyDeviceToDevice, s));
+  CK(cudaEventRecord(E.ev_out, s));
+  CK(cudaStreamWaitEvent(cs, E.ev_out, 0));
+  if (E.opt_async) {
+    E.pending = true; E.pend_sd = sd; E.pend_fuse = will_fuse;
+    return 0;
+  }
   unsigned int cnt[4], la_under = 0;
   CK(cudaMemcpyAsync(cnt, S.counters, sizeof cnt, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(&la_under, E.la_flag, sizeof la_under, cudaMemcpyDeviceToHost, s));
-  CK(cudaEventRecord(E.ev_out, s));
-  CK(cudaStreamWaitEvent(cs, E.ev_out, 0));
   CK(cudaStreamSynchronize(s));
-  cleanup();
-  if (la_under) {
-    cudaMemset(E.la_flag, 0, sizeof(unsigned int));
-    return fail(LD_ERR_STATE, "LinearAttention soft-max shift underflowed (%u rows): set option la_exact=1 for the exact-max path", la_under);
+  bool retry = false;
+  if ((rc = finish_checks(E, sd, will_fuse, cnt, la_under, allow_retry ? &retry : nullptr))) return rc;
+  if (retry) {
+    if ((rc = switch_to_exact_linattn(E))) return rc;
+    return ddim_impl(h, sd, cond, mask, noise, out, times, coefs, nsteps, fuse_step, cs, false);
   }
-  if (sd.branch_out && sd.mask_x && (cnt[0] == 0 || cnt[1] == 0)) return fail(LD_ERR_MASK, "mask should be binary");
-  if (will_fuse && !(cnt[2] > 0 && cnt[3] > 0)) return fail(LD_ERR_MASK, "x_out and x_in should be masked");
   return 0;
+}
+
+int ld_sample_ddim(ld_handle* h, const ld_sample_desc* sdp, const float* cond, const float* mask, const float* noise, float* out,
+                   const int32_t* times, const float* coefs, int nsteps, int fuse_step, void* stream) {
+  if (!h || !sdp || !cond || !noise || !out || !times || !coefs) return fail(LD_ERR_INVALID, "null argument");
+  Engine& E = h->E;
+  const ld_sample_desc sd = *sdp;
+  int rc = need_ready(E); if (rc) return rc;
+  if (E.pending) return fail(LD_ERR_STATE, "a deferred call is pending: call ld_sample_finish first");
+  if (nsteps < 1) return fail(LD_ERR_INVALID, "nsteps out of range");
+  if (!E.T) return fail(LD_ERR_STATE, "schedule not set");
+  for (int i = 0; i < nsteps; ++i)   // times index the per-timestep FiLM table and the schedule
+    if (times[i] < 0 || times[i] >= E.T) return fail(LD_ERR_INVALID, "times[%d] = %d is outside [0, %d)", i, times[i], E.T);
+  if (sd.branch_out && !mask) return fail(LD_ERR_INVALID, "branch mode needs a mask");
+  if ((rc = check_shape(E, sd.height, sd.width))) return rc;
+  return ddim_impl(h, sd, cond, mask, noise, out, times, coefs, nsteps, fuse_step, (cudaStream_t)stream, true);
 }
 
 int ld_posterior_step(ld_handle* h, int kind, int t, float* x_out, float* x_in, float* x0_out, float* x0_in, const float* cond,
@@ -1358,14 +1475,16 @@ int ld_posterior_step(ld_handle* h, int kind, int t, float* x_out, float* x_in, 
   Engine& E = h->E;
   if (ld_device_count() == 0) return fail(LD_ERR_NO_DEVICE, "no sm_100 CUDA device is available (there is no CPU fallback)");
   if (!E.T || t < 0 || t >= E.T) return fail(LD_ERR_STATE, "schedule not set or t out of range");
+  if (n <= 0 || n % 4) return fail(LD_ERR_INVALID, "n must be a positive multiple of 4");
   CK(cudaSetDevice(E.device));
   if (kind != 2 && (!mask || !cond || !x_in || !x0_in)) return fail(LD_ERR_INVALID, "branched step needs mask, cond and both branches");
   cudaStream_t s = (cudaStream_t)stream;
+  Scratch sc;
   float *bm = nullptr, *co = nullptr, *ci = nullptr, *oo = nullptr, *oi = nullptr; unsigned int* cnt = nullptr; int* td = nullptr;
-  CK(cudaMalloc(&bm, n * 4)); CK(cudaMalloc(&co, n * 4)); CK(cudaMalloc(&ci, n * 4));
-  CK(cudaMalloc(&oo, n * 4)); CK(cudaMalloc(&oi, n * 4));
-  CK(cudaMalloc(&cnt, 16)); CK(cudaMalloc(&td, 4));
-  CK(cudaMemsetAsync(cnt, 0, 16, s));
+  CK(sc.get(&bm, n * 4)); CK(sc.get(&co, n * 4)); CK(sc.get(&ci, n * 4));
+  CK(sc.get(&oo, n * 4)); CK(sc.get(&oi, n * 4));
+  CK(sc.get(&cnt, 32)); CK(sc.get(&td, 4));
+  CK(cudaMemsetAsync(cnt, 0, 32, s));
   CK(cudaMemcpyAsync(td, &t, 4, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(oo, x0_out, n * 4, cudaMemcpyDeviceToDevice, s));
   if (x0_in) CK(cudaMemcpyAsync(oi, x0_in, n * 4, cudaMemcpyDeviceToDevice, s));
@@ -1378,10 +1497,9 @@ int ld_posterior_step(ld_handle* h, int kind, int t, float* x_out, float* x_in, 
   p.kind = kind; p.o_out = oo; p.o_in = oi; p.x_out = x_out; p.x_in = x_in; p.x0_out = x0_out; p.x0_in = x0_in;
   p.bm = bm; p.cond_out = co; p.z = z; p.t_ptr = td; p.coef1 = E.coef1; p.coef2 = E.coef2; p.sigma = E.sigma;
   p.mask_x = sd->mask_x; p.ood_uses_cond = sd->ood_uses_cond; p.lo = sd->min_val; p.hi = sd->max_val;
-  p.n = n; p.z_stride = 0; p.tloop = t; p.counters = cnt;
+  p.n = n; p.z_stride = 0; p.tloop = t; p.counters = cnt; p.ticket = cnt + 4;
   E.launches += launch_step(p, s);
   CK(cudaStreamSynchronize(s));
-  cudaFree(bm); cudaFree(co); cudaFree(ci); cudaFree(oo); cudaFree(oi); cudaFree(cnt); cudaFree(td);
   return 0;
 }
 
@@ -1648,6 +1766,55 @@ int ld_debug_conv_time(int kernel, int C0, int C1, int N, int H, int W, int up, 
   return rc;
 }
 
+// Time the dominant convolution family (3x3 tcgen05, bf16) in the variants the sampler actually launches (bench.py roofline leg):
+// 0 plain, 1 + GroupNorm statistics of the output, 2 + normalise-on-load prologue (GroupNorm affine + FiLM + SiLU of the source)
+// and statistics, 3 dual: 3x3 + 1x1 res_conv of the same virtual concat [C0 | C1], two outputs, statistics.
+int ld_debug_conv_variant_time(int variant, int C0, int C1, int N, int H, int W, int Cout, int iters, float* ms_out, void* stream) {
+  if (ld_device_count() == 0) return fail(LD_ERR_NO_DEVICE, "no sm_100 CUDA device is available (there is no CPU fallback)");
+  if (variant < 0 || variant > 3 || !ms_out || iters < 1) return fail(LD_ERR_INVALID, "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int Cin = C0 + C1, G = 8;
+  const size_t npx = (size_t)N * H * W;
+  std::vector<float> pk((size_t)9 * Cin * Cout), p1((size_t)Cin * Cout), bias(Cout, 0.1f), ab((size_t)N * 2 * C0);
+  for (size_t i = 0; i < pk.size(); ++i) pk[i] = (float)((int)(i * 2654435761u % 2001) - 1000) * 1e-4f;
+  for (size_t i = 0; i < p1.size(); ++i) p1[i] = (float)((int)(i * 40503u % 2001) - 1000) * 1e-3f;
+  for (int n = 0; n < N; ++n)
+    for (int c = 0; c < C0; ++c) { ab[((size_t)n * 2) * C0 + c] = 1.0f + 0.01f * (float)(c % 7); ab[((size_t)n * 2 + 1) * C0 + c] = 0.05f * (float)(c % 5) - 0.1f; }
+  void *a0 = nullptr, *a1 = nullptr, *ao = nullptr, *ao2 = nullptr; float* abd = nullptr; double* st = nullptr;
+  ConvTcW tw;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(a0); cudaFree(a1); cudaFree(ao); cudaFree(ao2); cudaFree(abd); cudaFree(st);
+    cudaFree(tw.w); cudaFree(tw.w32); cudaFree(tw.bias); cudaFree(tw.bias2);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  };
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(LD_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
+  CKC(cudaMalloc(&a0, npx * C0 * 2)); CKC(cudaMemsetAsync(a0, 0x3c, npx * C0 * 2, s));
+  if (C1) { CKC(cudaMalloc(&a1, npx * C1 * 2)); CKC(cudaMemsetAsync(a1, 0x3c, npx * C1 * 2, s)); }
+  CKC(cudaMalloc(&ao, npx * Cout * 2));
+  if (variant == 3) CKC(cudaMalloc(&ao2, npx * Cout * 2));
+  CKC(cudaMalloc(&st, (size_t)N * G * 2 * sizeof(double))); CKC(cudaMemsetAsync(st, 0, (size_t)N * G * 2 * sizeof(double), s));
+  CKC(cudaMalloc(&abd, ab.size() * 4)); CKC(cudaMemcpyAsync(abd, ab.data(), ab.size() * 4, cudaMemcpyHostToDevice, s));
+  ConvTcArgs ta; ta.src0 = a0; ta.C0 = C0; ta.src1 = a1; ta.C1 = C1; ta.N = N; ta.H = H; ta.W = W; ta.Hin = H; ta.Win = W; ta.dst = ao;
+  if (variant >= 1) { ta.stats = st; ta.stats_G = G; }
+  if (variant == 2) { ta.pro_ab = abd; ta.pro_act = 1; }
+  if (variant == 3) ta.dst2 = ao2;
+  if (conv_tc_pack(pk.data(), bias.data(), Cin, Cout, 3, 1, 1, &tw, variant == 3 ? p1.data() : nullptr, variant == 3 ? bias.data() : nullptr) ||
+      !conv_tc_supports(tw, ta)) { cleanup(); return fail(LD_ERR_INVALID, "conv_tc: unsupported shape for variant %d", variant); }
+  CKC(cudaEventCreate(&e0)); CKC(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; ++i) conv_tc_launch(tw, ta, s);
+  CKC(cudaEventRecord(e0, s));
+  for (int i = 0; i < iters; ++i) conv_tc_launch(tw, ta, s);
+  CKC(cudaEventRecord(e1, s));
+  CKC(cudaEventSynchronize(e1));
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  *ms_out = ms / (float)iters;
+#undef CKC
+  cleanup();
+  return 0;
+}
+
 int64_t ld_launch_count(const ld_handle* h) { return h ? h->E.launches : 0; }
 int64_t ld_workspace_bytes(const ld_handle* h) {
   if (!h) return 0;
@@ -1657,13 +1824,16 @@ int64_t ld_workspace_bytes(const ld_handle* h) {
 }
 int ld_set_option(ld_handle* h, const char* name, int64_t value) {
   if (!h || !name) return fail(LD_ERR_INVALID, "null argument");
-  if (!strcmp(name, "micro_batch")) h->E.opt_micro_batch = value;
-  else if (!strcmp(name, "use_graph")) h->E.opt_use_graph = value;
-  else if (!strcmp(name, "debug_keep")) h->E.opt_debug_keep = value;
-  else if (!strcmp(name, "la_exact")) h->E.opt_la_exact = value;
-  else if (!strcmp(name, "attn_simt")) h->E.opt_attn_simt = value;
-  else if (!strcmp(name, "use_tc")) { if (h->E.finalized) return fail(LD_ERR_STATE, "use_tc must be set before finalize"); h->E.use_tc = value != 0 && h->E.bf; }
+  Engine& E = h->E;
+  if (!strcmp(name, "use_graph")) E.opt_use_graph = value;
+  else if (!strcmp(name, "async")) E.opt_async = value;
+  else if (!strcmp(name, "debug_keep")) E.opt_debug_keep = value;
+  else if (!strcmp(name, "la_exact")) E.opt_la_exact = value;
+  else if (!strcmp(name, "attn_simt")) E.opt_attn_simt = value;
+  else if (!strcmp(name, "use_tc")) { if (E.finalized) return fail(LD_ERR_STATE, "use_tc must be set before finalize"); E.use_tc = value != 0 && E.bf; }
   else return fail(LD_ERR_INVALID, "unknown option '%s'", name);
+  // options are read when a plan is built: drop every cached plan so that the new value takes effect on the next call
+  if (E.finalized && ld_device_count() > 0 && cudaSetDevice(E.device) == cudaSuccess) drop_plans(E);
   return 0;
 }
 

@@ -19,6 +19,8 @@ int launch_conv_cout1(const void* in, const float* w, const float* bias, float* 
 // GroupNorm statistics: sums[n][g] = {sum, sumsq} (double), buffer must be zeroed by the caller
 int launch_gn_stats(const void* x, double* sums, int N, int HW, int C, int G, bool bf, cudaStream_t s);
 int launch_gn_apply(const GnApplyP& p, bool bf, cudaStream_t s);
+// whether launch_gn_apply can fold a 1x1 convolution to one channel into its output pass (GnApplyP::dot_out)
+bool gn_apply_can_dot(int C, bool bf);
 // RMSNorm over C per pixel (ddpm.py:131-132): out = x / max(|x|,1e-12) * g * sqrt(C) (+ res)
 int launch_rmsnorm(const void* x, const float* g, const void* res, void* out, long long P, int C, bool bf,
                    cudaStream_t s);
@@ -77,7 +79,7 @@ struct StepP {
   float* x_out; float* x_in;               // states, updated in place (fusion/single write x_out)
   float* x0_out; float* x0_in;             // optional x0 records (may be null)
   const float* bm; const float* cond_out; const float* z;  // z null when t == 0
-  const int* t_ptr;         // device scalar: current timestep (graph-replay friendly)
+  int* t_ptr;               // device scalar: current timestep (graph-replay friendly); decremented by the kernel when `ticket` is set
   const float* coef1; const float* coef2; const float* sigma;  // [T]
   int mask_x, ood_uses_cond;
   float lo, hi;
@@ -86,6 +88,7 @@ struct StepP {
   int tloop;                // loop length (index of draw for step t is tloop - t, draw 0 is x_T)
   unsigned int* counters;   // [2]=#(x_out*m==0), [3]=#(x_in*(1-m)==0) at the fusion step
   float* x0_trace; long long trace_stride;  // optional [tloop][2][n]
+  unsigned int* ticket;     // optional (zero-initialised, self re-arming): the last block to finish writes *t_ptr = t - 1 (ddpm.py:951)
 };
 int launch_step(const StepP& p, cudaStream_t s);
 
@@ -99,18 +102,17 @@ struct DdimP {
   const float* bm; const float* cond_out;
   const float* z;           // noise tape: draw 0 is x_T, step i uses draw 1 + i (none for the last step)
   long long z_stride;
-  const int* idx_ptr;       // device scalar: current step index (graph-replay friendly)
+  int* idx_ptr;             // device scalar: current step index (graph-replay friendly); advanced by the kernel when `ticket` is set
   int nsteps;
   const float* coefs;       // device [nsteps][5]
   int mask_x, ood_uses_cond;
   float lo, hi;
   long long n;
   unsigned int* counters;   // [2]=#(eps_out*m==0), [3]=#(eps_in*(1-m)==0) at the fusion step
+  unsigned int* ticket;     // optional: the last block to finish advances idx and loads t = times[idx] (ddpm.py:996-998)
+  const int* times; int* t_ptr;   // device [nsteps] schedule of `time` values and the scalar the UNet plans read
 };
 int launch_ddim_step(const DdimP& p, cudaStream_t s);
-// idx += 1; t = times[idx] (when in range)
-int launch_ddim_advance(int* idx_ptr, const int* times, int nsteps, int* t_ptr, cudaStream_t s);
-int launch_dec_t(int* t_ptr, cudaStream_t s);
 
 int launch_nhwc_to_nchw_f32(const void* in, float* out, int N, int HW, int C, bool bf, cudaStream_t s);
 int launch_convert(const void* in, bool in_bf, void* out, bool out_bf, long long n, cudaStream_t s);

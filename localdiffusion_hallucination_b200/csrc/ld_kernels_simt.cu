@@ -338,8 +338,13 @@ __global__ void __launch_bounds__(256) gn_apply_bf16_fast_kernel(GnApplyP p, int
   const uint4* xb = p.xb ? reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.xb) + (size_t)n * p.HW * C) : nullptr;
   uint4* out = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (size_t)n * p.HW * C);
   constexpr int U = 4;
+  const int lpp = C / 8;                         // lanes per pixel
+  float dw[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dw[j] = p.dot_out ? p.dot_w[c0 + j] : 0.f;
   for (long long i0 = v0 + threadIdx.x; i0 < v1; i0 += 256 * U) {
     uint4 va[U], vb[U];
+    float acc_dot[U] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long i = i0 + (long long)u * 256;
@@ -352,6 +357,7 @@ __global__ void __launch_bounds__(256) gn_apply_bf16_fast_kernel(GnApplyP p, int
         const uint32_t wa[4] = {va[u].x, va[u].y, va[u].z, va[u].w};
         const uint32_t wb[4] = {vb[u].x, vb[u].y, vb[u].z, vb[u].w};
         uint32_t o[4];
+        float d = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wa[j]));
@@ -364,14 +370,28 @@ __global__ void __launch_bounds__(256) gn_apply_bf16_fast_kernel(GnApplyP p, int
           }
           __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
           o[j] = *reinterpret_cast<uint32_t*>(&h2);
+          d = fmaf(y0, dw[2 * j], d); d = fmaf(y1, dw[2 * j + 1], d);
         }
-        out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+        if (!p.dot_out) out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+        else acc_dot[u] = d;
+      }
+    }
+    if (p.dot_out) {
+      // the C / 8 threads that hold one pixel are neighbouring lanes (C <= 256): butterfly over them, the first one stores
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float d = acc_dot[u];
+        for (int o = 1; o < lpp; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        const long long i = i0 + (long long)u * 256;
+        if (i < v1 && (threadIdx.x & (lpp - 1)) == 0) p.dot_out[(size_t)n * p.HW + i / lpp] = d + p.dot_b[0];
       }
     }
   }
 }
 
+bool gn_apply_can_dot(int C, bool bf) { return bf && C % 8 == 0 && 2048 % C == 0 && C <= 256; }
 int launch_gn_apply(const GnApplyP& p, bool bf, cudaStream_t s) {
+  if (p.dot_out && !(bf && p.modeB != 2 && p.C % 8 == 0 && 2048 % p.C == 0 && p.C <= 256)) return -1;   // callers check gn_apply_can_dot()
   if (bf && p.modeB != 2 && p.C % 8 == 0 && 2048 % p.C == 0) {
     const long long nvec = (long long)p.HW * p.C / 8;
     int vpb = 256 * 4 * 4;                       // 16 vectors (256 B) per thread
@@ -866,48 +886,79 @@ __device__ __forceinline__ float post(float c1, float c2, float sg, float x0, fl
   const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xt));
   return __fadd_rn(mean, __fmul_rn(sg, z));
 }
+// Every thread owns four consecutive pixels (16-byte loads / stores of each of the fp32 planes; n % 4 == 0).  The loop bookkeeping of
+// p_sample_loop (`t -= 1`, ddpm.py:951) is folded in: every block reads t when it starts and takes a ticket when it is done; the block
+// that draws the last ticket -- by then every block has read t -- writes t - 1 for the next timestep and re-arms the ticket.
+__device__ __forceinline__ float4 ld4(const float* p, long long i) { return *reinterpret_cast<const float4*>(p + i); }
+__device__ __forceinline__ void st4(float* p, long long i, const float (&v)[4]) { *reinterpret_cast<float4*>(p + i) = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ void unpack4(const float4 v, float (&o)[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+__device__ __forceinline__ bool last_block_done(unsigned int* ticket) {
+  __shared__ unsigned int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int k = atomicAdd(ticket, 1u);
+    s_last = (k == gridDim.x - 1) ? 1u : 0u;
+    if (s_last) *ticket = 0u;
+  }
+  __syncthreads();
+  return s_last != 0u;
+}
 __global__ void __launch_bounds__(256) step_kernel(StepP p) {
   const int t = *p.t_ptr;
   const float c1 = p.coef1[t], c2 = p.coef2[t], sg = p.sigma[t];
   const float* z = (t > 0 && p.z) ? p.z + (size_t)(p.tloop - t) * p.z_stride : nullptr;
   float* tr = p.x0_trace ? p.x0_trace + (size_t)(p.tloop - 1 - t) * p.trace_stride : nullptr;
   unsigned int zo = 0, zi = 0;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i < p.n) {
-    const float zz = z ? z[i] : 0.0f;
+    float zz[4] = {0.f, 0.f, 0.f, 0.f}, xo[4], oo[4] = {0.f, 0.f, 0.f, 0.f}, r0[4], r1[4];
+    if (z) unpack4(ld4(z, i), zz);
+    unpack4(ld4(p.x_out, i), xo);
+    if (p.o_out) unpack4(ld4(p.o_out, i), oo);
     if (p.kind == 2) {
-      const float x0 = clampf(p.o_out[i], p.lo, p.hi);
-      p.x_out[i] = post(c1, c2, sg, x0, p.x_out[i], zz);
-      if (p.x0_out) p.x0_out[i] = x0;
-      if (tr) tr[i] = x0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { r0[k] = clampf(oo[k], p.lo, p.hi); xo[k] = post(c1, c2, sg, r0[k], xo[k], zz[k]); }
+      st4(p.x_out, i, xo);
+      if (p.x0_out) st4(p.x0_out, i, r0);
+      if (tr) st4(tr, i, r0);
     } else {
-      const float bm = p.bm[i];
-      float v;
-      if (p.mask_x) {
-        if (p.ood_uses_cond) v = p.cond_out[i];
-        else v = (bm == 0.0f) ? p.lo : __fmul_rn(p.o_out[i], bm);
-      } else {
-        v = p.o_out[i];
+      float bm[4], xi[4], oi[4], co[4] = {0.f, 0.f, 0.f, 0.f};
+      unpack4(ld4(p.bm, i), bm);
+      unpack4(ld4(p.x_in, i), xi);
+      unpack4(ld4(p.o_in, i), oi);
+      if (p.mask_x && p.ood_uses_cond) unpack4(ld4(p.cond_out, i), co);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float v;
+        if (p.mask_x) {
+          if (p.ood_uses_cond) v = co[k];
+          else v = (bm[k] == 0.0f) ? p.lo : __fmul_rn(oo[k], bm[k]);
+        } else {
+          v = oo[k];
+        }
+        const float x0o = clampf(v, p.lo, p.hi);
+        const float x0i = clampf(oi[k], p.lo, p.hi);
+        if (p.kind == 0) {
+          xo[k] = post(c1, c2, sg, x0o, xo[k], zz[k]);
+          xi[k] = post(c1, c2, sg, x0i, xi[k], zz[k]);
+          r0[k] = x0o; r1[k] = x0i;
+        } else {  // fusion step (ddpm.py:779-810)
+          const float im = 1.0f - bm[k];
+          float x0 = __fadd_rn(__fmul_rn(x0i, im), x0o);
+          const float a = __fmul_rn(xo[k], bm[k]), b = __fmul_rn(xi[k], im);
+          zo += a == 0.0f; zi += b == 0.0f;
+          const float xt = (a == 0.0f) ? b : a;
+          x0 = clampf(x0, p.lo, p.hi);
+          xo[k] = post(c1, c2, sg, x0, xt, zz[k]);
+          r0[k] = x0;
+        }
       }
-      const float x0o = clampf(v, p.lo, p.hi);
-      const float x0i = clampf(p.o_in[i], p.lo, p.hi);
-      if (p.kind == 0) {
-        p.x_out[i] = post(c1, c2, sg, x0o, p.x_out[i], zz);
-        p.x_in[i] = post(c1, c2, sg, x0i, p.x_in[i], zz);
-        if (p.x0_out) p.x0_out[i] = x0o;
-        if (p.x0_in) p.x0_in[i] = x0i;
-        if (tr) { tr[i] = x0o; tr[p.n + i] = x0i; }
-      } else {  // fusion step (ddpm.py:779-810)
-        const float im = 1.0f - bm;
-        float x0 = __fadd_rn(__fmul_rn(x0i, im), x0o);
-        const float xo = __fmul_rn(p.x_out[i], bm), xi = __fmul_rn(p.x_in[i], im);
-        zo = xo == 0.0f; zi = xi == 0.0f;
-        const float xt = (xo == 0.0f) ? xi : xo;
-        x0 = clampf(x0, p.lo, p.hi);
-        p.x_out[i] = post(c1, c2, sg, x0, xt, zz);
-        if (p.x0_out) p.x0_out[i] = x0;
-        if (tr) tr[i] = x0;
-      }
+      st4(p.x_out, i, xo);
+      if (p.kind == 0) st4(p.x_in, i, xi);
+      if (p.x0_out) st4(p.x0_out, i, r0);
+      if (p.kind == 0 && p.x0_in) st4(p.x0_in, i, r1);
+      if (tr) { st4(tr, i, r0); if (p.kind == 0) st4(tr + p.n, i, r1); }
     }
   }
   if (p.kind == 1) {
@@ -918,9 +969,10 @@ __global__ void __launch_bounds__(256) step_kernel(StepP p) {
       if (zi) atomicAdd(p.counters + 3, zi);
     }
   }
+  if (p.ticket && last_block_done(p.ticket) && threadIdx.x == 0) *p.t_ptr = t - 1;
 }
 int launch_step(const StepP& p, cudaStream_t s) {
-  step_kernel<<<cdiv(p.n, 256), 256, 0, s>>>(p);
+  step_kernel<<<cdiv(cdiv(p.n, 4), 256), 256, 0, s>>>(p);
   return 1;
 }
 // ---- DDIM (ddpm.py:979-1075): every product and sum is rounded separately, in the reference's evaluation order ----
@@ -939,39 +991,53 @@ __global__ void __launch_bounds__(256) ddim_step_kernel(DdimP p) {
   const float sr = cf[0], srm1 = cf[1], san = cf[2], c = cf[3], sg = cf[4];
   const float* z = (!last && p.z) ? p.z + (size_t)(1 + idx) * p.z_stride : nullptr;
   unsigned int zo = 0, zi = 0;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i < p.n) {
-    const float zz = z ? z[i] : 0.0f;
+    float zz[4] = {0.f, 0.f, 0.f, 0.f}, xo[4], oo[4] = {0.f, 0.f, 0.f, 0.f};
+    if (z) unpack4(ld4(z, i), zz);
+    unpack4(ld4(p.x_out, i), xo);
+    if (p.o_out) unpack4(ld4(p.o_out, i), oo);
     if (p.kind == 2) {
-      const float x0 = clampf(p.o_out[i], p.lo, p.hi);
-      const float xt = p.x_out[i];
-      p.x_out[i] = last ? x0 : ddim_next(san, c, sg, x0, eps_from(sr, srm1, xt, x0), zz);
-    } else {
-      const float bm = p.bm[i];
-      float v;
-      if (p.mask_x) {   // ddpm.py:697-708
-        if (p.ood_uses_cond) v = p.cond_out[i];
-        else v = (bm == 0.0f) ? p.lo : __fmul_rn(p.o_out[i], bm);
-      } else {
-        v = p.o_out[i];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float x0 = clampf(oo[k], p.lo, p.hi);
+        xo[k] = last ? x0 : ddim_next(san, c, sg, x0, eps_from(sr, srm1, xo[k], x0), zz[k]);
       }
-      const float x0o = clampf(v, p.lo, p.hi), x0i = clampf(p.o_in[i], p.lo, p.hi);
-      const float xo = p.x_out[i], xi = p.x_in[i];
-      if (last) {                         // img = [x_start_out, x_start_in]: never fused on the last step
-        p.x_out[i] = x0o; p.x_in[i] = x0i;
-      } else {
-        const float eo = eps_from(sr, srm1, xo, x0o), ei = eps_from(sr, srm1, xi, x0i);
-        if (p.kind == 0) {
-          p.x_out[i] = ddim_next(san, c, sg, x0o, eo, zz);
-          p.x_in[i] = ddim_next(san, c, sg, x0i, ei, zz);
-        } else {                          // fusion: select on x_start_out == 0, composite of the noise predictions
-          const float x0 = clampf(x0o == 0.0f ? x0i : x0o, p.lo, p.hi);
-          const float a = __fmul_rn(eo, bm), b = __fmul_rn(ei, __fsub_rn(1.0f, bm));
-          zo = a == 0.0f; zi = b == 0.0f;
-          const float eps = (a == 0.0f) ? b : a;
-          p.x_out[i] = ddim_next(san, c, sg, x0, eps, zz);
+      st4(p.x_out, i, xo);
+    } else {
+      float bm[4], xi[4], oi[4], co[4] = {0.f, 0.f, 0.f, 0.f};
+      unpack4(ld4(p.bm, i), bm);
+      unpack4(ld4(p.x_in, i), xi);
+      unpack4(ld4(p.o_in, i), oi);
+      if (p.mask_x && p.ood_uses_cond) unpack4(ld4(p.cond_out, i), co);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float v;
+        if (p.mask_x) {   // ddpm.py:697-708
+          if (p.ood_uses_cond) v = co[k];
+          else v = (bm[k] == 0.0f) ? p.lo : __fmul_rn(oo[k], bm[k]);
+        } else {
+          v = oo[k];
+        }
+        const float x0o = clampf(v, p.lo, p.hi), x0i = clampf(oi[k], p.lo, p.hi);
+        if (last) {                         // img = [x_start_out, x_start_in]: never fused on the last step
+          xo[k] = x0o; xi[k] = x0i;
+        } else {
+          const float eo = eps_from(sr, srm1, xo[k], x0o), ei = eps_from(sr, srm1, xi[k], x0i);
+          if (p.kind == 0) {
+            xo[k] = ddim_next(san, c, sg, x0o, eo, zz[k]);
+            xi[k] = ddim_next(san, c, sg, x0i, ei, zz[k]);
+          } else {                          // fusion: select on x_start_out == 0, composite of the noise predictions
+            const float x0 = clampf(x0o == 0.0f ? x0i : x0o, p.lo, p.hi);
+            const float a = __fmul_rn(eo, bm[k]), b = __fmul_rn(ei, __fsub_rn(1.0f, bm[k]));
+            zo += a == 0.0f; zi += b == 0.0f;
+            const float eps = (a == 0.0f) ? b : a;
+            xo[k] = ddim_next(san, c, sg, x0, eps, zz[k]);
+          }
         }
       }
+      st4(p.x_out, i, xo);
+      if (last || p.kind == 0) st4(p.x_in, i, xi);
     }
   }
   if (p.kind == 1) {
@@ -982,26 +1048,16 @@ __global__ void __launch_bounds__(256) ddim_step_kernel(DdimP p) {
       if (zi) atomicAdd(p.counters + 3, zi);
     }
   }
+  // step bookkeeping folded in (see step_kernel): idx += 1; t = times[idx] (ddpm.py:996-998)
+  if (p.ticket && last_block_done(p.ticket) && threadIdx.x == 0) {
+    *p.idx_ptr = idx + 1;
+    if (idx + 1 < p.nsteps) *p.t_ptr = p.times[idx + 1];
+  }
 }
 int launch_ddim_step(const DdimP& p, cudaStream_t s) {
-  ddim_step_kernel<<<cdiv(p.n, 256), 256, 0, s>>>(p);
+  ddim_step_kernel<<<cdiv(cdiv(p.n, 4), 256), 256, 0, s>>>(p);
   return 1;
 }
-__global__ void ddim_advance_kernel(int* idx, const int* times, int nsteps, int* t) {
-  const int i = *idx + 1;
-  *idx = i;
-  if (i < nsteps) *t = times[i];
-}
-int launch_ddim_advance(int* idx_ptr, const int* times, int nsteps, int* t_ptr, cudaStream_t s) {
-  ddim_advance_kernel<<<1, 1, 0, s>>>(idx_ptr, times, nsteps, t_ptr);
-  return 1;
-}
-__global__ void dec_t_kernel(int* t) { *t = *t - 1; }
-int launch_dec_t(int* t_ptr, cudaStream_t s) {
-  dec_t_kernel<<<1, 1, 0, s>>>(t_ptr);
-  return 1;
-}
-
 // =================================================================================================
 // layout helpers
 // =================================================================================================

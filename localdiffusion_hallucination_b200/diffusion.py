@@ -58,7 +58,10 @@ class GaussianDiffusion(nn.Module):
 
     # ---------------------------------------------------------------------------------------
     def _push_schedule(self, h):
-        key = (h.value, self.device)
+        # keyed on the engine GENERATION (a re-created handle may re-use the freed address) and on the buffers' version counters
+        # (a parent load_state_dict / in-place edit of the 13 buffers must reach the device)
+        bufs = (self.posterior_mean_coef1, self.posterior_mean_coef2, self.posterior_log_variance_clipped)
+        key = (self.model._engine_gen, str(self.device), tuple(b._version for b in bufs), tuple(b.data_ptr() for b in bufs))
         if self._schedule_on == key:
             return
         c1 = self.posterior_mean_coef1.detach().cpu().contiguous()

@@ -22,11 +22,14 @@ def shard_rows(t, rank, world, dim=0):
     return t.narrow(dim, lo, hi - lo)
 
 
-def gather_rows(local: torch.Tensor, total: int, group=None) -> torch.Tensor:
-    """All-gather variable-sized row blocks back into `[total, ...]` (identical on every rank)."""
+def gather_rows(local: torch.Tensor, total: int, group=None, dim: int = 0) -> torch.Tensor:
+    """All-gather variable-sized row blocks back into `[total, ...]` along `dim` (identical on every rank).
+    `dim=1` gathers the stacked pair output `[2, b, ...]` of a never-fused branch run (ddpm.py:965-970)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return local
+    if dim != 0:
+        return gather_rows(local.movedim(dim, 0).contiguous(), total, group).movedim(0, dim).contiguous()
     base, extra = divmod(total, world)
     if extra == 0:
         out = torch.empty((total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
@@ -40,13 +43,29 @@ def gather_rows(local: torch.Tensor, total: int, group=None) -> torch.Tensor:
     return torch.cat([p[: shard_bounds(total, r, world)[1] - shard_bounds(total, r, world)[0]] for r, p in enumerate(parts)])
 
 
-def sample_sharded(sample_fn, cond, mask, noise=None, group=None):
-    """Run `sample_fn(cond_rows, mask_rows, noise_rows) -> [rows, ...]` on this rank's rows of the
-    global batch and return the gathered `[B, ...]` result.  `noise` is the *global* tape
-    `[T, B, ...]`, sliced per rank so results do not depend on the world size."""
+def global_noise_tape(shape, steps, device, seed=10):
+    """The reference's draws for the GLOBAL batch (`torch.manual_seed(10)`, x_T, then one draw per step; ddpm.py:934-935, 852),
+    identical on every rank: slicing it per rank makes a sharded run reproduce the single-GPU run row for row."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    tape = torch.empty((steps,) + tuple(shape), device=device)
+    for i in range(steps):
+        tape[i] = torch.randn(shape, device=device, generator=g)
+    return tape
+
+
+def sample_sharded(sample_fn, cond, mask, noise=None, group=None, steps=None, pair=False):
+    """Run `sample_fn(cond_rows, mask_rows, noise_rows) -> [rows, ...]` on this rank's rows of the global batch and return the
+    gathered `[B, ...]` result (`pair=True`: the stacked `[2, B, ...]` output of a never-fused run, gathered along dim 1).
+    `noise` is the *global* tape `[T, B, ...]`, sliced per rank so results do not depend on the world size; when it is None the
+    global tape is drawn here (every rank draws the same `steps` x B tape from seed 10 and keeps its rows) -- letting every rank
+    seed its own local tape would give all shards the same noise rows."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     B = cond.shape[0]
+    if noise is None:
+        if steps is None:
+            raise ValueError("sample_sharded needs the global noise tape or `steps` to draw it")
+        noise = global_noise_tape(tuple(cond.shape), steps, cond.device)
     c, m = shard_rows(cond, rank, world), shard_rows(mask, rank, world)
     z = shard_rows(noise, rank, world, dim=1)
-    return gather_rows(sample_fn(c, m, z), B, group)
+    return gather_rows(sample_fn(c, m, z), B, group, dim=1 if pair else 0)

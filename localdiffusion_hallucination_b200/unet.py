@@ -92,6 +92,11 @@ class Unet(nn.Module):
             node.register_parameter(leaf, p)
         self._handle = None
         self._handle_device = None
+        self._engine_gen = 0        # bumped whenever a native engine is created (consumers re-push per-engine state)
+        self._param_version = None  # sum of the parameters' autograd version counters when the weights were last packed
+        # a parent's load_state_dict (the reference's `diffusion.load_state_dict(data['model'])`, ddpm.py:1517, or EMA copies)
+        # never calls a child's load_state_dict override, but it does run the child's post hooks: invalidate the engine there
+        self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module.release_engine())
 
     # -- reference API -----------------------------------------------------------------------
     @property
@@ -128,11 +133,6 @@ class Unet(nn.Module):
         return out
 
     # -- engine management ----------------------------------------------------------------------
-    def load_state_dict(self, *a, **k):
-        r = super().load_state_dict(*a, **k)
-        self.release_engine()  # weights changed: re-pack on next use
-        return r
-
     def release_engine(self):
         if self._handle is not None:
             _lib.lib().ld_destroy(self._handle)
@@ -161,7 +161,10 @@ class Unet(nn.Module):
         """Create (once) the native handle on the device the parameters live on and push the weights."""
         lib = _lib.lib()
         dev = next(self.parameters()).device
-        if self._handle is not None and self._handle_device == dev:
+        # in-place updates through autograd-visible ops (`p.copy_`, `p.mul_`, optimiser / EMA steps) bump the version counters;
+        # writes through `p.data` do not -- call release_engine() after those
+        pv = sum(p._version for p in self.parameters())
+        if self._handle is not None and self._handle_device == dev and self._param_version == pv:
             return self._handle
         self.release_engine()
         if dev.type != "cuda":
@@ -187,6 +190,8 @@ class Unet(nn.Module):
             lib.ld_destroy(h)
             raise
         self._handle, self._handle_device = h, dev
+        self._param_version = pv
+        self._engine_gen += 1
         return h
 
     def set_engine_options(self, **opts):

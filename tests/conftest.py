@@ -19,6 +19,14 @@ def golden():
     return np.load(os.path.join(ROOT, "tests", "golden", "golden.npz"), allow_pickle=False)
 
 
+@pytest.fixture(scope="session")
+def big():
+    """Live-reference fixtures of the benchmarked configurations (tests/golden/make_golden_big.py)."""
+    import numpy as np
+
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_big.npz"), allow_pickle=False)
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _built_library():
     """The shared library is built in-tree by `__graft_entry__.build()`; build it if it is missing."""

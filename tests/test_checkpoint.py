@@ -48,3 +48,26 @@ def test_strict_mismatch_raises():
         load_reference_checkpoint(gd, ck)
     with pytest.raises(KeyError):
         load_reference_checkpoint(gd, {"step": 1, "model": {}})
+
+
+def test_parent_load_state_dict_invalidates_the_engine():
+    """`diffusion.load_state_dict(...)` (ddpm.py:1517) never calls the child Unet's load_state_dict; the engine must be
+    invalidated from a hook that runs under the parent load, and in-place parameter updates must be noticed too."""
+    gd = _diffusion(0)
+    calls = []
+    gd.model.release_engine = lambda: calls.append(1)
+    gd.load_state_dict(gd.state_dict())
+    assert calls, "the Unet post hook did not run under the parent's load_state_dict"
+    v0 = sum(p._version for p in gd.model.parameters())
+    with torch.no_grad():
+        next(gd.model.parameters()).mul_(1.0)           # EMA / optimiser style in-place update
+    assert sum(p._version for p in gd.model.parameters()) != v0   # what Unet.engine() compares
+
+
+def test_weights_only_loading_is_the_default(tmp_path):
+    src, dst = _diffusion(1), _diffusion(2)
+    ck = _reference_style_ckpt(src)
+    ck["opt"] = {"state": {}, "param_groups": [{"lr": 1e-4}]}
+    path = tmp_path / "model-1.pt"
+    torch.save(ck, path)
+    assert load_reference_checkpoint(dst, str(path)) == 7   # plain containers + tensors load with weights_only=True

@@ -32,7 +32,17 @@ def _worker(rank, world, port, total, q):
         fn = lambda c, m, z: c * 2 + m + z.sum(dim=0)
         got = parallel.sample_sharded(fn, cond, mask, tape)
         want = fn(cond, mask, tape)
-        q.put((rank, bool(torch.equal(got, want)), tuple(got.shape)))
+        ok = bool(torch.equal(got, want))
+        # noise=None: the GLOBAL seed-10 tape is drawn and sliced per rank (every rank seeding its own local tape would hand all
+        # shards the same rows): equals the single-process run on the same global tape
+        got2 = parallel.sample_sharded(fn, cond, mask, None, steps=4)
+        want2 = fn(cond, mask, parallel.global_noise_tape(tuple(cond.shape), 4, cond.device))
+        ok = ok and bool(torch.equal(got2, want2))
+        # stacked pair output [2, B, ...] of a never-fused run (ddpm.py:965-970) is gathered along dim 1
+        fnp = lambda c, m, z: torch.stack((c + z[0], m - z[1]))
+        got3 = parallel.sample_sharded(fnp, cond, mask, tape, pair=True)
+        ok = ok and bool(torch.equal(got3, fnp(cond, mask, tape))) and got3.shape[1] == total
+        q.put((rank, ok, tuple(got.shape)))
     finally:
         dist.destroy_process_group()
 

@@ -21,15 +21,9 @@ def hp_of(name):
 
 def make_model(name, precision="fp32", seed=0, device=None, **opts):
     """Product `Unet` with the seed-0 default initialisation (bit-identical to the reference's)."""
-    from localdiffusion_hallucination_b200 import Unet
+    from localdiffusion_hallucination_b200.workload import make_model as mk
 
-    torch.manual_seed(seed)
-    m = Unet(**cases.MODEL_KW[name], precision=precision)
-    if opts:
-        m.set_engine_options(**opts)
-    if device is not None:
-        m = m.to(device)
-    return m.eval()
+    return mk(name, precision, seed, device, **opts)
 
 
 def cpu_state_dict(m):

@@ -1,7 +1,13 @@
-"""Top warp-stall locations (SASS) of an ncu report captured with --import-source on. usage: ncu_stalls.py report.ncu-rep [top] [ctx_line ...]"""
-import csv, subprocess, sys, collections
+"""Top warp-stall locations (SASS) of an ncu capture taken with --import-source on.
+usage: ncu_stalls.py report.ncu-rep|source.csv[.gz] [top] [ctx_line ...]"""
+import csv, gzip, subprocess, sys, collections
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 16
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".gz"):
+    raw = gzip.open(rep, "rt").read()
+elif rep.endswith(".csv"):
+    raw = open(rep).read()
+else:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines())); h = rows[1]; data = rows[2:]
 si = h.index("Warp Stall Sampling (All Samples)"); src = h.index("Source"); ie = h.index("Instructions Executed")
 tot = sum(int(r[si] or 0) for r in data if len(r) > si)
