@@ -165,6 +165,28 @@ LD_API int ld_posterior_step(ld_handle* h, int kind, int t, float* x_out, float*
                       float* x0_in, const float* cond, const float* mask, const float* z,
                       const ld_sample_desc* sd, int64_t n, void* stream);
 
+/* --- the two stages in front of the sampler: conditional-image producers and anomaly map -> masks -------------
+ * All pointers are device fp32; work is enqueued on `stream`; nothing synchronises. */
+/* `MNIST.__getitem__` (data.py:814-836): raw [N,S,S] in 0..255 -> hr = 2*(x/255) and cond = 2*(up(x[::2 rows])/255), both [N,1,S,S]
+ * (the reference's slice sub-samples the rows only, data.py:822-826; bilinear, align_corners=False). */
+LD_API int ld_prep_mnist(const float* raw, float* hr, float* cond, int N, int S, void* stream);
+/* `MedDataset_png` (data.py:380-414): centre crop of raw [N,Hs,Ws] to crop x crop, (x - mean)/std, + |min| per image when
+ * translate_zero -> out [N,1,crop,crop].  `scratch`: N * 4 bytes of device memory (unused without translate_zero). */
+LD_API int ld_prep_mri(const float* raw, float* out, void* scratch, int N, int Hs, int Ws, int crop, float mean, float std,
+                       int translate_zero, void* stream);
+/* Per-dataset threshold rules of test.py:259-375. */
+typedef enum ld_mask_rule {
+  LD_MASK_MNIST_8TO3 = 0, LD_MASK_MNIST_8TO5 = 1, LD_MASK_MRI_T12FLAIR = 2, LD_MASK_MRI_FLAIR2T1 = 3,
+  LD_MASK_MVTEC_TRANSISTOR = 4, LD_MASK_MVTEC_TOOTHBRUSH = 5, LD_MASK_MVTEC_GRID = 6
+} ld_mask_rule;
+/* test.py:237-381: anomaly map [B,1,h,w] (statistics over the whole batch, as the reference computes them; it runs B = 1) ->
+ * mask_pred [B,1,S,S] (soft, exactly 1.0 where the map reaches the threshold) and binary_mask (may be NULL).  h,w != S: bilinear
+ * resize first (test.py:246-247).  manual_cols > 0: the manual left-columns mask of test.py:379-381 replaces the detector's.
+ * `scratch`: ld_mask_scratch_bytes(B, S) bytes of device memory. */
+LD_API int64_t ld_mask_scratch_bytes(int B, int S);
+LD_API int ld_mask_from_anomaly(const float* amap, int B, int h, int w, int S, int rule, int manual_cols, float* mask_pred,
+                                float* binary_mask, void* scratch, void* stream);
+
 /* --- introspection for bench.py -------------------------------------------------------------- */
 /* Kernel launches enqueued by this handle since creation (our own kernels only). */
 LD_API int64_t ld_launch_count(const ld_handle* h);

@@ -52,6 +52,11 @@ SIGNATURES = {
     "ld_sample_finish": (C.c_int, [C.c_void_p]),
     "ld_posterior_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.POINTER(SampleDesc), C.c_int64, C.c_void_p]),
+    "ld_prep_mnist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "ld_prep_mri": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]),
+    "ld_mask_scratch_bytes": (C.c_int64, [C.c_int, C.c_int]),
+    "ld_mask_from_anomaly": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
     "ld_launch_count": (C.c_int64, [C.c_void_p]),
     "ld_workspace_bytes": (C.c_int64, [C.c_void_p]),
     "ld_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),

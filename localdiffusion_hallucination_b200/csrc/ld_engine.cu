@@ -1815,6 +1815,32 @@ int ld_debug_conv_variant_time(int variant, int C0, int C1, int N, int H, int W,
   return 0;
 }
 
+// ---- stages in front of the sampler (ld_producers.cu) ------------------------------------------------------------------------
+int ld_prep_mnist(const float* raw, float* hr, float* cond, int N, int S, void* stream) {
+  if (!raw || !hr || !cond || N < 1 || S < 2) return fail(LD_ERR_INVALID, "bad argument");
+  if (ld_device_count() == 0) return fail(LD_ERR_NO_DEVICE, "no sm_100 CUDA device is available (there is no CPU fallback)");
+  launch_mnist_cond(raw, hr, cond, N, S, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? 0 : fail(LD_ERR_CUDA, "ld_prep_mnist launch failed");
+}
+int ld_prep_mri(const float* raw, float* out, void* scratch, int N, int Hs, int Ws, int crop, float mean, float std, int translate_zero,
+                void* stream) {
+  if (!raw || !out || N < 1 || crop < 1 || crop > Hs || crop > Ws || !(std != 0.f)) return fail(LD_ERR_INVALID, "bad argument");
+  if (translate_zero && !scratch) return fail(LD_ERR_INVALID, "translate_zero needs N * 4 bytes of scratch");
+  if (ld_device_count() == 0) return fail(LD_ERR_NO_DEVICE, "no sm_100 CUDA device is available (there is no CPU fallback)");
+  launch_mri_norm(raw, out, (unsigned int*)scratch, N, Hs, Ws, crop, mean, std, translate_zero, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? 0 : fail(LD_ERR_CUDA, "ld_prep_mri launch failed");
+}
+int64_t ld_mask_scratch_bytes(int B, int S) { return (int64_t)mask_scratch_bytes(B, S); }
+int ld_mask_from_anomaly(const float* amap, int B, int h, int w, int S, int rule, int manual_cols, float* mask_pred, float* binary_mask,
+                         void* scratch, void* stream) {
+  if (!amap || !mask_pred || !scratch || B < 1 || h < 1 || w < 1 || S < 1 || rule < 0 || rule > LD_MASK_MVTEC_GRID)
+    return fail(LD_ERR_INVALID, "bad argument");
+  if ((long long)B * S * S < 2) return fail(LD_ERR_INVALID, "the standard deviation needs at least two elements");
+  if (ld_device_count() == 0) return fail(LD_ERR_NO_DEVICE, "no sm_100 CUDA device is available (there is no CPU fallback)");
+  launch_mask_from_anomaly(amap, B, h, w, S, rule, manual_cols, mask_pred, binary_mask, scratch, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? 0 : fail(LD_ERR_CUDA, "ld_mask_from_anomaly launch failed");
+}
+
 int64_t ld_launch_count(const ld_handle* h) { return h ? h->E.launches : 0; }
 int64_t ld_workspace_bytes(const ld_handle* h) {
   if (!h) return 0;

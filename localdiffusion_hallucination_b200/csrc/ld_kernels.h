@@ -114,6 +114,14 @@ struct DdimP {
 };
 int launch_ddim_step(const DdimP& p, cudaStream_t s);
 
+// ---- stages in front of the sampler (ld_producers.cu) --------------------------------------------------------------------
+int launch_mnist_cond(const float* raw, float* hr, float* cond, int N, int S, cudaStream_t s);
+int launch_mri_norm(const float* raw, float* out, unsigned int* mins, int N, int Hs, int Ws, int crop, float mean, float stdv, int translate_zero,
+                    cudaStream_t s);
+size_t mask_scratch_bytes(int B, int S);
+int launch_mask_from_anomaly(const float* amap, int B, int h, int w, int S, int rule, int manual_cols, float* mask_pred, float* binary, void* scratch,
+                             cudaStream_t s);
+
 int launch_nhwc_to_nchw_f32(const void* in, float* out, int N, int HW, int C, bool bf, cudaStream_t s);
 int launch_convert(const void* in, bool in_bf, void* out, bool out_bf, long long n, cudaStream_t s);
 int launch_copy_f32(const float* in, float* out, long long n, cudaStream_t s);
