@@ -208,7 +208,8 @@ LD_API int ld_debug_num_taps(ld_handle* h);
 LD_API int ld_debug_tap_info(ld_handle* h, int index, const char** name, int32_t dims[4]);
 LD_API int ld_debug_tap_fetch(ld_handle* h, int index, float* out_nchw, void* stream);
 /* One convolution through one kernel: kernel 0 = CUDA-core fp32, 1 = CUDA-core with bf16 storage,
- * 2 = tcgen05.  x0/x1/res/out: device fp32 NHWC; w_host: host fp32 [Cout, C0+C1, ks, ks]. */
+ * 2 = tcgen05, 3 = tcgen05 with the nearest x2 up-sampling folded into the filter (up == 1, 3x3 only).
+ * x0/x1/res/out: device fp32 NHWC; w_host: host fp32 [Cout, C0+C1, ks, ks]. */
 LD_API int ld_debug_conv(int kernel, const float* x0, int C0, const float* x1, int C1, int N, int Hin,
                          int Win, int up, int H, int W, const float* w_host, const float* bias_host,
                          int Cout, int ks, const float* res, float* out, void* stream);
@@ -228,6 +229,9 @@ LD_API int ld_debug_conv_dual(const float* x0, int C0, const float* x1, int C1, 
  * wqkv [384][C], g [C], wout [C][128], bout [C], g2 [C]: host fp32 in the reference's parameter layout. */
 LD_API int ld_debug_linattn(const float* x, int C, int N, int HW, const float* wqkv, const float* g, const float* wout,
                             const float* bout, const float* g2, float* out, void* stream);
+/* Same with `heads` in {4, 8} (wqkv [3*heads*32][C], wout [C][heads*32]): 8 heads run as two groups of four (C <= 64). */
+LD_API int ld_debug_linattn_h(const float* x, int C, int N, int HW, int heads, const float* wqkv, const float* g, const float* wout,
+                              const float* bout, const float* g2, float* out, void* stream);
 /* Test hook: tcgen05 flash-style soft-max attention (attend.py:98-113).  qkv: fp32 [N][n][3*heads*32] device
  * (channel = part*hid + h*32 + d, ddpm.py:276-277); out: fp32 [N][n][heads*32]. */
 LD_API int ld_debug_attention(const float* qkv, int N, int n, int heads, float* out, void* stream);

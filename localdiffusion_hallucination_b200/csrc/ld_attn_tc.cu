@@ -20,6 +20,7 @@
 #include <stdint.h>
 
 #include "ld_attn_tc.h"
+#include "ld_launch.cuh"
 #include "ld_tc_common.cuh"
 
 namespace ld {
@@ -45,6 +46,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __global__ void __launch_bounds__(128) attn_prep_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ Qp,
                                                         __nv_bfloat16* __restrict__ Kp, __nv_bfloat16* __restrict__ Vt, int n,
                                                         int heads) {
+  pdl_wait();
   const int blk = blockIdx.x, h = blockIdx.y, img = blockIdx.z, nblk = gridDim.x;
   const int hid = heads * 32;
   const int r = threadIdx.x, tok = blk * 128 + r;
@@ -110,6 +112,7 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const AttnParams p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;   // S at columns 0..127, O_blk at 128..159
+  pdl_wait();   // the operand images come from attn_prep_kernel (ld_launch.cuh)
 
   if (warp == kLoadWarp) {
     // ---------------------------------------------------------------- TMA bulk loads -------------
@@ -272,9 +275,9 @@ int attn_tc_launch(const void* qkv, void* out, void* scratch, int N, int n, int 
   __nv_bfloat16* Qp = (__nv_bfloat16*)scratch;
   __nv_bfloat16* Kp = Qp + tiles;
   __nv_bfloat16* Vt = Kp + tiles;
-  attn_prep_kernel<<<dim3(nblk, heads, N), 128, 0, s>>>((const __nv_bfloat16*)qkv, Qp, Kp, Vt, n, heads);
+  launch_k(attn_prep_kernel, dim3(nblk, heads, N), dim3(128), 0, s, true, (const __nv_bfloat16*)qkv, Qp, Kp, Vt, n, heads);
   AttnParams p{Qp, Kp, Vt, (__nv_bfloat16*)out, n, heads, nblk};
-  attn_tc_kernel<<<dim3(nblk, heads, N), kThreads, kSmem, s>>>(p);
+  launch_k(attn_tc_kernel, dim3(nblk, heads, N), dim3(kThreads), kSmem, s, true, p);
   return 2;
 }
 

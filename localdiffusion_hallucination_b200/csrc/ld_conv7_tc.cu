@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "ld_conv7_tc.h"
+#include "ld_launch.cuh"
 #include "ld_tc_common.cuh"
 
 namespace ld {
@@ -60,6 +61,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv7_tc_kernel(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) pdl_trigger();   // persistent grid: the next kernel's CTAs may be scheduled (ld_launch.cuh)
+  pdl_wait();                            // x is written by the previous timestep's update kernel
   const int tpi = p.tiles_x * p.tiles_y;
 
   if (warp < 4) {
@@ -239,8 +242,8 @@ int conv7_tc_launch(const Conv7TcW& w, const float* x, void* out, int N, int H, 
   p.ntiles = N * p.tiles_x * p.tiles_y;
   int grid = 2 * g_sms;
   if (grid > p.ntiles) grid = p.ntiles;
-  if (w.Cout == 32) conv7_tc_kernel<32><<<grid, kThreads, smem_bytes<32>(), s>>>(p);
-  else conv7_tc_kernel<64><<<grid, kThreads, smem_bytes<64>(), s>>>(p);
+  if (w.Cout == 32) launch_k(conv7_tc_kernel<32>, dim3(grid), dim3(kThreads), smem_bytes<32>(), s, true, p);
+  else launch_k(conv7_tc_kernel<64>, dim3(grid), dim3(kThreads), smem_bytes<64>(), s, true, p);
   return 1;
 }
 

@@ -40,6 +40,7 @@
 #include <vector>
 
 #include "ld_conv_tc.h"
+#include "ld_launch.cuh"
 #include "ld_tc_common.cuh"
 
 namespace ld {
@@ -96,6 +97,7 @@ struct alignas(64) KParams {
   int mt, nacc;                      // mt = 2: every streamed weight stage serves TWO consecutive tiles of the CTA (two accumulators);
                                      // nacc = accumulator stages (2, or 1 when two NT-wide accumulators already fill TMEM)
   int ds, ds_cs;                     // 2x2 stride-2 (pixel-unshuffle) conv run as a 1x1 over four strided TMA gathers; ds_cs = source channels
+  int ps;                            // > 0: pixel-shuffle output of the folded nearest-x2 + 3x3 convolution (ConvTcArgs::ps = real Cout)
   int a_stage, lbo16;                // activation stage pitch (bytes) and chunk stride (16-byte units)
   int off_a, off_b, off_coef;        // shared memory carve-up (bytes)
   // normalise-on-load prologue (GroupNorm affine [+ FiLM] + activation of the source tensor)
@@ -264,6 +266,11 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int n_tile = blockIdx.y;
+  // PDL (ld_launch.cuh): the grid is persistent (every CTA resident), so the next kernel's CTAs may be scheduled from now on; every
+  // role that touches tensors of earlier kernels (activations, residual, GroupNorm coefficients / statistics) waits for them here --
+  // the weight warp does not: weights and bias are constants, its loads overlap the previous kernel's tail
+  if (threadIdx.x == 0) pdl_trigger();
+  if (warp != kWWarp) pdl_wait();
 
   if (warp < R::kProdWarps) {
     if (LEAN || p.tma_in) {
@@ -500,11 +507,13 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
         stat_img = img;
       }
       long long opix = -1;
+      int ogy = 0, ogx = 0;
       if (MX) {
         const int gy = tw.ty * G::TH + (m >> 4), gx = tw.tx * G::TW + (m & 15);
         if ((m & 15) < G::TW && gy < p.H && gx < p.W) opix = ((long long)img * p.H + gy) * p.W + gx;
       } else if (tile2d) {
         const int gy = tw.ty * 16 + (m >> 3), gx = tw.tx * 8 + (m & 7);
+        ogy = gy; ogx = gx;
         if (gy < p.H && gx < p.W) opix = ((long long)img * p.H + gy) * p.W + gx;
       } else {
         const long long gp = (long long)tw.tile * 128 + m;
@@ -592,7 +601,11 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
               *reinterpret_cast<uint4*>(orow + (((c0 + 1) ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
           } else if (opix >= 0 && !(p.dbg & 4)) {
-            const size_t o = (size_t)opix * p.Cout + nbase + j0;
+            size_t o = (size_t)opix * p.Cout + nbase + j0;
+            if (p.ps) {   // virtual channel (py, px, c) of low-resolution pixel (gy, gx) -> channel c of output pixel (2 gy + py, 2 gx + px)
+              const int cidx = nbase + j0, q = cidx / p.ps, c = cidx - q * p.ps;
+              o = ((((size_t)img * (2 * p.H) + 2 * ogy + (q >> 1)) * (2 * p.W)) + 2 * ogx + (q & 1)) * p.ps + c;
+            }
             *reinterpret_cast<uint4*>(p.dst + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(p.dst + o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
@@ -978,10 +991,10 @@ int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
     p.step_ty = r / p.tiles_x; p.step_tx = r - p.step_ty * p.tiles_x;
   }
   if constexpr (NT >= 128) {
-    if (lean && p.mt == 2) { conv_tc_kernel<NT, KS, KC, true, 2><<<dim3((unsigned)gx, (unsigned)ntiles_y), Roles<true>::kThreads, smem, s>>>(p); return 1; }
+    if (lean && p.mt == 2) { launch_k(conv_tc_kernel<NT, KS, KC, true, 2>, dim3((unsigned)gx, (unsigned)ntiles_y), Roles<true>::kThreads, smem, s, true, p); return 1; }
   }
-  if (lean) conv_tc_kernel<NT, KS, KC, true><<<dim3((unsigned)gx, (unsigned)ntiles_y), Roles<true>::kThreads, smem, s>>>(p);
-  else conv_tc_kernel<NT, KS, KC, false><<<dim3((unsigned)gx, (unsigned)ntiles_y), Roles<false>::kThreads, smem, s>>>(p);
+  if (lean) launch_k(conv_tc_kernel<NT, KS, KC, true>, dim3((unsigned)gx, (unsigned)ntiles_y), Roles<true>::kThreads, smem, s, true, p);
+  else launch_k(conv_tc_kernel<NT, KS, KC, false>, dim3((unsigned)gx, (unsigned)ntiles_y), Roles<false>::kThreads, smem, s, true, p);
   return 1;
 }
 
@@ -1003,6 +1016,8 @@ namespace {
 __global__ void gn_coef_kernel(const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ film, int film_stride, int G, int C, double cnt, float eps, float* __restrict__ ab) {
   const int n = blockIdx.x;
+  if (threadIdx.x == 0) pdl_trigger();   // N small blocks, all resident: let the consuming convolution set itself up (ld_launch.cuh)
+  pdl_wait();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / (C / G);
     const double su = stats[((size_t)n * G + g) * 2], sq = stats[((size_t)n * G + g) * 2 + 1];
@@ -1023,7 +1038,7 @@ __global__ void gn_coef_kernel(const double* __restrict__ stats, const float* __
 
 int gn_coef_launch(const double* stats, const float* gamma, const float* beta, const float* film, int film_stride, int G, int C, int N,
                    long long HW, float eps, float* ab, cudaStream_t s) {
-  gn_coef_kernel<<<N, C < 256 ? C : 256, 0, s>>>(stats, gamma, beta, film, film_stride, G, C, (double)HW * (C / G), eps, ab);
+  launch_k(gn_coef_kernel, dim3(N), dim3(C < 256 ? C : 256), 0, s, true, stats, gamma, beta, film, film_stride, G, C, (double)HW * (C / G), eps, ab);
   return 1;
 }
 
@@ -1098,11 +1113,33 @@ int conv_tc_pack(const float* w, const float* bias, int Cin, int Cout, int ks, i
   return 0;
 }
 
+int conv_tc_pack_up2(const float* w, const float* bias, int Cin, int Cout, ConvTcW* out) {
+  out->ready = false;
+  if (Cout % 16 || Cin % 32 || !pick_ntile(4 * Cout) || pick_ntile(4 * Cout) < 128) return 0;
+  // which low-resolution offset d in {-1, 0, +1} (index d + 1) a filter tap k in {0, 1, 2} lands on, per output parity
+  static const int off[2][3] = {{0, 1, 1}, {1, 1, 2}};
+  const int Co4 = 4 * Cout;
+  std::vector<float> wv((size_t)9 * Cin * Co4, 0.f), bv;
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px)
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          const int tap = off[py][ky] * 3 + off[px][kx], q = py * 2 + px;
+          for (int c = 0; c < Cin; ++c)
+            for (int o = 0; o < Cout; ++o)
+              wv[((size_t)tap * Cin + c) * Co4 + q * Cout + o] += w[((size_t)(ky * 3 + kx) * Cin + c) * Cout + o];
+        }
+  if (bias) { bv.resize(Co4); for (int i = 0; i < Co4; ++i) bv[i] = bias[i % Cout]; }
+  return conv_tc_pack(wv.data(), bias ? bv.data() : nullptr, Cin, Co4, 3, 1, 1, out);
+}
+
 bool conv_tc_supports(const ConvTcW& w, const ConvTcArgs& a) {
   if (!w.ready) return false;
   if (a.ds) return w.ks == 1 && w.Cin == 4 * a.C0 && a.C0 % 32 == 0 && !a.src1 && !a.up && !a.pro_ab && !a.stats && !a.res &&
                   a.Hin == 2 * a.H && a.Win == 2 * a.W && encode_fn() != nullptr;
   if (a.C0 + a.C1 != w.Cin || a.C0 % 32 || a.C1 % 32) return false;
+  if (a.ps) return w.ks == 3 && !w.dual && w.Cout == 4 * a.ps && a.ps % 16 == 0 && w.ntile >= 128 && !a.src1 && !a.up && !a.res && !a.stats && !a.pro_ab &&
+                   !a.dst2 && a.Hin == a.H && a.Win == a.W;
   if (w.dual != (a.dst2 != nullptr)) return false;
   if (w.dual && (w.ks != 3 || w.ntile > 64 || w.Cout != w.ntile || a.up || a.res)) return false;   // 4 NT TMEM columns, two CTAs per SM
   if (a.up && (w.ks != 3 || a.src1)) return false;
@@ -1121,11 +1158,14 @@ long long* conv_tc_trace() { return nullptr; }
 // Kernel parameters (incl. the three encoded tensor maps) are cached per distinct (weights, arguments): plans replay
 // the same launches every timestep and cuTensorMapEncodeTiled is a host-side driver call.
 static bool build_params(const ConvTcW& w, const ConvTcArgs& a, KParams& p) {
-  const bool k64 = w.w && a.C0 % 64 == 0 && a.C1 % 64 == 0;
+  bool k64 = w.w && a.C0 % 64 == 0 && a.C1 % 64 == 0;
+  // folded up-sampling convolution with a filter of <= 150 KB: 32-channel chunks halve the activation stages, which lets the whole
+  // filter stay resident in shared memory instead of being streamed for every tile
+  if (a.ps && w.w32 && (size_t)9 * w.Cin * w.Cout * 2 <= 150 * 1024) k64 = false;
   const int kc = k64 ? 64 : 32;
   const bool mx = kUseMX && w.ks == 3 && w.ntile == 32;   // merged-x geometry (see Geo): 8 x 14 output tiles
   p = KParams{};
-  p.ds = a.ds; p.ds_cs = a.C0;
+  p.ds = a.ds; p.ds_cs = a.C0; p.ps = a.ps;
   p.src0 = (const __nv_bfloat16*)a.src0; p.src1 = (const __nv_bfloat16*)a.src1; p.C0 = a.C0; p.C1 = a.C1;
   p.N = a.N; p.H = a.H; p.W = a.W; p.Hin = a.Hin; p.Win = a.Win; p.up = a.up;
   p.nchunks = w.Cin / kc;
@@ -1157,7 +1197,7 @@ static bool build_params(const ConvTcW& w, const ConvTcArgs& a, KParams& p) {
     if (a.pro_ab && noxf) p.tma_in = 0;
     p.xf = (a.pro_ab && p.tma_in) ? 1 : 0;
   }
-  p.tma_out = map_out(&p.map_out, a.dst, a.N, a.H, a.W, w.Cout, w.ntile, a.ds ? 3 : w.ks, mx) ? 1 : 0;
+  p.tma_out = (!a.ps && map_out(&p.map_out, a.dst, a.N, a.H, a.W, w.Cout, w.ntile, a.ds ? 3 : w.ks, mx)) ? 1 : 0;
   if (mx) {
     p.tiles_x = (a.W + 13) / 14; p.tiles_y = (a.H + 7) / 8;
     p.ntiles = a.N * p.tiles_x * p.tiles_y;
@@ -1195,7 +1235,7 @@ ParamKey make_key(const ConvTcW& w, const ConvTcArgs& a) {
   k.v[i++] = ((uint64_t)(uint32_t)a.N << 32) | (uint32_t)a.H;
   k.v[i++] = ((uint64_t)(uint32_t)a.W << 32) | (uint32_t)a.Hin;
   k.v[i++] = ((uint64_t)(uint32_t)a.Win << 32) | (uint32_t)((a.up & 1) | ((a.ds & 1) << 1) | ((a.pro_act & 3) << 2));
-  k.v[i++] = (uint64_t)(uint32_t)a.stats_G;
+  k.v[i++] = ((uint64_t)(uint32_t)a.ps << 32) | (uint32_t)a.stats_G;
   k.v[i++] = (uint64_t)(uintptr_t)w.w; k.v[i++] = (uint64_t)(uintptr_t)w.w32; k.v[i++] = (uint64_t)(uintptr_t)w.bias;
   k.v[i++] = (uint64_t)(uintptr_t)w.bias2;
   k.v[i++] = ((uint64_t)(uint32_t)w.Cin << 32) | (uint32_t)w.Cout;

@@ -26,6 +26,9 @@ struct ConvTcArgs {
   int Hin = 0, Win = 0;        // stored source extent
   int up = 0;                  // read src0 through a nearest x2 up-sampling
   int ds = 0;                  // pixel-unshuffle down-sampling (ddpm.py:122): weights packed as a 1x1 over (p1, p2, c); Hin = 2H
+  int ps = 0;                  // nearest x2 up-sampling + 3x3 (ddpm.py:114-118) run as ONE 3x3 convolution over the LOW-resolution source
+                               // with 4 * ps "virtual" output channels (output parity (py, px), channel c), see conv_tc_pack_up2: N, H, W are
+                               // the low-resolution extent, dst is [N, 2H, 2W, ps] and the epilogue scatters (pixel shuffle); ps = real Cout
   void* dst = nullptr;         // bf16 [N,H,W,Cout]
   const void* res = nullptr;   // optional bf16 residual added in the epilogue
   void* dst2 = nullptr;        // dual weights only: bf16 [N,H,W,Cout] output of the fused 1x1 convolution
@@ -41,6 +44,11 @@ struct ConvTcArgs {
 // `w_1x1` ([Cin][Cout]) / `bias_1x1`: optional 1x1 convolution of the same input fused as a second output (3x3 only)
 int conv_tc_pack(const float* w_tap_cin_cout, const float* bias, int Cin, int Cout, int ks, int stride, int pad, ConvTcW* out,
                  const float* w_1x1 = nullptr, const float* bias_1x1 = nullptr);
+// nearest x2 up-sampling followed by a 3x3 convolution == four 2x2 convolutions of the low-resolution image, one per output parity:
+// output (2i+py, 2j+px) only sees low-resolution rows {i-1, i} (py = 0) or {i, i+1} (py = 1), with the taps that fall on the same
+// source pixel pre-summed.  Packed as a 3x3 convolution with 4 * Cout output channels ordered (py, px, c); 2.25x fewer MACs and
+// tensor-core tiles with N = 4 * Cout instead of Cout.  `w` is fp32 [9 taps][Cin][Cout] like conv_tc_pack.
+int conv_tc_pack_up2(const float* w_tap_cin_cout, const float* bias, int Cin, int Cout, ConvTcW* out);
 bool conv_tc_supports(const ConvTcW& w, const ConvTcArgs& a);
 // GroupNorm statistics {sum, sumsq}[N][G][2] (+ optional per-image FiLM [2C] scale, shift) -> coefficient table [N][2][C]
 int gn_coef_launch(const double* stats, const float* gamma, const float* beta, const float* film, int film_stride, int G, int C, int N,

@@ -59,6 +59,7 @@ struct ConvW {
   float* w = nullptr;     // fp32 [taps][Cin][Cout]  (CUDA-core path, c1 and cout1 kernels)
   float* bias = nullptr;  // fp32 [Cout] or null
   ConvTcW tc;             // bf16 tcgen05 packing (empty in fp32 mode)
+  ConvTcW tc_up2;         // nearest-x2 + 3x3 folded into one low-resolution convolution with pixel-shuffle output (conv_tc_pack_up2)
 };
 
 struct ResW { ConvW c1, c2, res; ConvTcW c1_dual; bool has_res = false, has_film = false; int film_off = 0; float *g1, *b1, *g2, *b2; int Cin, Cout; };
@@ -346,7 +347,7 @@ static int pack_attn(Engine& E, const std::string& p, int C, bool full) {
   else {
     if ((rc = pack_conv(E, p + ".to_out.0", true, false, &a.out))) return rc;
     if ((rc = vecp(E, p + ".to_out.1.g", &a.g2))) return rc;
-    if (E.use_tc && E.d.attn_heads == 4 && E.d.attn_dim_head == 32 &&
+    if (E.use_tc && (E.d.attn_heads == 4 || E.d.attn_heads == 8) && E.d.attn_dim_head == 32 &&
         linattn_tc_pack(W(E, p + ".to_qkv.weight").host.data(), W(E, p + ".norm.g").host.data(), W(E, p + ".to_out.0.weight").host.data(),
                         W(E, p + ".to_out.0.bias").host.data(), W(E, p + ".to_out.1.g").host.data(), C, E.d.attn_heads, &a.la))
       return fail(LD_ERR_CUDA, "linattn_tc_pack(%s) failed", p.c_str());
@@ -418,6 +419,15 @@ static int finalize(Engine& E) {
     ConvW cw;
     if (i < L - 1) rc = pack_conv(E, p + ".3.1", true, false, &cw); else rc = pack_conv(E, p + ".3", true, false, &cw);
     if (rc) return rc;
+    if (i < L - 1 && E.use_tc && cw.tc.ready) {   // Upsample (ddpm.py:114-118): fold the nearest x2 into the filter
+      const WSpec& w = W(E, p + ".3.1.weight");
+      const int co = (int)w.shape[0], ci = (int)w.shape[1];
+      std::vector<float> pk((size_t)9 * ci * co);
+      for (int o = 0; o < co; ++o)
+        for (int c = 0; c < ci; ++c)
+          for (int t = 0; t < 9; ++t) pk[((size_t)t * ci + c) * co + o] = w.host[((size_t)o * ci + c) * 9 + t];
+      if (conv_tc_pack_up2(pk.data(), W(E, p + ".3.1.bias").host.data(), ci, co, &cw.tc_up2)) return fail(LD_ERR_CUDA, "conv_tc_pack_up2(%s) failed", p.c_str());
+    }
     E.samp[p + ".3"] = cw;
   }
   if ((rc = pack_res(E, "final_res_block", true, fw, fb))) return rc;
@@ -482,6 +492,20 @@ struct Builder {
     bool own_a = false;
     ConvTcArgs ta;
     bool use_tc = false;
+    static int no_up2 = -1;   // env LD_CONV_NO_UP2=1: keep the replicate-on-load up-sampling path (A/B aid)
+    if (no_up2 < 0) { const char* e = getenv("LD_CONV_NO_UP2"); no_up2 = e ? atoi(e) : 0; }
+    if (E.use_tc && up && !b && !resid && !pro && !stats_off && cw.tc_up2.ready && !no_up2) {
+      ConvTcArgs tu;
+      tu.src0 = a.p; tu.C0 = a.C; tu.N = a.N; tu.H = a.H; tu.W = a.W; tu.Hin = a.H; tu.Win = a.W; tu.ps = cw.Cout;
+      if (outH == 2 * a.H && outW == 2 * a.W && conv_tc_supports(cw.tc_up2, tu)) {
+        Ten o = act(a.N, outH, outW, cw.Cout);
+        if (err) return o;
+        tu.dst = o.p;
+        const ConvTcW* w = &cw.tc_up2;
+        op([tu, w](cudaStream_t s) { return conv_tc_launch(*w, tu, s); });
+        return o;
+      }
+    }
     if (E.use_tc && cw.tc.ready) {
       ta.src0 = a.p; ta.C0 = a.C; ta.src1 = b ? b->p : nullptr; ta.C1 = b ? b->C : 0;
       ta.N = a.N; ta.H = outH; ta.W = outW; ta.Hin = a.H; ta.Win = a.W; ta.up = up ? 1 : 0;
@@ -631,10 +655,10 @@ struct Builder {
     if (!a.full && a.la.ready && !E.opt_la_exact) {
       // fused tcgen05 LinearAttention: x is read twice, the result written once (ld_linattn_tc.cu)
       Ten out = act_t(x);
-      Ten mn = alloc(x.N, 1, 1, 128 * x.C, 2);
+      Ten mn = alloc(x.N, 1, 1, hid * x.C, 2);
       LinAttnTcArgs la;
       la.x = x.p; la.out = out.p; la.N = x.N; la.HW = x.H * x.W; la.Mn = mn.p; la.flag = E.la_flag;
-      const size_t ctx_off = (size_t)zalloc((size_t)x.N * 128 * x.C * 4), ks_off = (size_t)zalloc((size_t)x.N * 128 * 4);
+      const size_t ctx_off = (size_t)zalloc((size_t)x.N * hid * x.C * 4), ks_off = (size_t)zalloc((size_t)x.N * hid * 4);
       const LinAttnTcW* w = &a.la;
       Plan* pp = &P;
       op([pp, la, w, ctx_off, ks_off](cudaStream_t s) {
@@ -1548,7 +1572,15 @@ int ld_debug_conv(int kernel, const float* x0, int C0, const float* x1, int C1, 
   if (res) { CK(cudaMalloc(&ar, nout * Cout * esz)); launch_convert(res, false, ar, bf, (long long)nout * Cout, s); }
   CK(cudaMalloc(&ao, nout * Cout * esz));
   int rc = 0;
-  if (kernel == 2) {
+  if (kernel == 3) {   // nearest x2 + 3x3 folded into one low-resolution convolution with pixel-shuffle output
+    ConvTcW tw;
+    ConvTcArgs ta; ta.src0 = a0; ta.C0 = C0; ta.N = N; ta.H = Hin; ta.W = Win; ta.Hin = Hin; ta.Win = Win; ta.ps = Cout; ta.dst = ao;
+    if (!up || ks != 3 || x1 || res || H != 2 * Hin || W != 2 * Win) rc = fail(LD_ERR_INVALID, "kernel 3 is the up-sampling 3x3 convolution");
+    else if (conv_tc_pack_up2(pk.data(), bias_host, Cin, Cout, &tw) || !tw.ready) rc = fail(LD_ERR_INVALID, "conv_tc_pack_up2: unsupported shape");
+    else if (conv_tc_launch(tw, ta, s) < 0) rc = fail(LD_ERR_INVALID, "conv_tc_launch: unsupported arguments");
+    cudaStreamSynchronize(s);
+    cudaFree(tw.w); cudaFree(tw.w32); cudaFree(tw.bias);
+  } else if (kernel == 2) {
     ConvTcW tw;
     if (conv_tc_pack(pk.data(), bias_host, Cin, Cout, ks, 1, ks / 2, &tw) || !tw.ready) rc = fail(LD_ERR_INVALID, "conv_tc_pack: unsupported shape");
     else {
@@ -1648,15 +1680,19 @@ int ld_debug_conv_dual(const float* x0, int C0, const float* x1, int C1, int N, 
 // Fused tcgen05 LinearAttention block, attn(x) + x (test hook).  x/out: fp32 NHWC device; weights: host, torch layout.
 int ld_debug_linattn(const float* x, int C, int N, int HW, const float* wqkv, const float* g, const float* wout, const float* bout,
                      const float* g2, float* out, void* stream) {
+  return ld_debug_linattn_h(x, C, N, HW, 4, wqkv, g, wout, bout, g2, out, stream);
+}
+int ld_debug_linattn_h(const float* x, int C, int N, int HW, int heads, const float* wqkv, const float* g, const float* wout, const float* bout,
+                       const float* g2, float* out, void* stream) {
   if (ld_device_count() == 0) return fail(LD_ERR_NO_DEVICE, "no sm_100 CUDA device is available (there is no CPU fallback)");
   cudaStream_t s = (cudaStream_t)stream;
   LinAttnTcW w;
-  if (linattn_tc_pack(wqkv, g, wout, bout, g2, C, 4, &w) || !w.ready) return fail(LD_ERR_INVALID, "linattn_tc_pack: unsupported shape");
-  const size_t n = (size_t)N * HW * C;
+  if (linattn_tc_pack(wqkv, g, wout, bout, g2, C, heads, &w) || !w.ready) return fail(LD_ERR_INVALID, "linattn_tc_pack: unsupported shape");
+  const size_t n = (size_t)N * HW * C, hid = (size_t)heads * 32;
   void *xb = nullptr, *ob = nullptr, *mn = nullptr; float *ctx = nullptr, *ks = nullptr; unsigned int* flag = nullptr;
-  CK(cudaMalloc(&xb, n * 2)); CK(cudaMalloc(&ob, n * 2)); CK(cudaMalloc(&mn, (size_t)N * 128 * C * 2));
-  CK(cudaMalloc(&ctx, (size_t)N * 128 * C * 4)); CK(cudaMalloc(&ks, (size_t)N * 128 * 4)); CK(cudaMalloc(&flag, 4));
-  CK(cudaMemsetAsync(ctx, 0, (size_t)N * 128 * C * 4, s)); CK(cudaMemsetAsync(ks, 0, (size_t)N * 128 * 4, s)); CK(cudaMemsetAsync(flag, 0, 4, s));
+  CK(cudaMalloc(&xb, n * 2)); CK(cudaMalloc(&ob, n * 2)); CK(cudaMalloc(&mn, (size_t)N * hid * C * 2));
+  CK(cudaMalloc(&ctx, (size_t)N * hid * C * 4)); CK(cudaMalloc(&ks, (size_t)N * hid * 4)); CK(cudaMalloc(&flag, 4));
+  CK(cudaMemsetAsync(ctx, 0, (size_t)N * hid * C * 4, s)); CK(cudaMemsetAsync(ks, 0, (size_t)N * hid * 4, s)); CK(cudaMemsetAsync(flag, 0, 4, s));
   launch_convert(x, false, xb, true, (long long)n, s);
   LinAttnTcArgs a; a.x = xb; a.out = ob; a.N = N; a.HW = HW; a.Z = ctx; a.ksum = ks; a.Mn = mn; a.flag = flag;
   int rc = linattn_tc_launch(w, a, s) < 0 ? fail(LD_ERR_INVALID, "linattn_tc_launch failed") : 0;
@@ -1734,14 +1770,18 @@ int ld_debug_conv_time(int kernel, int C0, int C1, int N, int H, int W, int up, 
   p.ks = ks; p.stride = 1; p.pad = ks / 2; p.up = up; p.w = dw; p.bias = db; p.Cout = Cout; p.dst = ao; p.res = nullptr;
   p.M = (long long)nout;
   int rc = 0;
+  if (kernel == 3) {
+    ta = ConvTcArgs(); ta.src0 = a0; ta.C0 = C0; ta.N = N; ta.H = Hin; ta.W = Win; ta.Hin = Hin; ta.Win = Win; ta.ps = Cout; ta.dst = ao;
+    if (!up || C1 || conv_tc_pack_up2(pk.data(), bias.data(), Cin, Cout, &tw) || !conv_tc_supports(tw, ta)) rc = fail(LD_ERR_INVALID, "conv_tc up2: unsupported shape");
+  } else
   if (kernel == 2 && (conv_tc_pack(pk.data(), bias.data(), Cin, Cout, ks, 1, ks / 2, &tw) || !conv_tc_supports(tw, ta)))
     rc = fail(LD_ERR_INVALID, "conv_tc: unsupported shape");
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   if (!rc) {
-    for (int i = 0; i < 3; ++i) { if (kernel == 2) conv_tc_launch(tw, ta, s); else launch_conv_simt(p, bf, s); }
+    for (int i = 0; i < 3; ++i) { if (kernel >= 2) conv_tc_launch(tw, ta, s); else launch_conv_simt(p, bf, s); }
     cudaEventRecord(e0, s);
-    for (int i = 0; i < iters; ++i) { if (kernel == 2) conv_tc_launch(tw, ta, s); else launch_conv_simt(p, bf, s); }
+    for (int i = 0; i < iters; ++i) { if (kernel >= 2) conv_tc_launch(tw, ta, s); else launch_conv_simt(p, bf, s); }
     cudaEventRecord(e1, s);
     cudaError_t e = cudaEventSynchronize(e1);
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);

@@ -2,6 +2,7 @@
 // them; the bf16 path uses everything here except the generic convolution, which is replaced by
 // the tcgen05 implicit GEMM in ld_conv_tc.cu.  All tensors are NHWC, storage type T.
 #include "ld_kernels.h"
+#include "ld_launch.cuh"
 
 namespace ld {
 
@@ -313,6 +314,7 @@ __global__ void __launch_bounds__(256) gn_apply_bf16_fast_kernel(GnApplyP p, int
   const int n = blockIdx.y, C = p.C;
   float* aA = sh; float* bA = sh + C;
   const double cntA = (double)p.HW * (C / p.GA);
+  pdl_wait();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / (C / p.GA);
     const double su = p.statsA[((size_t)n * p.GA + g) * 2], sq = p.statsA[((size_t)n * p.GA + g) * 2 + 1];
@@ -397,7 +399,7 @@ int launch_gn_apply(const GnApplyP& p, bool bf, cudaStream_t s) {
     int vpb = 256 * 4 * 4;                       // 16 vectors (256 B) per thread
     if (nvec < vpb) vpb = (int)(((nvec + 255) / 256) * 256);
     dim3 grid(cdiv(nvec, vpb), p.N);
-    gn_apply_bf16_fast_kernel<<<grid, 256, 2 * (size_t)p.C * sizeof(float), s>>>(p, vpb);
+    launch_k(gn_apply_bf16_fast_kernel, grid, dim3(256), 2 * (size_t)p.C * sizeof(float), s, true, p, vpb);
     return 1;
   }
   int ppb = 2048 * 32 / p.C;
@@ -416,6 +418,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const T* __restrict__ x, const float* __restrict__ g,
                                                       const T* __restrict__ res, T* __restrict__ out, long long P, int C,
                                                       int L) {
+  pdl_wait();
   const int cv = C >> 2;            // vec4 per pixel
   const int per = cv / L;           // vec4 per lane (1, 2 or 4)
   const int lane = threadIdx.x % L;
@@ -454,7 +457,7 @@ int launch_rmsnorm(const void* x, const float* g, const void* res, void* out, lo
   while (L * 2 <= 32 && cv % (L * 2) == 0) L *= 2;
   while (cv / L > 4 && L < 32) L *= 2;
   const long long threads = P * L;
-  if (bf) rmsnorm_kernel<bf16><<<cdiv(threads, 256), 256, 0, s>>>((const bf16*)x, g, (const bf16*)res, (bf16*)out, P, C, L);
+  if (bf) launch_k(rmsnorm_kernel<bf16>, dim3(cdiv(threads, 256)), dim3(256), 0, s, true, (const bf16*)x, g, (const bf16*)res, (bf16*)out, P, C, L);
   else rmsnorm_kernel<float><<<cdiv(threads, 256), 256, 0, s>>>((const float*)x, g, (const float*)res, (float*)out, P, C, L);
   return 1;
 }
@@ -841,6 +844,8 @@ int launch_time_film(const TimeP& p, cudaStream_t s) {
 }
 
 __global__ void film_gather_kernel(const float* __restrict__ table, int total, const int* __restrict__ t_scalar, float* __restrict__ film) {
+  if (threadIdx.x == 0) pdl_trigger();   // first kernel of a timestep (launched without the PDL attribute): lets the init conv set itself up
+  pdl_wait();
   const float4* src = reinterpret_cast<const float4*>(table + (size_t)(*t_scalar) * total);
   float4* dst = reinterpret_cast<float4*>(film);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total / 4; i += gridDim.x * blockDim.x) dst[i] = src[i];
@@ -905,6 +910,7 @@ __device__ __forceinline__ bool last_block_done(unsigned int* ticket) {
   return s_last != 0u;
 }
 __global__ void __launch_bounds__(256) step_kernel(StepP p) {
+  pdl_wait();
   const int t = *p.t_ptr;
   const float c1 = p.coef1[t], c2 = p.coef2[t], sg = p.sigma[t];
   const float* z = (t > 0 && p.z) ? p.z + (size_t)(p.tloop - t) * p.z_stride : nullptr;
@@ -972,7 +978,7 @@ __global__ void __launch_bounds__(256) step_kernel(StepP p) {
   if (p.ticket && last_block_done(p.ticket) && threadIdx.x == 0) *p.t_ptr = t - 1;
 }
 int launch_step(const StepP& p, cudaStream_t s) {
-  step_kernel<<<cdiv(cdiv(p.n, 4), 256), 256, 0, s>>>(p);
+  launch_k(step_kernel, dim3(cdiv(cdiv(p.n, 4), 256)), dim3(256), 0, s, true, p);
   return 1;
 }
 // ---- DDIM (ddpm.py:979-1075): every product and sum is rounded separately, in the reference's evaluation order ----
@@ -985,6 +991,7 @@ __device__ __forceinline__ float ddim_next(float san, float c, float sg, float x
   return __fadd_rn(__fadd_rn(__fmul_rn(x0, san), __fmul_rn(c, eps)), __fmul_rn(sg, z));
 }
 __global__ void __launch_bounds__(256) ddim_step_kernel(DdimP p) {
+  pdl_wait();
   const int idx = *p.idx_ptr;
   const bool last = idx >= p.nsteps - 1;   // time_next < 0 (ddpm.py:1009-1012, 1053-1056)
   const float* cf = p.coefs + (size_t)idx * 5;
@@ -1055,7 +1062,7 @@ __global__ void __launch_bounds__(256) ddim_step_kernel(DdimP p) {
   }
 }
 int launch_ddim_step(const DdimP& p, cudaStream_t s) {
-  ddim_step_kernel<<<cdiv(cdiv(p.n, 4), 256), 256, 0, s>>>(p);
+  launch_k(ddim_step_kernel, dim3(cdiv(cdiv(p.n, 4), 256)), dim3(256), 0, s, true, p);
   return 1;
 }
 // =================================================================================================

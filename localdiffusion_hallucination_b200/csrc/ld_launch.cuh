@@ -1,0 +1,40 @@
+// Programmatic dependent launch (PDL) between the ~100 kernels of a timestep.
+//
+// Every kernel of the per-timestep sequence is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may be
+// scheduled while the previous kernel is still draining, run their set-up (mbarrier init, TMEM allocation, tensor-map prefetch,
+// loads of CONSTANT data such as weights) and then block in `griddepcontrol.wait` until the previous grid has completed and its
+// memory is visible.  Persistent kernels (all CTAs resident) release their dependents early with `griddepcontrol.launch_dependents`;
+// for multi-wave kernels the release is implicit when the last block exits.  Inside stream capture the attribute becomes a
+// programmatic edge of the CUDA graph.  `griddepcontrol.wait` is a no-op for a kernel launched without the attribute, so every
+// kernel carries it unconditionally; env LD_PDL=0 switches the attribute off (A/B aid).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdlib.h>
+
+#include <utility>
+
+namespace ld {
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LD_PDL"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+
+// kernel<<<grid, block, smem, s>>>(args...) with the PDL attribute (pdl == true and LD_PDL != 0)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+}  // namespace ld

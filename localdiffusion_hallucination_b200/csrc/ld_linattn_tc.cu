@@ -1,4 +1,5 @@
-// LinearAttention (ddpm.py:214-251) fused into two tcgen05 kernels for sm_100a (heads = 4, dim_head = 32).
+// LinearAttention (ddpm.py:214-251) fused into two tcgen05 kernels for sm_100a (dim_head = 32; heads = 4, or 8 as two head groups of
+// four: pass A runs once per group, pass B walks (tile, group) pairs and accumulates both groups into one output accumulator).
 //
 // The reference materialises qkv = to_qkv(RMSNorm(x)) ([384, H*W] per image, 768 B per pixel in bf16), two
 // soft-maxes and two einsums.  Here x is read twice and the result written once; qkv never leaves the SM:
@@ -27,6 +28,7 @@
 
 #include <vector>
 
+#include "ld_launch.cuh"
 #include "ld_linattn_tc.h"
 #include "ld_tc_common.cuh"
 
@@ -48,16 +50,17 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 struct CtxParams {
   const __nv_bfloat16* x;   // [N][HW][C]
-  const __nv_bfloat16* wk;  // packed [C/8][128][8]
-  const float* kb2;         // [128] log2(e) * bound of |k_d|
-  float* Z;                 // [N][128 (h,d)][C]
-  float* ksum;              // [N][128]
+  const __nv_bfloat16* wk;  // packed [HG][C/8 + 2][128][8]
+  const float* kb2;         // [HG * 128] log2(e) * bound of |k_d|
+  float* Z;                 // [N][HG * 128 (h,d)][C]
+  float* ksum;              // [N][HG * 128]
   int HW, slices;
+  int hgs;                  // head groups (blockIdx.z)
 };
 struct OutParams {
   const __nv_bfloat16* x;   // [N][HW][C]
-  const __nv_bfloat16* wq;  // packed [C/8][128][8]
-  const __nv_bfloat16* Mn;  // [N] packed [16][C][8]
+  const __nv_bfloat16* wq;  // packed [HG][C/8][128][8]
+  const __nv_bfloat16* Mn;  // [N] packed [HG * 16][C][8]
   const float* bout; const float* g2;
   __nv_bfloat16* out;
   int HW, slices;
@@ -267,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, CtxCfg<C>::CTAS) la_ctx_kernel(const
                  d1_empty = d1_full + 32, p_full = d1_empty + 32, p_empty = p_full + 32, z_full = p_empty + 32,
                  raw_full = z_full + 8, raw_empty = raw_full + 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.y;
+  const int n = blockIdx.y, hg = blockIdx.z;
   const int HT = (p.HW + 63) / 64;
   const int h0 = (int)((long long)HT * blockIdx.x / p.slices), h1 = (int)((long long)HT * (blockIdx.x + 1) / p.slices);
   const int nh = h1 - h0;
@@ -288,6 +291,8 @@ __global__ void __launch_bounds__(kThreads, CtxCfg<C>::CTAS) la_ctx_kernel(const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) pdl_trigger();   // one resident wave: the next kernel's CTAs may be scheduled (ld_launch.cuh)
+  pdl_wait();                            // x comes from the previous kernel
   // TMEM columns: K^T buffer b at b*64 (64 pixels each);  Z at ZCOL .. ZCOL+C, its column C = sum of P over pixels (ksum)
   if (nh <= 0) {
     if (warp == kMmaWarp) tmem_dealloc(tmem_base, K::TMEM_COLS);
@@ -308,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, CtxCfg<C>::CTAS) la_ctx_kernel(const
     // half tiles ahead of MMA2, so a transform warp-group always finds its next K^T tile ready.
     if (lane == 0) {
       mbar_arrive_expect_tx(w_full, K::W_BYTES);
-      bulk_g2s(smem_u32(w_s), p.wk, K::W_BYTES, w_full);
+      bulk_g2s(smem_u32(w_s), reinterpret_cast<const uint8_t*>(p.wk) + (size_t)hg * K::W_BYTES, K::W_BYTES, w_full);
     }
     __syncwarp();
     mbar_wait(w_full, 0);
@@ -396,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, CtxCfg<C>::CTAS) la_ctx_kernel(const
     if (g == 0) {
       mbar_wait(z_full, 0);
       tc_fence_after();
-      float* dst = p.Z + ((size_t)n * 128 + r) * C;
+      float* dst = p.Z + (((size_t)n * p.hgs + hg) * 128 + r) * C;
 #pragma unroll 1
       for (int c0 = 0; c0 < C; c0 += 32) {
         uint32_t zr[32];
@@ -408,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, CtxCfg<C>::CTAS) la_ctx_kernel(const
       uint32_t ks[16];
       tmem_ld16(lane_base + (uint32_t)(K::ZCOL + C), ks);
       tmem_ld_wait();
-      atomicAdd(p.ksum + (size_t)n * 128 + r, __uint_as_float(ks[0]));
+      atomicAdd(p.ksum + ((size_t)n * p.hgs + hg) * 128 + r, __uint_as_float(ks[0]));
     }
   }
   tc_fence_before();
@@ -425,16 +430,18 @@ __global__ void __launch_bounds__(256) la_fold_kernel(const float* __restrict__ 
                                                       const float* __restrict__ Ut, __nv_bfloat16* __restrict__ Mn, int C,
                                                       unsigned int* __restrict__ flag) {
   extern __shared__ float zs[];      // [32 d][C]: Z[(h,d)][c] * 32^-0.5 / ksum[(h,d)]
-  const int h = blockIdx.x, n = blockIdx.y;
+  const int h = blockIdx.x, n = blockIdx.y, hid = (int)gridDim.x * 32;
+  if (threadIdx.x == 0) pdl_trigger();
+  pdl_wait();
   for (int i = threadIdx.x; i < 32 * C; i += 256) {
     const int d = i / C;
-    const float ks = ksum[(size_t)n * 128 + h * 32 + d];
+    const float ks = ksum[(size_t)n * hid + h * 32 + d];
     if (i % C == 0 && !(ks > 1e-30f) && flag) atomicAdd(flag, 1u);
-    zs[i] = Z[((size_t)n * 128 + h * 32) * C + i] * 0.17677669529663687f / ks;
+    zs[i] = Z[((size_t)n * hid + h * 32) * C + i] * 0.17677669529663687f / ks;
   }
   __syncthreads();
   const float* u = Ut + (size_t)h * C * C;
-  __nv_bfloat16* dst = Mn + (size_t)n * 128 * C;
+  __nv_bfloat16* dst = Mn + (size_t)n * hid * C;
   // thread -> (c', group of 8 d): consecutive threads take consecutive c' (coalesced rows of Ut)
   for (int i = threadIdx.x; i < 4 * C; i += 256) {
     const int cp = i % C, dg = i / C;
@@ -457,23 +464,28 @@ __global__ void __launch_bounds__(256) la_fold_kernel(const float* __restrict__ 
 // ================================================================================================
 // pass B: output
 // ================================================================================================
-template <int C>
+template <int C, int HG>
 struct OutCfg {
   static constexpr int XS = C >= 64 ? 2 : 3;
   static constexpr int X_STAGE = 128 * C * 2;
-  static constexpr int WQ_BYTES = 128 * C * 2;
-  static constexpr int MN_BYTES = 128 * C * 2;
+  static constexpr int WQ_BYTES = HG * 128 * C * 2;   // W'_q of every head group
+  static constexpr int MN_BYTES = HG * 128 * C * 2;   // Mn of every head group
   static constexpr int P_BYTES = 128 * 128 * 2;
-  static constexpr int NP = C >= 128 ? 2 : 4;         // P buffers: two per transform warp-group (one when smem is full)
+  static constexpr int NP = (C >= 128 || (C >= 64 && HG > 1)) ? 2 : 4;   // P buffers: two per transform warp-group (one when smem is full)
   static constexpr int RS = C >= 128 ? 0 : (C >= 64 ? 2 : 3);   // raw x ring fed by cp.async.bulk
   static constexpr int MN2 = C <= 32 ? MN_BYTES : 0;   // second Mn buffer (flat tile lists cross one image boundary); no room at C >= 64
   static constexpr int SMEM_MIN = WQ_BYTES + MN_BYTES + MN2 + XS * X_STAGE + NP * P_BYTES + RS * X_STAGE + 2 * C * 4 + 32 * 8 + 16;
   static constexpr int SMEM = SMEM_MIN > 117 * 1024 ? SMEM_MIN : 117 * 1024;   // one CTA per SM: it owns all 512 TMEM columns
 };
 
-template <int C>
+// HG head groups of four heads: the tile list is walked as VIRTUAL tiles j = tile * HG + hg.  Virtual tile j belongs to transform
+// warp-group j & 1 (its Q buffer, its P buffers) exactly like a tile does for HG = 1; the second MMA of every virtual tile of a tile
+// accumulates into the SAME output accumulator (O buffer = tile & 1), which is complete after the last head group; the epilogue of
+// tile t is run by warp-group t & 1.
+template <int C, int HG>
 __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) {
-  using K = OutCfg<C>;
+  using K = OutCfg<C, HG>;
+  constexpr int LHG = HG == 2 ? 1 : 0;
   constexpr int PPG = K::NP / 2;                      // P buffers per warp-group
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* wq_s = smem;
@@ -520,6 +532,8 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) pdl_trigger();   // one resident wave (ld_launch.cuh)
+  pdl_wait();                            // Mn comes from la_fold_kernel, x from the kernel before pass A
   // TMEM columns: Q of warp-group g at g*128;  O of warp-group g at 256 + g*C
   if (nt <= 0) {
     if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
@@ -542,9 +556,9 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
     if (lane == 0) {
       mbar_arrive_expect_tx(w_full, K::WQ_BYTES + K::MN_BYTES + K::MN2);
       bulk_g2s(smem_u32(wq_s), p.wq, K::WQ_BYTES, w_full);
-      bulk_g2s(smem_u32(mn_s), p.Mn + (size_t)n * 128 * C, K::MN_BYTES, w_full);
+      bulk_g2s(smem_u32(mn_s), p.Mn + (size_t)n * HG * 128 * C, K::MN_BYTES, w_full);
       const int n2 = (p.flat && n + 1 < p.N) ? n + 1 : n;
-      if (K::MN2) bulk_g2s(smem_u32(mn_s + K::MN_BYTES), p.Mn + (size_t)n2 * 128 * C, K::MN_BYTES, w_full);
+      if (K::MN2) bulk_g2s(smem_u32(mn_s + K::MN_BYTES), p.Mn + (size_t)n2 * HG * 128 * C, K::MN_BYTES, w_full);
     }
     __syncwarp();
     mbar_wait(w_full, 0);
@@ -554,46 +568,49 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
     const uint32_t wq_lo = desc_lo(smem_u32(wq_s), 2048), mn_lo = desc_lo(smem_u32(mn_s), C * 16), x_lo0 = desc_lo(smem_u32(x_s), 2048),
                    p_lo0 = desc_lo(smem_u32(p_s), 2048);
     auto mma2 = [&](int j) {
-      const int g = j & 1, u = j >> 1, pi = pidx(j);
+      const int t = j >> LHG, hg = j & (HG - 1), ob = t & 1, pi = pidx(j);
       mbar_wait(p_full + 8 * pi, ppar(j));
-      mbar_wait(d2_empty + 8 * g, (u & 1) ^ 1);
+      if (hg == 0) mbar_wait(d2_empty + 8 * ob, ((t >> 1) & 1) ^ 1);   // the epilogue of tile t - 2 has read this accumulator
       tc_fence_after();
       if (elect_one()) {
         const uint32_t p_lo = p_lo0 + (uint32_t)(pi * (K::P_BYTES >> 4));
+        const uint32_t mn_t = mn_lo + (uint32_t)((K::MN2 && t0 + t >= NTL) ? (K::MN_BYTES >> 4) : 0) + (uint32_t)(hg * 16 * C);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)   // K = 128 (h,d) = 8 x 16
-          umma_bf16_lh(tmem_base + 256u + (uint32_t)(g * C), p_lo + (uint32_t)(2 * k * 128), hi128,
-                       mn_lo + (uint32_t)((K::MN2 && t0 + j >= NTL) ? (K::MN_BYTES >> 4) : 0) + (uint32_t)(2 * k * C), hi128,
-                       idesc2, k > 0 ? 1u : 0u);
+        for (int k = 0; k < 8; ++k)   // K = 128 (h,d) of this head group = 8 x 16
+          umma_bf16_lh(tmem_base + 256u + (uint32_t)(ob * C), p_lo + (uint32_t)(2 * k * 128), hi128, mn_t + (uint32_t)(2 * k * C), hi128,
+                       idesc2, (hg > 0 || k > 0) ? 1u : 0u);
         umma_commit(p_empty + 8 * pi);
-        umma_commit(d2_full + 8 * g);
+        if (hg == HG - 1) umma_commit(d2_full + 8 * ob);
       }
       __syncwarp();
     };
-    auto mma1 = [&](int i) {
-      const int s = i % K::XS, g = i & 1, u = i >> 1;
-      mbar_wait(x_full + 8 * s, (i / K::XS) & 1);
+    auto mma1 = [&](int j) {
+      const int t = j >> LHG, hg = j & (HG - 1);
+      const int s = t % K::XS, g = j & 1, u = j >> 1;
+      mbar_wait(x_full + 8 * s, (t / K::XS) & 1);
       mbar_wait(d1_empty + 8 * g, (u & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t x_lo = x_lo0 + (uint32_t)(s * (K::X_STAGE >> 4));
+        const uint32_t wq_g = wq_lo + (uint32_t)(hg * (128 * C * 2 >> 4));
 #pragma unroll
         for (int k = 0; k < C / 16; ++k)
-          umma_bf16_lh(tmem_base + (uint32_t)(g * 128), x_lo + (uint32_t)(2 * k * 128), hi128, wq_lo + (uint32_t)(2 * k * 128), hi128, idesc1,
+          umma_bf16_lh(tmem_base + (uint32_t)(g * 128), x_lo + (uint32_t)(2 * k * 128), hi128, wq_g + (uint32_t)(2 * k * 128), hi128, idesc1,
                        k > 0 ? 1u : 0u);
-        umma_commit(x_empty + 8 * s);
+        if (hg == HG - 1) umma_commit(x_empty + 8 * s);   // the stage is read by every head group of the tile
         umma_commit(d1_full + 8 * g);
       }
       __syncwarp();
     };
-    // Q of tile i+1 before the second MMA of tile i-1: its group frees the Q buffer three quarters into the soft-max of tile i-1
-    // and delivers P(i-1) only at the end -- this order has Q(i+1) waiting when the group comes back
+    // Q of virtual tile j+1 before the second MMA of j-1: its group frees the Q buffer three quarters into the soft-max of j-1
+    // and delivers P(j-1) only at the end -- this order has Q(j+1) waiting when the group comes back
+    const int nv = nt * HG;
     mma1(0);
-    for (int i = 0; i < nt; ++i) {
-      if (i + 1 < nt) mma1(i + 1);
-      if (i >= 1) mma2(i - 1);
+    for (int j = 0; j < nv; ++j) {
+      if (j + 1 < nv) mma1(j + 1);
+      if (j >= 1) mma2(j - 1);
     }
-    mma2(nt - 1);
+    mma2(nv - 1);
   } else {
     // ---------------------------------------------------------------- transform + epilogue -------
     // Warp-group g owns tiles g, g+2, ...  Order: T(i), T(i+2), E(i), T(i+4), E(i+2), ... so that the epilogue of a
@@ -649,7 +666,7 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full + 8 * pi);
     };
-    auto epilogue = [&](int i) {
+    auto epilogue = [&](int i) {   // i = tile; run by warp-group i & 1 == g
       const int u = i >> 1;
       const int px = (t0 + i) * 128 + m;
       const __nv_bfloat16* xr = ximg + (size_t)px * C;
@@ -729,14 +746,21 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
         }
       }
     };
+    // virtual tiles j = g, g + 2, ...: tile t = j / HG; this group runs the epilogue of the tiles with t & 1 == g
+    const int nv = nt * HG;
     if constexpr (PPG == 2) {
-      if (g < nt) transform(g);
-      for (int i = g; i < nt; i += 2) {
-        if (i + 2 < nt) transform(i + 2);
-        epilogue(i);
+      if (g < nv) transform(g);
+      for (int j = g; j < nv; j += 2) {
+        if (j + 2 < nv) transform(j + 2);
+        const int t = j >> LHG;
+        if (HG == 1 || (t & 1) == g) epilogue(t);
       }
     } else {
-      for (int i = g; i < nt; i += 2) { transform(i); epilogue(i); }
+      for (int j = g; j < nv; j += 2) {
+        transform(j);
+        const int t = j >> LHG;
+        if (HG == 1 || (t & 1) == g) epilogue(t);
+      }
     }
   }
   tc_fence_before();
@@ -750,32 +774,33 @@ int sms() {
   return g_sms;
 }
 
-template <int C>
+template <int C, int HG>
 int configure_c() {
   if (cudaFuncSetAttribute(la_ctx_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, CtxCfg<C>::SMEM) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(la_out_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, OutCfg<C>::SMEM) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(la_out_kernel<C, HG>, cudaFuncAttributeMaxDynamicSharedMemorySize, OutCfg<C, HG>::SMEM) != cudaSuccess) return -1;
   return 0;
 }
 
-template <int C>
+template <int C, int HG>
 int launch_c(const LinAttnTcW& w, const LinAttnTcArgs& a, cudaStream_t s) {
   // slices per image: ONE wave of CTAs (each owns all 512 TMEM columns of its SM), at least 4 half tiles per CTA
   const int HT = (a.HW + 63) / 64, NTL = (a.HW + 127) / 128;
   int sl = sms() / a.N; if (sl < 1) sl = 1;
-  int slA = CtxCfg<C>::CTAS * sms() / a.N; if (slA > HT / 4) slA = HT / 4; if (slA < 1) slA = 1;
+  int slA = CtxCfg<C>::CTAS * sms() / (a.N * HG); if (slA > HT / 4) slA = HT / 4; if (slA < 1) slA = 1;
   int slB = sl; if (slB > NTL / 2) slB = NTL / 2; if (slB < 1) slB = 1;
   // pass B: when tiles never straddle images, all SMs share one flat tile list (a CTA crosses at most one image boundary)
   static int flat_env = -1; if (flat_env < 0) { const char* e = getenv("LD_LA_FLAT"); flat_env = e ? atoi(e) : 1; }   // LD_LA_FLAT=0: per-image slices (A/B aid)
   const long long Tb = (long long)a.N * NTL;
   int ctasB = sms(); if (ctasB > Tb / 2) ctasB = (int)(Tb / 2);
-  const bool flatB = flat_env && OutCfg<C>::MN2 > 0 && a.HW % 128 == 0 && ctasB >= 1 && Tb / ctasB + 1 <= NTL;
-  CtxParams cp{(const __nv_bfloat16*)a.x, (const __nv_bfloat16*)w.wk, w.kb2, a.Z, a.ksum, a.HW, slA};
+  const bool flatB = flat_env && OutCfg<C, HG>::MN2 > 0 && a.HW % 128 == 0 && ctasB >= 1 && Tb / ctasB + 1 <= NTL;
+  CtxParams cp{(const __nv_bfloat16*)a.x, (const __nv_bfloat16*)w.wk, w.kb2, a.Z, a.ksum, a.HW, slA, HG};
   static int only = -1; if (only < 0) { const char* e = getenv("LD_LA_ONLY"); only = e ? atoi(e) : 0; }   // debug: 1 = pass A only, 2 = pass B only
-  if (only != 2) la_ctx_kernel<C><<<dim3(slA, a.N), kThreads, CtxCfg<C>::SMEM, s>>>(cp);
-  la_fold_kernel<<<dim3(4, a.N), 256, 32 * C * sizeof(float), s>>>(a.Z, a.ksum, w.Ut, (__nv_bfloat16*)a.Mn, C, a.flag);
+  if (only != 2) launch_k(la_ctx_kernel<C>, dim3(slA, a.N, HG), dim3(kThreads), CtxCfg<C>::SMEM, s, true, cp);
+  launch_k(la_fold_kernel, dim3(4 * HG, a.N), dim3(256), 32 * C * sizeof(float), s, true, (const float*)a.Z, (const float*)a.ksum, (const float*)w.Ut,
+           (__nv_bfloat16*)a.Mn, C, a.flag);
   OutParams op{(const __nv_bfloat16*)a.x, (const __nv_bfloat16*)w.wq, (const __nv_bfloat16*)a.Mn, w.bout, w.g2,
                (__nv_bfloat16*)a.out, a.HW, slB, w.q_use_max, flatB ? 1 : 0, a.N};
-  if (only != 1) la_out_kernel<C><<<flatB ? dim3(ctasB, 1) : dim3(slB, a.N), kThreads, OutCfg<C>::SMEM, s>>>(op);
+  if (only != 1) launch_k(la_out_kernel<C, HG>, flatB ? dim3(ctasB, 1) : dim3(slB, a.N), dim3(kThreads), OutCfg<C, HG>::SMEM, s, true, op);
   return 3;
 }
 
@@ -784,62 +809,69 @@ int launch_c(const LinAttnTcW& w, const LinAttnTcArgs& a, cudaStream_t s) {
 int linattn_tc_pack(const float* wqkv, const float* g, const float* wout, const float* bout, const float* g2, int C, int heads,
                     LinAttnTcW* out) {
   out->ready = false;
-  if (heads != 4 || !(C == 32 || C == 64 || C == 128)) return 0;
-  out->C = C;
+  // heads = 4, or 8 = two head groups (C <= 64: pass B keeps W'_q and Mn of both groups in shared memory)
+  if (!((heads == 4 && (C == 32 || C == 64 || C == 128)) || (heads == 8 && (C == 32 || C == 64)))) return 0;
+  out->C = C; out->heads = heads;
+  const int HG = heads / 4, hid = heads * 32;
   const float sq = sqrtf((float)C);
-  // fold RMSNorm's g * sqrt(C) (ddpm.py:131-132) into the 1x1 to_qkv weights (ddpm.py:227); rows: q 0..127, k 128..255, v 256..383
-  auto pack_rows = [&](int row0, int nblocks, std::vector<__nv_bfloat16>& dst, float extra = 1.0f) {
-    dst.resize((size_t)nblocks * 128 * C);
-    for (int b = 0; b < nblocks; ++b)
+  // fold RMSNorm's g * sqrt(C) (ddpm.py:131-132) into the 1x1 to_qkv weights (ddpm.py:227); rows: q 0..hid-1, k hid..2hid-1, v 2hid..3hid-1
+  // a block = the 128 rows of one head group, packed [chunks][128][8] with `chunks` >= C/8 (extra chunks zero)
+  auto pack_rows = [&](int row0, int chunks, std::vector<__nv_bfloat16>& dst, float extra) {
+    dst.assign((size_t)HG * chunks * 128 * 8, __float2bfloat16_rn(0.f));
+    for (int b = 0; b < HG; ++b)
       for (int c8 = 0; c8 < C / 8; ++c8)
         for (int r = 0; r < 128; ++r)
           for (int e = 0; e < 8; ++e) {
             const int c = c8 * 8 + e;
-            dst[(((size_t)b * (C / 8) + c8) * 128 + r) * 8 + e] = __float2bfloat16_rn(wqkv[(size_t)(row0 + b * 128 + r) * C + c] * g[c] * sq * extra);
+            dst[(((size_t)b * chunks + c8) * 128 + r) * 8 + e] = __float2bfloat16_rn(wqkv[(size_t)(row0 + b * 128 + r) * C + c] * g[c] * sq * extra);
           }
   };
   std::vector<__nv_bfloat16> q, k;
-  pack_rows(0, 1, q, 1.4426950408889634f);   // q rows carry log2(e): the soft-max over d uses ex2 directly
-  pack_rows(128, 1, k, 1.4426950408889634f);  // k rows carry log2(e) as well
+  const int KCH = C / 8 + 2;
+  pack_rows(0, C / 8, q, 1.4426950408889634f);   // q rows carry log2(e): the soft-max over d uses ex2 directly
+  pack_rows(hid, KCH, k, 1.4426950408889634f);   // k rows carry log2(e) as well
   // Soft-max over the pixel axis is shift invariant: row d is shifted by the analytic bound |k'_d| <= |W'_k[d,:]| * |xhat|
   // (|xhat| <= 1 + 2^-8).  The (bf16) negative bound sits in the weight of the ones channel the producers append to xhat
   // (two extra 8-channel chunks: [C/8] = {-bound, 0 x 7}, [C/8 + 1] = 0), so MMA1 delivers k' - bound directly.
-  std::vector<float> kb(128);
-  k.resize((size_t)(C / 8 + 2) * 128 * 8, __float2bfloat16_rn(0.f));
-  for (int r = 0; r < 128; ++r) {
-    double ss = 0;
-    for (int c8 = 0; c8 < C / 8; ++c8)
-      for (int e = 0; e < 8; ++e) { const double v = (double)__bfloat162float(k[((size_t)c8 * 128 + r) * 8 + e]); ss += v * v; }
-    kb[r] = (float)(sqrt(ss) * 1.01);
-    k[((size_t)(C / 8) * 128 + r) * 8] = __float2bfloat16_rn(-kb[r]);
-  }
+  std::vector<float> kb((size_t)hid);
+  for (int b = 0; b < HG; ++b)
+    for (int r = 0; r < 128; ++r) {
+      double ss = 0;
+      for (int c8 = 0; c8 < C / 8; ++c8)
+        for (int e = 0; e < 8; ++e) { const double v = (double)__bfloat162float(k[(((size_t)b * KCH + c8) * 128 + r) * 8 + e]); ss += v * v; }
+      kb[b * 128 + r] = (float)(sqrt(ss) * 1.01);
+      k[(((size_t)b * KCH + C / 8) * 128 + r) * 8] = __float2bfloat16_rn(-kb[b * 128 + r]);
+    }
   // |q'_d| <= |W'_q[d,:]|: when every bound is small the soft-max over d needs no max subtraction (2^q' cannot overflow)
   double qb = 0;
-  for (int r = 0; r < 128; ++r) {
-    double ss = 0;
-    for (int c8 = 0; c8 < C / 8; ++c8)
-      for (int e = 0; e < 8; ++e) { const double v = (double)__bfloat162float(q[((size_t)c8 * 128 + r) * 8 + e]); ss += v * v; }
-    if (sqrt(ss) > qb) qb = sqrt(ss);
-  }
+  for (int b = 0; b < HG; ++b)
+    for (int r = 0; r < 128; ++r) {
+      double ss = 0;
+      for (int c8 = 0; c8 < C / 8; ++c8)
+        for (int e = 0; e < 8; ++e) { const double v = (double)__bfloat162float(q[(((size_t)b * (C / 8) + c8) * 128 + r) * 8 + e]); ss += v * v; }
+      if (sqrt(ss) > qb) qb = sqrt(ss);
+    }
   out->q_use_max = qb * 1.01 > 60.0 ? 1 : 0;
   // Ut[h][c][c'] = sum_e Wout[c'][(h,e)] * W'_v[(h,e)][c],  W'_v = W_v * g * sqrt(C)   (to_out.0 o v-projection, per head)
-  std::vector<float> ut((size_t)4 * C * C);
-  for (int h = 0; h < 4; ++h)
+  std::vector<float> ut((size_t)heads * C * C);
+  for (int h = 0; h < heads; ++h)
     for (int c = 0; c < C; ++c)
       for (int cp = 0; cp < C; ++cp) {
         double a = 0;
         for (int e = 0; e < 32; ++e)
-          a += (double)wout[(size_t)cp * 128 + h * 32 + e] * (double)wqkv[(size_t)(256 + h * 32 + e) * C + c] * (double)g[c] * (double)sq;
+          a += (double)wout[(size_t)cp * hid + h * 32 + e] * (double)wqkv[(size_t)(2 * hid + h * 32 + e) * C + c] * (double)g[c] * (double)sq;
         ut[((size_t)h * C + c) * C + cp] = (float)a;
       }
   auto up = [](const void* h, size_t bytes, void** d) {
     if (cudaMalloc(d, bytes) != cudaSuccess) return -1;
     return cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? 0 : -1;
   };
-  if (up(q.data(), q.size() * 2, &out->wq) || up(k.data(), k.size() * 2, &out->wk) || up(kb.data(), 128 * 4, (void**)&out->kb2) ||
+  if (up(q.data(), q.size() * 2, &out->wq) || up(k.data(), k.size() * 2, &out->wk) || up(kb.data(), kb.size() * 4, (void**)&out->kb2) ||
       up(ut.data(), ut.size() * 4, (void**)&out->Ut) || up(bout, C * 4, (void**)&out->bout) || up(g2, C * 4, (void**)&out->g2))
     return -1;
-  int rc = C == 32 ? configure_c<32>() : C == 64 ? configure_c<64>() : configure_c<128>();
+  int rc;
+  if (HG == 1) rc = C == 32 ? configure_c<32, 1>() : C == 64 ? configure_c<64, 1>() : configure_c<128, 1>();
+  else rc = C == 32 ? configure_c<32, 2>() : configure_c<64, 2>();
   if (rc) return -1;
   out->ready = true;
   return 0;
@@ -852,10 +884,15 @@ void linattn_tc_free(LinAttnTcW* w) {
 
 int linattn_tc_launch(const LinAttnTcW& w, const LinAttnTcArgs& a, cudaStream_t s) {
   if (!w.ready) return -1;
+  if (w.heads == 8) {
+    if (w.C == 32) return launch_c<32, 2>(w, a, s);
+    if (w.C == 64) return launch_c<64, 2>(w, a, s);
+    return -1;
+  }
   switch (w.C) {
-    case 32: return launch_c<32>(w, a, s);
-    case 64: return launch_c<64>(w, a, s);
-    case 128: return launch_c<128>(w, a, s);
+    case 32: return launch_c<32, 1>(w, a, s);
+    case 64: return launch_c<64, 1>(w, a, s);
+    case 128: return launch_c<128, 1>(w, a, s);
   }
   return -1;
 }

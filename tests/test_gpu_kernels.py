@@ -72,6 +72,25 @@ def test_conv_kernels_match_torch(case, kernel):
         assert util.rel_err(out, ref(True)) < 4e-3
 
 
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[7] == 1] + [(64, 0, 32, 3, 2, 64, 48, 1, False), (128, 0, 64, 3, 1, 40, 24, 1, False)])
+def test_folded_upsampling_conv_matches_torch(case):
+    """nearest x2 + 3x3 (ddpm.py:114-118) as ONE low-resolution convolution with 4 * Cout parity channels and a pixel-shuffle
+    epilogue (conv_tc_pack_up2): compared with torch on the up-sampled image.  The four 2x2 filters are summed in fp32 and rounded
+    to bf16 once, so the reference is the un-rounded-weight convolution with a bf16-level tolerance."""
+    C0, C1, Cout, ks, N, H, W, up, use_res = case
+    g = torch.Generator().manual_seed(C0 * 5 + Cout + H)
+    dev = torch.device("cuda:0")
+    x0 = torch.randn(N, H // 2, W // 2, C0, generator=g).to(dev)
+    w = (torch.randn(Cout, C0, 3, 3, generator=g) / (C0 * 9) ** 0.5).to(dev)
+    b = torch.randn(Cout, generator=g).to(dev)
+    out = run_conv(3, x0, None, w, b, None, 1, H, W)
+    x = F.interpolate(x0.bfloat16().float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1).permute(0, 2, 3, 1)
+    assert util.rel_err(out, ref) < 5e-3
+    old = run_conv(2, x0, None, w, b, None, 1, H, W)      # the replicate-on-load path it replaces
+    assert util.rel_err(out, old) < 5e-3
+
+
 # (C0, Cout, N, H, W, pro_G (0 = no prologue), act, film, stats_G (0 = none))
 FUSED_CASES = [
     (32, 32, 2, 32, 32, 8, 1, True, 8),      # ResnetBlock block2 at dim 32 (ddpm.py:174-185)
@@ -179,32 +198,37 @@ LINATTN_CASES = [(32, 2, 1024), (64, 1, 784), (128, 2, 256), (32, 3, 4096), (64,
                  (64, 20, 4096)]   # many images: flat / sliced tile lists cross image boundaries
 
 
-@pytest.mark.parametrize("C_,N,HW", LINATTN_CASES)
-def test_fused_linear_attention_matches_torch(C_, N, HW):
+# 8 heads (BASELINE configs[3]): two head groups of four; (C, N, HW)
+LINATTN8_CASES = [(32, 2, 1024), (64, 3, 4096), (32, 5, 16384), (64, 1, 1000), (32, 3, 65536), (64, 20, 4096)]
+
+
+@pytest.mark.parametrize("C_,N,HW,heads", [c + (4,) for c in LINATTN_CASES] + [c + (8,) for c in LINATTN8_CASES])
+def test_fused_linear_attention_matches_torch(C_, N, HW, heads):
     """attn(x) + x of LinearAttention (ddpm.py:214-251, 425) through the fused tcgen05 kernels."""
     lib = _lib.lib()
     dev = torch.device("cuda:0")
-    g = torch.Generator().manual_seed(C_ + N + HW)
+    hid = heads * 32
+    g = torch.Generator().manual_seed(C_ + N + HW + heads)
     x = (torch.randn(N, HW, C_, generator=g) * 1.3).bfloat16().float()
-    wqkv = torch.randn(384, C_, generator=g) / C_ ** 0.5
+    wqkv = torch.randn(3 * hid, C_, generator=g) / C_ ** 0.5
     gn = torch.rand(C_, generator=g) + 0.5
-    wout = torch.randn(C_, 128, generator=g) / 128 ** 0.5
+    wout = torch.randn(C_, hid, generator=g) / hid ** 0.5
     bout = torch.randn(C_, generator=g) * 0.1
     g2 = torch.rand(C_, generator=g) + 0.5
     rd = dev if N * HW > 200000 else torch.device("cpu")   # plain torch fp64 reference (on the GPU for the big cases)
     xd = x.double().to(rd)
     xn = F.normalize(xd, dim=-1) * gn.double().to(rd) * C_ ** 0.5
-    q, k, v = (xn @ wqkv.double().to(rd).T).view(N, HW, 3, 4, 32).unbind(dim=2)
+    q, k, v = (xn @ wqkv.double().to(rd).T).view(N, HW, 3, heads, 32).unbind(dim=2)
     q = q.softmax(dim=-1) * 32 ** -0.5
     k = k.softmax(dim=1)
     ctx = torch.einsum("nphd,nphe->nhde", k, v)
-    o = torch.einsum("nhde,nphd->nphe", ctx, q).reshape(N, HW, 128) @ wout.double().to(rd).T + bout.double().to(rd)
+    o = torch.einsum("nhde,nphd->nphe", ctx, q).reshape(N, HW, hid) @ wout.double().to(rd).T + bout.double().to(rd)
     attn = (F.normalize(o, dim=-1) * g2.double().to(rd) * C_ ** 0.5).cpu()
     xd = xd.cpu()
     del q, k, v, o, xn
     out = torch.empty(N, HW, C_, device=dev)
-    rc = lib.ld_debug_linattn(x.to(dev).data_ptr(), C_, N, HW, wqkv.contiguous().data_ptr(), gn.data_ptr(), wout.contiguous().data_ptr(),
-                              bout.data_ptr(), g2.data_ptr(), out.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    rc = lib.ld_debug_linattn_h(x.to(dev).data_ptr(), C_, N, HW, heads, wqkv.contiguous().data_ptr(), gn.data_ptr(), wout.contiguous().data_ptr(),
+                                bout.data_ptr(), g2.data_ptr(), out.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
     _lib.check(rc)
     got = out.cpu().double() - xd   # attention branch (the residual is exact up to the output rounding)
     assert util.rel_err(got, attn) < 2.5e-2
