@@ -187,6 +187,14 @@ LD_API int64_t ld_mask_scratch_bytes(int B, int S);
 LD_API int ld_mask_from_anomaly(const float* amap, int B, int h, int w, int S, int rule, int manual_cols, float* mask_pred,
                                 float* binary_mask, void* scratch, void* stream);
 
+/* PatchCore nearest-neighbour search (models.py:179-217, `euclidean_dist` + `nearest_neighbors(n_neighbors=1)`) on tcgen05:
+ * embedding [M][D], memory_bank [Nb][D] (device fp32) -> patch_scores [M] = min_j sqrt(clamp(|x|^2 - 2 x.y + |y|^2, 0)) and
+ * locations [M] (int64, lowest index among exact ties).  Operands are split into bf16 hi + lo parts (three MMAs per k-step), so the
+ * distances are fp32-accurate.  `scratch`: ld_knn_scratch_bytes(M, Nb, D) bytes of device memory. */
+LD_API int64_t ld_knn_scratch_bytes(int M, int Nb, int D);
+LD_API int ld_knn_min(const float* embedding, const float* memory_bank, int M, int Nb, int D, float* patch_scores, int64_t* locations,
+                      void* scratch, void* stream);
+
 /* --- introspection for bench.py -------------------------------------------------------------- */
 /* Kernel launches enqueued by this handle since creation (our own kernels only). */
 LD_API int64_t ld_launch_count(const ld_handle* h);
@@ -200,6 +208,8 @@ LD_API int64_t ld_workspace_bytes(const ld_handle* h);
  *                            kernels' analytic soft-max shift underflows, see ld_sample);
  *   "attn_simt", "debug_keep", "use_tc" (before ld_finalize_weights): test aids. */
 LD_API int ld_set_option(ld_handle* h, const char* name, int64_t value);
+/* Current value of a tunable ("la_exact" reads 1 once the engine has switched LinearAttention to the exact-max kernels). */
+LD_API int ld_get_option(const ld_handle* h, const char* name, int64_t* value);
 
 /* --- test hooks (used by tests/ only) ---------------------------------------------------------
  * Named intermediate activations of the last `ld_unet_forward` (requires option "debug_keep"=1

@@ -57,9 +57,12 @@ SIGNATURES = {
     "ld_mask_scratch_bytes": (C.c_int64, [C.c_int, C.c_int]),
     "ld_mask_from_anomaly": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
+    "ld_knn_scratch_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    "ld_knn_min": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ld_launch_count": (C.c_int64, [C.c_void_p]),
     "ld_workspace_bytes": (C.c_int64, [C.c_void_p]),
     "ld_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "ld_get_option": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]),
     "ld_debug_num_taps": (C.c_int, [C.c_void_p]),
     "ld_debug_tap_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]),
     "ld_debug_tap_fetch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

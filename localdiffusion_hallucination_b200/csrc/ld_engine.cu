@@ -968,6 +968,7 @@ int ld_create(const ld_model_desc* d, int device, ld_handle** out) {
   h->E.d = *d; h->E.device = device;
   h->E.bf = d->precision == LD_PREC_BF16;
   h->E.use_tc = h->E.bf;
+  if (const char* e = getenv("LD_USE_GRAPH")) h->E.opt_use_graph = atoi(e);   // development aid: eager launches (A/B against graph replay)
   build_specs(h->E);
   *out = h;
   return 0;
@@ -1881,6 +1882,14 @@ int ld_mask_from_anomaly(const float* amap, int B, int h, int w, int S, int rule
   return cudaGetLastError() == cudaSuccess ? 0 : fail(LD_ERR_CUDA, "ld_mask_from_anomaly launch failed");
 }
 
+int64_t ld_knn_scratch_bytes(int M, int Nb, int D) { return (int64_t)knn_scratch_bytes(M, Nb, D); }
+int ld_knn_min(const float* x, const float* bank, int M, int Nb, int D, float* score, int64_t* loc, void* scratch, void* stream) {
+  if (!x || !bank || !score || !loc || !scratch || M < 1 || Nb < 1 || D < 1) return fail(LD_ERR_INVALID, "bad argument");
+  if (ld_device_count() == 0) return fail(LD_ERR_NO_DEVICE, "no sm_100 CUDA device is available (there is no CPU fallback)");
+  if (knn_tc_launch(x, bank, M, Nb, D, score, (long long*)loc, scratch, (cudaStream_t)stream) < 0) return fail(LD_ERR_CUDA, "knn_tc_launch failed");
+  return cudaGetLastError() == cudaSuccess ? 0 : fail(LD_ERR_CUDA, "ld_knn_min launch failed");
+}
+
 int64_t ld_launch_count(const ld_handle* h) { return h ? h->E.launches : 0; }
 int64_t ld_workspace_bytes(const ld_handle* h) {
   if (!h) return 0;
@@ -1900,6 +1909,19 @@ int ld_set_option(ld_handle* h, const char* name, int64_t value) {
   else return fail(LD_ERR_INVALID, "unknown option '%s'", name);
   // options are read when a plan is built: drop every cached plan so that the new value takes effect on the next call
   if (E.finalized && ld_device_count() > 0 && cudaSetDevice(E.device) == cudaSuccess) drop_plans(E);
+  return 0;
+}
+
+int ld_get_option(const ld_handle* h, const char* name, int64_t* value) {
+  if (!h || !name || !value) return fail(LD_ERR_INVALID, "null argument");
+  const Engine& E = h->E;
+  if (!strcmp(name, "use_graph")) *value = E.opt_use_graph;
+  else if (!strcmp(name, "async")) *value = E.opt_async;
+  else if (!strcmp(name, "debug_keep")) *value = E.opt_debug_keep;
+  else if (!strcmp(name, "la_exact")) *value = E.opt_la_exact;
+  else if (!strcmp(name, "attn_simt")) *value = E.opt_attn_simt;
+  else if (!strcmp(name, "use_tc")) *value = E.use_tc ? 1 : 0;
+  else return fail(LD_ERR_INVALID, "unknown option '%s'", name);
   return 0;
 }
 

@@ -122,6 +122,10 @@ size_t mask_scratch_bytes(int B, int S);
 int launch_mask_from_anomaly(const float* amap, int B, int h, int w, int S, int rule, int manual_cols, float* mask_pred, float* binary, void* scratch,
                              cudaStream_t s);
 
+// PatchCore nearest-neighbour search on tcgen05 (ld_knn_tc.cu): x [M][D], bank [Nb][D] fp32 -> score [M], loc [M]
+size_t knn_scratch_bytes(int M, int Nb, int D);
+int knn_tc_launch(const float* x, const float* bank, int M, int Nb, int D, float* score, long long* loc, void* scratch, cudaStream_t s);
+
 int launch_nhwc_to_nchw_f32(const void* in, float* out, int N, int HW, int C, bool bf, cudaStream_t s);
 int launch_convert(const void* in, bool in_bf, void* out, bool out_bf, long long n, cudaStream_t s);
 int launch_copy_f32(const float* in, float* out, long long n, cudaStream_t s);

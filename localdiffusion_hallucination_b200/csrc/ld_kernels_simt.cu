@@ -309,6 +309,9 @@ __device__ __forceinline__ float silu_tanh(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
   return fmaf(h, t, h);
 }
+// DOT: fold a 1x1 convolution to one fp32 channel into the output pass (GnApplyP::dot_out) -- a separate instantiation, so that the
+// plain pass keeps its register count (73) and three blocks per SM
+template <bool DOT>
 __global__ void __launch_bounds__(256) gn_apply_bf16_fast_kernel(GnApplyP p, int vec_per_block) {
   extern __shared__ float sh[];  // aA[C], bA[C]
   const int n = blockIdx.y, C = p.C;
@@ -343,7 +346,7 @@ __global__ void __launch_bounds__(256) gn_apply_bf16_fast_kernel(GnApplyP p, int
   const int lpp = C / 8;                         // lanes per pixel
   float dw[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) dw[j] = p.dot_out ? p.dot_w[c0 + j] : 0.f;
+  for (int j = 0; j < 8; ++j) dw[j] = DOT ? p.dot_w[c0 + j] : 0.f;
   for (long long i0 = v0 + threadIdx.x; i0 < v1; i0 += 256 * U) {
     uint4 va[U], vb[U];
     float acc_dot[U] = {0.f, 0.f, 0.f, 0.f};
@@ -372,13 +375,13 @@ __global__ void __launch_bounds__(256) gn_apply_bf16_fast_kernel(GnApplyP p, int
           }
           __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
           o[j] = *reinterpret_cast<uint32_t*>(&h2);
-          d = fmaf(y0, dw[2 * j], d); d = fmaf(y1, dw[2 * j + 1], d);
+          if (DOT) { d = fmaf(y0, dw[2 * j], d); d = fmaf(y1, dw[2 * j + 1], d); }
         }
-        if (!p.dot_out) out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+        if (!DOT) out[i] = make_uint4(o[0], o[1], o[2], o[3]);
         else acc_dot[u] = d;
       }
     }
-    if (p.dot_out) {
+    if (DOT) {
       // the C / 8 threads that hold one pixel are neighbouring lanes (C <= 256): butterfly over them, the first one stores
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -399,7 +402,8 @@ int launch_gn_apply(const GnApplyP& p, bool bf, cudaStream_t s) {
     int vpb = 256 * 4 * 4;                       // 16 vectors (256 B) per thread
     if (nvec < vpb) vpb = (int)(((nvec + 255) / 256) * 256);
     dim3 grid(cdiv(nvec, vpb), p.N);
-    launch_k(gn_apply_bf16_fast_kernel, grid, dim3(256), 2 * (size_t)p.C * sizeof(float), s, true, p, vpb);
+    if (p.dot_out) launch_k(gn_apply_bf16_fast_kernel<true>, grid, dim3(256), 2 * (size_t)p.C * sizeof(float), s, true, p, vpb);
+    else launch_k(gn_apply_bf16_fast_kernel<false>, grid, dim3(256), 2 * (size_t)p.C * sizeof(float), s, true, p, vpb);
     return 1;
   }
   int ppb = 2048 * 32 / p.C;

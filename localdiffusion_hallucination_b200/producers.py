@@ -83,3 +83,20 @@ def masks_from_anomaly(anomaly_map, rule, img_size=None, manual_cols=0, want_bin
     _lib.check(lib.ld_mask_from_anomaly(a.data_ptr(), b, h, w, s, MASK_RULES[rule], int(manual_cols), mp.data_ptr(),
                                         bm.data_ptr() if bm is not None else None, scratch.data_ptr(), _stream(a.device)))
     return mp, bm
+
+
+def knn_min(embedding, memory_bank):
+    """PatchCore `nearest_neighbors(embedding, n_neighbors=1)` (models.py:179-217) on the tensor cores: embedding [M,D] and
+    memory_bank [Nb,D] on the device -> (patch_scores [M], locations [M] int64).  The [M x Nb] distance matrix is never formed."""
+    _need_cuda(embedding)
+    x = embedding.to(torch.float32).contiguous()
+    y = memory_bank.to(x.device, torch.float32).contiguous()
+    m, d = x.shape
+    nb, d2 = y.shape
+    assert d == d2
+    lib = _lib.lib()
+    score = torch.empty(m, device=x.device)
+    loc = torch.empty(m, dtype=torch.int64, device=x.device)
+    scratch = torch.empty(int(lib.ld_knn_scratch_bytes(m, nb, d)), dtype=torch.uint8, device=x.device)
+    _lib.check(lib.ld_knn_min(x.data_ptr(), y.data_ptr(), m, nb, d, score.data_ptr(), loc.data_ptr(), scratch.data_ptr(), _stream(x.device)))
+    return score, loc

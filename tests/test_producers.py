@@ -106,3 +106,30 @@ def test_gpu_mask_feeds_the_sampler_contract():
     name, rule, cfg, amap, size, manual = [c for c in pc.mask_cases() if c[0] == "mri_t12flair_3"][0]
     mp, bm = producers.masks_from_anomaly(amap.repeat(1, 1, 1, 1).to(DEV), rule, size)
     assert torch.equal((mp >= 1.0).float(), bm) and 0 < float(bm.mean()) < 1
+
+
+@pytest.mark.gpu
+def test_gpu_knn_matches_reference(gp):
+    """PatchCore nearest neighbour (models.py:179-217) on tcgen05 with split-bf16 operands: fp32-level distances, same locations."""
+    for name, x, bank in pc.knn_cases():
+        sc, loc = producers.knn_min(x.to(DEV), bank.to(DEV))
+        ref_sc, ref_loc = torch.from_numpy(gp[f"knn_{name}_score"]), torch.from_numpy(gp[f"knn_{name}_loc"])
+        sc, loc = sc.cpu(), loc.cpu()
+        assert util.max_abs(sc, ref_sc) < 2e-3, name          # sqrt amplifies the rounding of d^2 near 0 (the exact hit)
+        big = ref_sc > 0.1
+        assert util.rel_err(sc[big], ref_sc[big]) < 1e-5, name
+        # locations: identical wherever the runner-up is not within rounding distance of the minimum
+        d = torch.cdist(x.double(), bank.double())
+        top2 = d.topk(2, largest=False, dim=1).values
+        clear = (top2[:, 1] - top2[:, 0]) > 1e-4
+        assert torch.equal(loc[clear], ref_loc[clear]) and int(clear.sum()) > 0.9 * len(loc), name
+    # PatchCore-sized problem: 784 patches of one image against a 16k-entry bank of 1536-d features; fp64 reference on the GPU
+    g = torch.Generator().manual_seed(9)
+    x, bank = torch.randn(784, 1536, generator=g).to(DEV), torch.randn(16385, 1536, generator=g).to(DEV)
+    sc, loc = producers.knn_min(x, bank)
+    d = torch.cdist(x.double(), bank.double())
+    ref_sc, ref_loc = d.min(dim=1)
+    assert util.rel_err(sc, ref_sc) < 1e-5
+    top2 = d.topk(2, largest=False, dim=1).values
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-3
+    assert torch.equal(loc[clear].cpu(), ref_loc[clear].cpu())
