@@ -123,6 +123,13 @@ LD_API int ld_set_schedule(ld_handle* h, int T, const float* posterior_mean_coef
                     const float* posterior_mean_coef2, const float* posterior_log_variance_clipped,
                     const float* sigma);
 
+/* Objective of the denoiser (ddpm.py:534-536, 731-761).  Default pred_x0 (the shipped config.yaml:45): x0 = model output.  For
+ * pred_noise pass (sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod), for pred_v (sqrt_alphas_cumprod,
+ * sqrt_one_minus_alphas_cumprod): x0 = a[t] * x_t - b[t] * output (ddpm.py:631-653); a == NULL switches back to pred_x0.
+ * Single-trajectory sampling only: ld_sample / ld_sample_ddim fail with LD_ERR_INVALID for sd->branch_out with these objectives,
+ * where the reference dies with UnboundLocalError. */
+LD_API int ld_set_objective(ld_handle* h, int T, const float* a, const float* b);
+
 /* --- `Unet.forward(x, cond_img, time)` (ddpm.py:404-451) -------------------------------------
  * x, cond, out: device fp32 [N,1,H,W]; t: device int64 [N]. */
 LD_API int ld_unet_forward(ld_handle* h, const float* x, const float* cond, const int64_t* t, float* out,
@@ -135,7 +142,8 @@ LD_API int ld_cond_encode(ld_handle* h, const float* cond, float* feat, int N, i
  * noise: device fp32 [num_timesteps, B,1,H,W]; noise[0] is x_T (already q_sample'd by the host
  *        when use_gt), noise[1+i] is the draw of loop iteration i (t = T-1-i), none for t == 0.
  * out:   device fp32 [B,1,H,W] (or [2,B,1,H,W] when return_pair).
- * x0_trace: optional device fp32 [num_timesteps, 2, B,1,H,W] (slot 1 unused after fusion). */
+ * x0_trace: optional device fp32 [num_timesteps, 2, B,1,H,W]: slot 0 = x0 of the step (OOD branch while branched), slot 1 = x0 of
+ *        the IND branch while branched, the UPDATED image x_{t-1} on single-trajectory steps (return_all_timesteps, ddpm.py:964). */
 LD_API int ld_sample(ld_handle* h, const ld_sample_desc* sd, const float* cond, const float* mask,
               const float* noise, float* out, float* x0_trace, void* stream);
 /* Host synchronisation: the loop itself never touches the host (t lives on the device, one CUDA graph per timestep).  By default

@@ -46,6 +46,7 @@ SIGNATURES = {
     "ld_load_weight": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int]),
     "ld_finalize_weights": (C.c_int, [C.c_void_p]),
     "ld_set_schedule": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ld_set_objective": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ld_unet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ld_cond_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ld_sample": (C.c_int, [C.c_void_p, C.POINTER(SampleDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

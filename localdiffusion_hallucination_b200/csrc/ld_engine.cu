@@ -22,8 +22,14 @@
 #include "ld_linattn_tc.h"
 #include "ld_attn_tc.h"
 #include "ld_conv7_tc.h"
+#include "ld_launch.cuh"
 
 namespace ld {
+
+int& pdl_flag() {
+  static int v = [] { const char* e = getenv("LD_PDL"); return e ? atoi(e) : 1; }();
+  return v;
+}
 
 static thread_local char g_err[1024] = "";
 static int fail(int code, const char* fmt, ...) {
@@ -117,11 +123,12 @@ struct Engine {
   // schedule
   int T = 0;
   float *coef1 = nullptr, *coef2 = nullptr, *sigma = nullptr;
+  float *obj_a = nullptr, *obj_b = nullptr;   // pred_noise / pred_v: x0 = a[t] x_t - b[t] out (null: pred_x0)
   // runtime
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   int64_t launches = 0;
-  int64_t opt_use_graph = 1, opt_debug_keep = 0, opt_la_exact = 0, opt_attn_simt = 0, opt_async = 0;
+  int64_t opt_use_graph = 1, opt_debug_keep = 0, opt_la_exact = 0, opt_attn_simt = 0, opt_async = 0, opt_up2 = 1;
   bool pending = false; ld_sample_desc pend_sd{}; bool pend_fuse = false;   // opt_async: checks deferred to ld_sample_finish
   unsigned int* la_flag = nullptr;        // soft-max underflow counter of the fused LinearAttention
   // sampler: FiLM rows of every timestep [film_tab_T][film_total] -- time MLP + block MLPs depend on t only (ddpm.py:339-344,191-194),
@@ -156,6 +163,8 @@ struct Engine {
     if (coef1) cudaFree(coef1);
     if (coef2) cudaFree(coef2);
     if (sigma) cudaFree(sigma);
+    if (obj_a) cudaFree(obj_a);
+    if (obj_b) cudaFree(obj_b);
     if (ev_in) cudaEventDestroy(ev_in);
     if (ev_out) cudaEventDestroy(ev_out);
     if (own_stream) cudaStreamDestroy(own_stream);
@@ -494,7 +503,7 @@ struct Builder {
     bool use_tc = false;
     static int no_up2 = -1;   // env LD_CONV_NO_UP2=1: keep the replicate-on-load up-sampling path (A/B aid)
     if (no_up2 < 0) { const char* e = getenv("LD_CONV_NO_UP2"); no_up2 = e ? atoi(e) : 0; }
-    if (E.use_tc && up && !b && !resid && !pro && !stats_off && cw.tc_up2.ready && !no_up2) {
+    if (E.use_tc && up && !b && !resid && !pro && !stats_off && cw.tc_up2.ready && !no_up2 && E.opt_up2) {
       ConvTcArgs tu;
       tu.src0 = a.p; tu.C0 = a.C; tu.N = a.N; tu.H = a.H; tu.W = a.W; tu.Hin = a.H; tu.Win = a.W; tu.ps = cw.Cout;
       if (outH == 2 * a.H && outW == 2 * a.W && conv_tc_supports(cw.tc_up2, tu)) {
@@ -1035,6 +1044,25 @@ int ld_set_schedule(ld_handle* h, int T, const float* c1, const float* c2, const
   return 0;
 }
 
+// Objective of the denoiser (ddpm.py:534-536): pred_x0 (a == NULL), or pred_noise / pred_v through the per-timestep pair (a, b) with
+// x0 = a[t] * x_t - b[t] * model_output: (sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod) resp. (sqrt_alphas_cumprod,
+// sqrt_one_minus_alphas_cumprod) (ddpm.py:631-653).  Only single-trajectory sampling supports them -- like the reference, whose branch
+// path dies with UnboundLocalError for anything but pred_x0 (ddpm.py:731-761).
+int ld_set_objective(ld_handle* h, int T, const float* a, const float* b) {
+  if (!h) return fail(LD_ERR_INVALID, "null handle");
+  if (ld_device_count() == 0) return fail(LD_ERR_NO_DEVICE, "no sm_100 CUDA device is available (there is no CPU fallback)");
+  Engine& E = h->E;
+  CK(cudaSetDevice(E.device));
+  if (E.obj_a) { cudaFree(E.obj_a); cudaFree(E.obj_b); E.obj_a = E.obj_b = nullptr; }
+  if (!a) return 0;
+  if (!b || T <= 0) return fail(LD_ERR_INVALID, "bad objective tables");
+  if (E.T && T != E.T) return fail(LD_ERR_INVALID, "objective tables must have the schedule's length (%d)", E.T);
+  CK(cudaMalloc(&E.obj_a, T * sizeof(float))); CK(cudaMalloc(&E.obj_b, T * sizeof(float)));
+  CK(cudaMemcpy(E.obj_a, a, T * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(E.obj_b, b, T * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 static int need_ready(Engine& E) {
   if (ld_device_count() == 0) return fail(LD_ERR_NO_DEVICE, "no sm_100 CUDA device is available (there is no CPU fallback)");
   if (!E.finalized) return fail(LD_ERR_STATE, "weights not finalized");
@@ -1197,6 +1225,7 @@ static StepP make_step(Engine& E, const ld_sample_desc& sd, int kind, const floa
   p.n = n; p.z_stride = n; p.tloop = sd.num_timesteps; p.counters = S.counters;
   p.x0_trace = x0_trace; p.trace_stride = 2 * n;
   p.ticket = S.counters + 4;   // the step kernel also does `t -= 1` (ddpm.py:951)
+  p.ca = E.obj_a; p.cb = E.obj_b;
   return p;
 }
 
@@ -1355,6 +1384,7 @@ int ld_sample(ld_handle* h, const ld_sample_desc* sdp, const float* cond, const 
   if (E.pending) return fail(LD_ERR_STATE, "a deferred call is pending: call ld_sample_finish first");
   if (sd.num_timesteps < 1 || sd.num_timesteps > E.T) return fail(LD_ERR_INVALID, "num_timesteps out of range");
   if (sd.branch_out && !mask) return fail(LD_ERR_INVALID, "branch mode needs a mask");
+  if (sd.branch_out && E.obj_a) return fail(LD_ERR_INVALID, "branch sampling needs objective pred_x0 (ddpm.py:731-761)");
   if ((rc = check_shape(E, sd.height, sd.width))) return rc;
   return sample_impl(h, sd, cond, mask, noise, out, x0_trace, (cudaStream_t)stream, true);
 }
@@ -1425,6 +1455,7 @@ static int ddim_impl(ld_handle* h, const ld_sample_desc& sd, const float* cond, 
     p.bm = S.bm; p.cond_out = S.cond_out; p.z = noise; p.z_stride = n; p.idx_ptr = idx_d; p.nsteps = nsteps; p.coefs = coefs_d;
     p.mask_x = sd.mask_x; p.ood_uses_cond = sd.ood_uses_cond; p.lo = sd.min_val; p.hi = sd.max_val; p.n = n; p.counters = S.counters;
     p.ticket = S.counters + 4; p.times = times_d; p.t_ptr = S.t_dev;   // the step kernel also advances (idx, t) (ddpm.py:996-998)
+    p.ca = E.obj_a; p.cb = E.obj_b;
     return p;
   };
   auto body = [&](int kind, cudaStream_t st) -> int {
@@ -1490,6 +1521,7 @@ int ld_sample_ddim(ld_handle* h, const ld_sample_desc* sdp, const float* cond, c
   for (int i = 0; i < nsteps; ++i)   // times index the per-timestep FiLM table and the schedule
     if (times[i] < 0 || times[i] >= E.T) return fail(LD_ERR_INVALID, "times[%d] = %d is outside [0, %d)", i, times[i], E.T);
   if (sd.branch_out && !mask) return fail(LD_ERR_INVALID, "branch mode needs a mask");
+  if (sd.branch_out && E.obj_a) return fail(LD_ERR_INVALID, "branch sampling needs objective pred_x0 (ddpm.py:731-761)");
   if ((rc = check_shape(E, sd.height, sd.width))) return rc;
   return ddim_impl(h, sd, cond, mask, noise, out, times, coefs, nsteps, fuse_step, (cudaStream_t)stream, true);
 }
@@ -1905,6 +1937,8 @@ int ld_set_option(ld_handle* h, const char* name, int64_t value) {
   else if (!strcmp(name, "debug_keep")) E.opt_debug_keep = value;
   else if (!strcmp(name, "la_exact")) E.opt_la_exact = value;
   else if (!strcmp(name, "attn_simt")) E.opt_attn_simt = value;
+  else if (!strcmp(name, "pdl")) pdl_flag() = value != 0;      // process-wide: programmatic dependent launch (ld_launch.cuh)
+  else if (!strcmp(name, "up2")) E.opt_up2 = value;
   else if (!strcmp(name, "use_tc")) { if (E.finalized) return fail(LD_ERR_STATE, "use_tc must be set before finalize"); E.use_tc = value != 0 && E.bf; }
   else return fail(LD_ERR_INVALID, "unknown option '%s'", name);
   // options are read when a plan is built: drop every cached plan so that the new value takes effect on the next call
@@ -1920,6 +1954,8 @@ int ld_get_option(const ld_handle* h, const char* name, int64_t* value) {
   else if (!strcmp(name, "debug_keep")) *value = E.opt_debug_keep;
   else if (!strcmp(name, "la_exact")) *value = E.opt_la_exact;
   else if (!strcmp(name, "attn_simt")) *value = E.opt_attn_simt;
+  else if (!strcmp(name, "pdl")) *value = pdl_flag();
+  else if (!strcmp(name, "up2")) *value = E.opt_up2;
   else if (!strcmp(name, "use_tc")) *value = E.use_tc ? 1 : 0;
   else return fail(LD_ERR_INVALID, "unknown option '%s'", name);
   return 0;

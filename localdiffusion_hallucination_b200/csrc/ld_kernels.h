@@ -88,7 +88,9 @@ struct StepP {
   int tloop;                // loop length (index of draw for step t is tloop - t, draw 0 is x_T)
   unsigned int* counters;   // [2]=#(x_out*m==0), [3]=#(x_in*(1-m)==0) at the fusion step
   float* x0_trace; long long trace_stride;  // optional [tloop][2][n]
-  unsigned int* ticket;     // optional (zero-initialised, self re-arming): the last block to finish writes *t_ptr = t - 1 (ddpm.py:951)
+  unsigned int* ticket;     // optional (zero-initialised, self re-arming): the last block to finish writes *t_ptr = t - 1 (ddpm.py:951)  // single-trajectory steps with objective pred_noise / pred_v (ddpm.py:731-737, 757-761): x0 = ca[t] * x_t - cb[t] * model_output
+  // (predict_start_from_noise / predict_start_from_v, ddpm.py:631-653); null for pred_x0 (x0 = model_output)
+  const float* ca; const float* cb;
 };
 int launch_step(const StepP& p, cudaStream_t s);
 
@@ -111,6 +113,7 @@ struct DdimP {
   unsigned int* counters;   // [2]=#(eps_out*m==0), [3]=#(eps_in*(1-m)==0) at the fusion step
   unsigned int* ticket;     // optional: the last block to finish advances idx and loads t = times[idx] (ddpm.py:996-998)
   const int* times; int* t_ptr;   // device [nsteps] schedule of `time` values and the scalar the UNet plans read
+  const float* ca; const float* cb;   // [T] tables indexed by time, see StepP (single-trajectory steps only)
 };
 int launch_ddim_step(const DdimP& p, cudaStream_t s);
 

@@ -927,11 +927,17 @@ __global__ void __launch_bounds__(256) step_kernel(StepP p) {
     unpack4(ld4(p.x_out, i), xo);
     if (p.o_out) unpack4(ld4(p.o_out, i), oo);
     if (p.kind == 2) {
+      const bool conv = p.ca != nullptr;   // pred_noise / pred_v: x0 from (x_t, model output), separately rounded like the reference
+      const float ca = conv ? p.ca[t] : 0.f, cb = conv ? p.cb[t] : 0.f;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { r0[k] = clampf(oo[k], p.lo, p.hi); xo[k] = post(c1, c2, sg, r0[k], xo[k], zz[k]); }
+      for (int k = 0; k < 4; ++k) {
+        const float raw = conv ? __fsub_rn(__fmul_rn(ca, xo[k]), __fmul_rn(cb, oo[k])) : oo[k];
+        r0[k] = clampf(raw, p.lo, p.hi);
+        xo[k] = post(c1, c2, sg, r0[k], xo[k], zz[k]);
+      }
       st4(p.x_out, i, xo);
       if (p.x0_out) st4(p.x0_out, i, r0);
-      if (tr) st4(tr, i, r0);
+      if (tr) { st4(tr, i, r0); st4(tr + p.n, i, xo); }   // trace slot 1 on single-trajectory steps: the updated image x_{t-1}
     } else {
       float bm[4], xi[4], oi[4], co[4] = {0.f, 0.f, 0.f, 0.f};
       unpack4(ld4(p.bm, i), bm);
@@ -1009,9 +1015,14 @@ __global__ void __launch_bounds__(256) ddim_step_kernel(DdimP p) {
     unpack4(ld4(p.x_out, i), xo);
     if (p.o_out) unpack4(ld4(p.o_out, i), oo);
     if (p.kind == 2) {
+      const bool conv = p.ca != nullptr;
+      const int tt = conv ? p.times[idx] : 0;
+      const float ca = conv ? p.ca[tt] : 0.f, cb = conv ? p.cb[tt] : 0.f;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float x0 = clampf(oo[k], p.lo, p.hi);
+        // clip_x_start=True, rederive_pred_noise=True (ddpm.py:1049): eps is re-derived from the clamped x0 for every objective
+        const float raw = conv ? __fsub_rn(__fmul_rn(ca, xo[k]), __fmul_rn(cb, oo[k])) : oo[k];
+        const float x0 = clampf(raw, p.lo, p.hi);
         xo[k] = last ? x0 : ddim_next(san, c, sg, x0, eps_from(sr, srm1, xo[k], x0), zz[k]);
       }
       st4(p.x_out, i, xo);

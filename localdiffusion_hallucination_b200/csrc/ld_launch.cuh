@@ -18,11 +18,9 @@ namespace ld {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-inline bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("LD_PDL"); v = e ? atoi(e) : 1; }
-  return v != 0;
-}
+// process-wide switch (ld_set_option "pdl"; initial value from env LD_PDL, default on); defined in ld_engine.cu
+int& pdl_flag();
+inline bool pdl_enabled() { return pdl_flag() != 0; }
 
 // kernel<<<grid, block, smem, s>>>(args...) with the PDL attribute (pdl == true and LD_PDL != 0)
 template <typename... KArgs, typename... Args>

@@ -69,6 +69,15 @@ class GaussianDiffusion(nn.Module):
         lv = self.posterior_log_variance_clipped.detach().cpu().contiguous()
         sg = (0.5 * lv).exp().contiguous()  # ddpm.py:853
         _lib.check(_lib.lib().ld_set_schedule(h, c1.numel(), c1.data_ptr(), c2.data_ptr(), lv.data_ptr(), sg.data_ptr()))
+        # objective (ddpm.py:534-536): pred_x0 needs nothing; pred_noise / pred_v hand over the pair of per-timestep coefficients of
+        # predict_start_from_noise / predict_start_from_v (ddpm.py:631-653)
+        if self.objective == "pred_x0":
+            _lib.check(_lib.lib().ld_set_objective(h, 0, None, None))
+        else:
+            names = {"pred_noise": ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod"),
+                     "pred_v": ("sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod")}[self.objective]
+            a, b = (getattr(self, n).detach().cpu().contiguous() for n in names)
+            _lib.check(_lib.lib().ld_set_objective(h, a.numel(), a.data_ptr(), b.data_ptr()))
         self._schedule_on = key
 
     def make_noise_tape(self, shape, steps, device):
@@ -169,12 +178,15 @@ class GaussianDiffusion(nn.Module):
             u = torch.unique(mask)
             if len(u) == 1 and u == 1:
                 cfg["mask_cond"] = cfg["mask_x"] = cfg["branch_out"] = cfg["start_intermediate"] = False
-        if return_all_timesteps:
-            raise NotImplementedError("return_all_timesteps stacks branch lists and fails in the reference (ddpm.py:964)")
         if cfg["branch_out"] and self.objective != "pred_x0":
-            raise UnboundLocalError("branch sampling needs objective='pred_x0' (ddpm.py:731-761)")
-        if self.objective != "pred_x0":
-            raise NotImplementedError("only objective='pred_x0' is on the sampler hot path")
+            # the reference's branch path only defines `model_output_*` (ddpm.py:694-695): the other objectives hit an unbound name
+            raise UnboundLocalError("cannot access local variable 'model_output' where it is not associated with a value "
+                                    "(branch sampling needs objective='pred_x0', ddpm.py:731-761)")
+        if return_all_timesteps and cfg["branch_out"]:
+            # `torch.stack(imgs, dim=1)` over a list that holds [out, in] pairs (ddpm.py:865, 964)
+            raise TypeError("expected Tensor as element 1 in argument 0, but got list (return_all_timesteps with branch_out, ddpm.py:964)")
+        if return_all_timesteps and self.is_ddim_sampling:
+            raise NotImplementedError("return_all_timesteps is supported on the DDPM path only")
         if cfg.get("classifier", False) and cfg["start_intermediate"]:
             raise NotImplementedError("classifier gate is out of scope (ddpm.py:883-916)")
 
@@ -214,9 +226,9 @@ class GaussianDiffusion(nn.Module):
         sd.min_val, sd.max_val = float(min_max_val[0]), float(min_max_val[1])
         pair = (not self.start_intermediate) and bool(self.branch_out)  # ddpm.py:965-970
         sd.return_pair = int(pair)
-        sd.record_x0 = int(return_all_outputs)
+        sd.record_x0 = int(return_all_outputs or return_all_timesteps)
         out = torch.empty((2, B, Cc, S, S) if pair else (B, Cc, S, S), device=dev)
-        trace = torch.zeros((steps, 2, B, Cc, S, S), device=dev) if return_all_outputs else None
+        trace = torch.zeros((steps, 2, B, Cc, S, S), device=dev) if sd.record_x0 else None
         will_fuse = sd.branch_out and sd.start_intermediate
         rc = _lib.lib().ld_sample(h, C.byref(sd), cond.data_ptr(), mk.data_ptr() if mk is not None else None,
                                   noise.data_ptr(), out.data_ptr(), trace.data_ptr() if trace is not None else None,
@@ -225,6 +237,10 @@ class GaussianDiffusion(nn.Module):
             cfg["branch_out"] = False
             cfg["mask_x"] = False
         _lib.check(rc)
+        if return_all_timesteps:  # ddpm.py:946, 964: imgs = [x_T, x_{T-1}, ..., x_0] stacked along dim 1 (single trajectory only)
+            out = torch.cat((noise[0].unsqueeze(1), trace[:, 1].permute(1, 0, 2, 3, 4)), dim=1)
+            if pair:  # ddpm.py:965-970 stacks whatever `ret` is
+                out = torch.stack((out, out), dim=0)
         if return_all_outputs:  # ddpm.py:973-974: (ret, x_start_lst, confidence_map)
             lst = []
             branched = bool(sd.branch_out)

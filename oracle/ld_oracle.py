@@ -284,6 +284,14 @@ class Sampler:
             return self.model_fn(x, cond, t)
         return unet_forward(self.sd, self.hp, x, cond, t)
 
+    # -- ddpm.py:631-653, 731-761: x0 from the model output for the three objectives (single trajectory) ------------------
+    def _x0_from_output(self, x, o, t: int):
+        if self.objective == "pred_noise":
+            return self.buf["sqrt_recip_alphas_cumprod"][t] * x - self.buf["sqrt_recipm1_alphas_cumprod"][t] * o
+        if self.objective == "pred_v":
+            return self.buf["sqrt_alphas_cumprod"][t] * x - self.buf["sqrt_one_minus_alphas_cumprod"][t] * o
+        return o
+
     # -- ddpm.py:659-666 -----------------------------------------------------------------------
     def _posterior(self, x0, xt, t: int):
         mean = self.buf["posterior_mean_coef1"][t] * x0 + self.buf["posterior_mean_coef2"][t] * xt
@@ -328,7 +336,7 @@ class Sampler:
             m_i, _ = self._posterior(x0_in, x[1], t)
             return (m_o, m_i), lv, (x0_out, x0_in), None
         o = self._model(x, cond, tt)  # ddpm.py:716 -- full, unmasked condition
-        x0 = o.clamp(lo, hi)  # ddpm.py:821
+        x0 = self._x0_from_output(x, o, t).clamp(lo, hi)  # ddpm.py:731-761, 821
         mean, lv = self._posterior(x0, x, t)
         return mean, lv, x0, None
 
@@ -445,7 +453,8 @@ def ddim_sample(smp: "Sampler", cond: Tensor, mask: Tensor, min_max_val, noise_t
             else:
                 img = [x0_out * alpha_next.sqrt() + c * e_out + sigma * noise, x0_in * alpha_next.sqrt() + c * e_in + sigma * noise]
         else:
-            x0 = smp._model(img, cond, tt).clamp(lo, hi)  # ddpm.py:716, clip_x_start (and the idempotent re-clamp of 1050-1051)
+            # ddpm.py:716, 731-761 with clip_x_start (and the idempotent re-clamp of 1050-1051); eps is re-derived from the clamped x0
+            x0 = smp._x0_from_output(img, smp._model(img, cond, tt), time).clamp(lo, hi)
             eps = eps_of(img, time, x0)
             if time_next < 0:
                 img = x0

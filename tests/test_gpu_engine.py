@@ -51,7 +51,10 @@ def test_checkpoint_ingest_then_sample(tmp_path, prec):
     before = dst.sample(cond, None, batch_size=2, mask=mask, min_max_val=MM, noise=tape)   # engine built with the OLD weights
     assert load_reference_checkpoint(dst, str(path)) == 7
     got = dst.sample(cond, None, batch_size=2, mask=mask, min_max_val=MM, noise=tape)
-    assert util.max_abs(got, want) < 1e-4                                  # atomics order only
+    if prec == "fp32":
+        assert util.max_abs(got, want) < 1e-4                              # atomics order only
+    else:
+        assert util.psnr(got, want, MM[1]) > 45.0                          # ... amplified by bf16 rounding of the activations
     assert util.max_abs(got, before) > 1e-3                                # and it really changed
     # oracle on the ingested weights
     sd = {k[len("model."):]: v.cpu() for k, v in dst.state_dict().items() if k.startswith("model.")}

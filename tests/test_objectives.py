@@ -1,0 +1,80 @@
+"""Single-trajectory objectives pred_noise / pred_v (ddpm.py:731-737, 757-761), `return_all_timesteps` (ddpm.py:946, 964) and the
+reference's failure modes for the branched path.  Fixtures: tests/golden/golden_obj.npz (tests/golden/make_golden_obj.py, live
+reference)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from localdiffusion_hallucination_b200 import GaussianDiffusion
+from oracle import ld_oracle as lo
+from tests import util
+from tests.golden import cases
+from tests.golden.make_golden_obj import CASES, inputs
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def go():
+    return np.load(os.path.join(util.ROOT, "tests", "golden", "golden_obj.npz"), allow_pickle=False)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_objectives_match_reference(go, name):
+    obj, T, steps, eta = CASES[name]
+    B, S, cond, mask, mm = inputs()
+    smp = lo.Sampler(cases.base_config("mri", 2, branch_out=False), util.cpu_state_dict(util.make_model("mnist")), util.hp_of("mnist"),
+                     image_size=S, timesteps=T, objective=obj)
+    tape = list(cases.noise_tape(B, S, T if steps is None else steps))
+    with torch.no_grad():
+        o = smp.sample(cond, mask, mm, tape) if steps is None else lo.ddim_sample(smp, cond, mask, mm, tape, steps, eta)
+    assert util.max_abs(o, torch.from_numpy(go[f"{name}_out"])) < (1e-3 if obj == "pred_noise" else 5e-5)
+
+
+def test_branched_objective_error_is_the_reference_one(go):
+    assert str(go["branch_pred_noise_error"]) == "UnboundLocalError"
+    m = util.make_model("mnist")
+    gd = GaussianDiffusion(cases.base_config("mri", 2), m, image_size=32, timesteps=4, objective="pred_noise")
+    B, S, cond, mask, mm = inputs()
+    with pytest.raises(UnboundLocalError):   # raised on the host before any device work
+        gd.sample(cond, None, batch_size=B, mask=mask, min_max_val=mm, noise=cases.noise_tape(B, S, 4))
+    gd2 = GaussianDiffusion(cases.base_config("mri", 2), m, image_size=32, timesteps=4, objective="pred_x0")
+    with pytest.raises(TypeError):           # torch.stack over [out, in] lists (ddpm.py:964)
+        gd2.sample(cond, None, batch_size=B, mask=mask, min_max_val=mm, noise=cases.noise_tape(B, S, 4), return_all_timesteps=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(CASES))
+def test_gpu_objectives_match_reference(go, name):
+    obj, T, steps, eta = CASES[name]
+    B, S, cond, mask, mm = inputs()
+    ref = torch.from_numpy(go[f"{name}_out"])
+    n = T if steps is None else steps
+    for prec in ("fp32", "bf16"):
+        m = util.make_model("mnist", prec, device=DEV)
+        cfg = cases.base_config("mri", 2, branch_out=False)
+        gd = GaussianDiffusion(cfg, m, image_size=S, timesteps=T, sampling_timesteps=steps, ddim_sampling_eta=eta, objective=obj).to(DEV)
+        out = gd.sample(cond, None, batch_size=B, mask=mask, min_max_val=mm, noise=cases.noise_tape(B, S, n))
+        p = util.psnr(out, ref, mm[1])
+        # pred_noise amplifies the model-output error by sqrt(1/abar - 1) (~1e2 at the first steps): looser bars than pred_x0 / pred_v
+        bar = {"fp32": 50.0 if obj == "pred_noise" else 60.0, "bf16": 25.0 if obj == "pred_noise" else 40.0}[prec]
+        assert p > bar, (prec, p)
+        assert cfg == cases.base_config("mri", 2, branch_out=False)
+
+
+@pytest.mark.gpu
+def test_gpu_return_all_timesteps(go):
+    B, S, cond, mask, mm = inputs()
+    T = 6
+    ref = torch.from_numpy(go["all_t_out"])
+    m = util.make_model("mnist", "fp32", device=DEV)
+    gd = GaussianDiffusion(cases.base_config("mri", 2, branch_out=False), m, image_size=S, timesteps=T, objective="pred_x0").to(DEV)
+    tape = cases.noise_tape(B, S, T)
+    out = gd.sample(cond, None, batch_size=B, mask=mask, min_max_val=mm, noise=tape, return_all_timesteps=True)
+    assert tuple(out.shape) == (B, T + 1, 1, S, S)
+    assert torch.equal(out[:, 0].cpu(), tape[0])            # imgs[0] is x_T
+    assert util.max_abs(out, ref) < 2e-3 * mm[1]
+    last = gd.sample(cond, None, batch_size=B, mask=mask, min_max_val=mm, noise=tape)
+    assert util.max_abs(out[:, -1], last) < 1e-4
