@@ -27,7 +27,9 @@
 namespace ld {
 
 int& pdl_flag() {
-  static int v = [] { const char* e = getenv("LD_PDL"); return e ? atoi(e) : 1; }();
+  // measured in-process on the bench workload (tools/gpu_ab.py pdl=0,1): 5.21 ms per timestep without, 5.55 ms with -- the early-scheduled
+  // CTAs of the next kernel start at different times on different SMs and skew the static tile split of the persistent kernels.  Off by default.
+  static int v = [] { const char* e = getenv("LD_PDL"); return e ? atoi(e) : 0; }();
   return v;
 }
 

@@ -6,7 +6,8 @@
 // memory is visible.  Persistent kernels (all CTAs resident) release their dependents early with `griddepcontrol.launch_dependents`;
 // for multi-wave kernels the release is implicit when the last block exits.  Inside stream capture the attribute becomes a
 // programmatic edge of the CUDA graph.  `griddepcontrol.wait` is a no-op for a kernel launched without the attribute, so every
-// kernel carries it unconditionally; env LD_PDL=0 switches the attribute off (A/B aid).
+// kernel carries it unconditionally.  MEASURED SLOWER on the bench workload (see pdl_flag() in ld_engine.cu), hence OFF by default:
+// `ld_set_option(h, "pdl", 1)` or env LD_PDL=1 enables it.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdlib.h>
@@ -18,7 +19,7 @@ namespace ld {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// process-wide switch (ld_set_option "pdl"; initial value from env LD_PDL, default on); defined in ld_engine.cu
+// process-wide switch (ld_set_option "pdl"; initial value from env LD_PDL, default off); defined in ld_engine.cu
 int& pdl_flag();
 inline bool pdl_enabled() { return pdl_flag() != 0; }
 

@@ -31,6 +31,7 @@ for r in range(rounds + 1):
         out = gd.sample(cond, None, batch_size=B, mask=mask, min_max_val=wl.MRI_MIN_MAX, noise=tape)
         e1.record(); torch.cuda.synchronize()
         if r > 0: res[v].append(e0.elapsed_time(e1) / T)
+        if v in outs and r == rounds: print(f"{opt}={v}: max |diff| between two runs of the same variant:", float((outs[v] - out).abs().max()))
         outs[v] = out
 for v in vals:
     print(f"{opt}={v}: median {statistics.median(res[v]):.4f} ms/timestep  (min {min(res[v]):.4f}, max {max(res[v]):.4f}, n={len(res[v])})")
