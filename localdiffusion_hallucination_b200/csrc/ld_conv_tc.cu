@@ -56,6 +56,11 @@ namespace {
 #define LD_CONV_EG 2                   // epilogue warp-groups of the lean kernel (alternate tiles)
 #endif
 constexpr bool kUseMX = LD_CONV_MX != 0;
+// LD_EXP (bit mask, A/B builds for TIMING ONLY -- results are wrong when set): 1 no fence.proxy.async in the epilogue, 2 no named barriers,
+// 4 no staging st.shared, 8 no TMEM read, 16 no cp.async.bulk.wait_group
+#ifndef LD_EXP
+#define LD_EXP 0
+#endif
 constexpr int kTeamThreads = 128;      // one producer team = 4 warps
 constexpr int kTeams = 2;
 // Warp roles.  Full kernel (register-staging producers): warps 0-7 producers, 8-11 epilogue, 12 MMA, 13 weights.
@@ -240,7 +245,8 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
   constexpr int NMMA = MX ? 3 * NT : NT;  // UMMA N
   constexpr int B_STAGE = NMMA * KC * 2;
   // two accumulator stages of NT (dual: 2 NT) fp32 columns; NT in {32,64,128,256} -> power of two >= 64
-  const int NACC = MT == 2 ? p.nacc : 2;   // MT (template): tiles per streamed weight stage, see KParams::mt
+  const int NACC = p.nacc;   // accumulator stages: 2, 4 (narrow tiles: the MMA warp may run further ahead of the epilogue), or 1 (MT == 2, NT = 256)
+  const int LNACC = NACC == 4 ? 2 : (NACC == 2 ? 1 : 0);
   const uint32_t acc_cols = MX ? 4 * NT : (p.dual ? 2 * NT : NT);   // MX: 96 + 32 (fused 1x1)
   const uint32_t acc_stride = (uint32_t)MT * acc_cols, TM_COLS = (uint32_t)NACC * acc_stride;
   const int TAPSW = TAPS + (p.dual ? 1 : 0);   // weight stages per channel chunk
@@ -254,9 +260,9 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
   float* sacc_all = coef + p.coef_floats;             // [2][256] GroupNorm partial sums of each epilogue warp-group
   float* bias_s = sacc_all + 512;                         // [NT] bias of this CTA's output channels
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 2 * NT);   // bias_s[NT..2NT): bias of the fused 1x1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * SA_MAX + 2 * SB + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * SA_MAX + 2 * SB + 8);
   const uint32_t a_full = smem_u32(bars), a_empty = a_full + 8 * SA_MAX, b_full = a_empty + 8 * SA_MAX, b_empty = b_full + 8 * SB,
-                 acc_full = b_empty + 8 * SB, acc_empty = acc_full + 16, raw_full = acc_empty + 16;
+                 acc_full = b_empty + 8 * SB, acc_empty = acc_full + 32, raw_full = acc_empty + 32;
   const bool xf = LEAN && p.xf;      // TMA -> raw_full -> transform warps -> a_full -> MMA
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int SA = p.sa;
@@ -264,7 +270,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
   if (threadIdx.x == 0) {
     for (int i = 0; i < SA; ++i) { mbar_init(a_full + 8 * i, (p.tma_in && !xf) ? 1 : 4); mbar_init(a_empty + 8 * i, 1); mbar_init(raw_full + 8 * i, 1); }
     for (int i = 0; i < SB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, (MT == 2 && R::kEpiGroups == 2 && !xf) ? 256 : 128); }
+    for (int i = 0; i < 4; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, (MT == 2 && R::kEpiGroups == 2 && !xf) ? 256 : 128); }
     fence_barrier_init();
     if (p.tma_in) { tma_prefetch_desc(&p.map_a0); if (p.C1) tma_prefetch_desc(&p.map_a1); }
     if (p.tma_out) tma_prefetch_desc(&p.map_out);
@@ -520,10 +526,10 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
     for (; tw.tile < tw.end; tw.next(p), ++it_tile) {
       // accumulator of this tile: pair q = it_tile / MT, member mi; stage as = q % NACC, completion parity of its use
       const int q = MT == 2 ? it_tile >> 1 : it_tile, mi = MT == 2 ? (it_tile & 1) : 0;
-      const int as = NACC == 2 ? (q & 1) : 0;
-      const uint32_t aph = (uint32_t)(NACC == 2 ? (q >> 1) : q) & 1u;
-      // two warp-groups: group eg drains accumulator stage eg (mt == 1) or member eg of every pair (mt == 2)
-      if (two_groups && (MT == 2 ? mi : as) != eg) continue;
+      const int as = q & (NACC - 1);
+      const uint32_t aph = (uint32_t)(q >> LNACC) & 1u;
+      // two warp-groups: group eg drains the accumulator stages of its parity (mt == 1) or member eg of every pair (mt == 2)
+      if (two_groups && (MT == 2 ? mi : (as & 1)) != eg) continue;
       // mt == 2 with one warp-group: the stage goes back to the MMA warp after the last member of the pair
       const bool arrive_here = MT == 1 || two_groups || mi == 1 || it_tile == my_tiles - 1;
       const int img = tw.img;
@@ -550,11 +556,11 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
       // TMA store path: the store that read this staging buffer two tiles ago must have finished reading it
       // (ncu source view: with ONE staging buffer per warp-group 31 % of the stall samples sat here, waiting for the previous tile's
       // store to drain; every group now alternates between two buffers)
-      const int ob = two_groups ? (p.obuf == 4 ? 2 * eg + (n_mine & 1) : eg) : as;
+      const int ob = two_groups ? (p.obuf == 4 ? 2 * eg + (n_mine & 1) : eg) : (as & 1);
       ++n_mine;
       if (NT <= 64 && p.tma_out) {
-        if (etid == 0) { if (two_groups && p.obuf != 4) bulk_wait_group_read<0>(); else bulk_wait_group_read<1>(); }
-        named_bar(ebar, 128);
+        if (etid == 0 && !(LD_EXP & 16)) { if (two_groups && p.obuf != 4) bulk_wait_group_read<0>(); else bulk_wait_group_read<1>(); }
+        if (!(LD_EXP & 2)) named_bar(ebar, 128);
       }
       // staged output row: MX tiles are 8 x 14 pixels dense (patch columns 14, 15 of every row produce nothing)
       const int orow_i = MX ? (m >> 4) * G::TW + (m & 15) : m;
@@ -563,8 +569,8 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
       for (int j1 = 0; j1 < NT; j1 += 32) {
         uint32_t r32[32];
         if (!MX) {
-          tmem_ld32(trow + j1, r32);
-          tmem_ld_wait();
+          if (!(LD_EXP & 8)) { tmem_ld32(trow + j1, r32); tmem_ld_wait(); }
+          else { for (int j = 0; j < 32; ++j) r32[j] = (uint32_t)(m + j); }
           if (j1 + 32 == NT && !p.dual && arrive_here) {   // every TMEM read of this thread is complete: hand the stage back
             tc_fence_before();
             mbar_arrive(acc_empty + 8 * as);
@@ -621,7 +627,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
             // 16-byte chunk index XOR row bits = the TMA 64B / 128B swizzle pattern: conflict-free row-per-thread stores
             const int c0 = j0 >> 3;
             const int sw = NT == 32 ? ((orow_i >> 1) & 3) : (orow_i & 7);
-            if (!MX || (m & 15) < G::TW) {
+            if ((!MX || (m & 15) < G::TW) && !((LD_EXP & 4) && pk[0] != 0x12345678u)) {
               *reinterpret_cast<uint4*>(orow + ((c0 ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               *reinterpret_cast<uint4*>(orow + (((c0 + 1) ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
@@ -659,8 +665,8 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
         }
       }
       if (NT <= 64 && p.tma_out) {
-        fence_proxy_async();               // my generic-proxy writes are visible to the TMA unit
-        named_bar(ebar, 128);
+        if (!(LD_EXP & 1)) fence_proxy_async();               // my generic-proxy writes are visible to the TMA unit
+        if (!(LD_EXP & 2)) named_bar(ebar, 128);
         if (etid == 0) {
           if (!(p.dbg & 4)) {
             const uint32_t src = smem_u32(o_s + (size_t)ob * (128 * O_ROW));
@@ -674,8 +680,8 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
     }
     if (MT == 2 && two_groups && eg == 1 && (my_tiles & 1)) {
       // the last pair has one member (drained by group 0): this group still owes its 128 arrivals on the stage
-      const int q = my_tiles >> 1, as = NACC == 2 ? (q & 1) : 0;
-      mbar_wait(acc_full + 8 * as, (uint32_t)(NACC == 2 ? (q >> 1) : q) & 1u);
+      const int q = my_tiles >> 1, as = q & (NACC - 1);
+      mbar_wait(acc_full + 8 * as, (uint32_t)(q >> LNACC) & 1u);
       mbar_arrive(acc_empty + 8 * as);
     }
     if (p.stats && stat_img >= 0) flush_stats(stat_img);
@@ -698,8 +704,8 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
       for (int q = 0; it_tile < my_tiles; it_tile += MT, ++q) {
         // one iteration = one tile, or (mt == 2) a pair of consecutive tiles that share every streamed weight stage
         const int nm = (MT == 2 && it_tile + 1 < my_tiles) ? 2 : 1;
-        const int as = NACC == 2 ? (q & 1) : 0;
-        mbar_wait(acc_empty + 8 * as, ((uint32_t)(NACC == 2 ? (q >> 1) : q) & 1u) ^ 1u);
+        const int as = q & (NACC - 1);
+        mbar_wait(acc_empty + 8 * as, ((uint32_t)(q >> LNACC) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t dcol = tmem_base + (uint32_t)as * acc_stride;
         uint32_t acc = 0;
@@ -938,7 +944,7 @@ size_t layout(KParams& p, int sa, int nb_stages) {
   p.off_b = (int)off;
   off += (size_t)nb_stages * (MX ? 3 * NT : NT) * KC * 2;
   p.off_coef = (int)off;
-  off += (size_t)(p.coef_floats + 512 + 2 * NT) * 4 + (3 * SA_MAX + 2 * SB + 4) * 8 + 16;
+  off += (size_t)(p.coef_floats + 512 + 2 * NT) * 4 + (3 * SA_MAX + 2 * SB + 8) * 8 + 16;
   off = (off + 127) & ~(size_t)127;
   p.off_raw = (int)off;
   p.raw_stage = p.xf == 2 ? ((G::CH * G::RP * G::RR * 16 + 127) & ~127) : 0;
@@ -966,7 +972,16 @@ int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
   size_t smem = layout<NT, KS, KC>(p, sa, p.nb_stages);
   if (smem > (size_t)cfg().max_smem) { sa = 3; p.mt = 1; smem = layout<NT, KS, KC>(p, sa, p.nb_stages); }   // pairs need four activation stages
   p.nacc = (p.mt == 2 && NT == 256) ? 1 : 2;
-  const int tm_cols = MX ? 8 * NT : (p.mt == 2 ? p.nacc * 2 * NT : (p.dual ? 4 : 2) * NT);   // TMEM columns per CTA
+  {
+    // narrow tiles (NT <= 64) leave TMEM to spare: four accumulator stages let the MMA warp run two tiles ahead of each epilogue
+    // warp-group.  MEASURED: no effect on any variant of the 32-channel convolution (81 / 88 / 136 / 178 us with 2 or 4 stages,
+    // profiles/r3_conv_pipeline_ab.md) -- the launch is bound by shared-memory bandwidth, not by pipeline depth.  env LD_CONV_NACC=4 enables.
+    static int nacc_env = -1;
+    if (nacc_env < 0) { const char* e = getenv("LD_CONV_NACC"); nacc_env = e ? atoi(e) : 2; }
+    if (nacc_env == 4 && !MX && p.mt == 1 && NT <= 64 && (!p.dual || NT == 32) && p.tma_in && LD_CONV_EG == 2) p.nacc = 4;
+  }
+  const int tm_cols_raw = MX ? 8 * NT : (p.mt == 2 ? p.nacc * 2 * NT : (p.dual ? 2 : 1) * p.nacc * NT);
+  int tm_cols = 32; while (tm_cols < tm_cols_raw) tm_cols <<= 1;   // TMEM columns per CTA (allocations are powers of two >= 32)
   if (smem > (size_t)cfg().max_smem) return -1;
   if (p.tma_in && sa == 4) {   // a third co-resident CTA is worth more than a fourth activation stage
     const size_t smem3 = layout<NT, KS, KC>(p, 3, p.nb_stages);
@@ -990,6 +1005,23 @@ int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
       const int occ43 = smem43 ? (int)((size_t)cfg().max_smem_sm / (smem43 + 1024)) : 0;
       if (smem43 && (occ43 >= occ2 || occ43 >= cap)) { sa = 3; p.sa = 3; smem = smem43; }
       else { p.obuf = 2; layout<NT, KS, KC>(p, sa, p.nb_stages); }
+    }
+  }
+  {
+    // deeper activation ring while it costs no co-resident CTA (env LD_CONV_SA = 5 or 6).  MEASURED: 4, 5 and 6 stages give the same
+    // times on every variant (profiles/r3_conv_pipeline_ab.md), so the default stays at 4.
+    static int sa_cap = -1;
+    if (sa_cap < 0) { const char* e = getenv("LD_CONV_SA"); sa_cap = e ? atoi(e) : 4; if (sa_cap > SA_MAX) sa_cap = SA_MAX; }
+    const int cap = Roles<true>::kMinCtas < 512 / tm_cols ? Roles<true>::kMinCtas : 512 / tm_cols;
+    auto occ_of = [&](size_t b) { int o = (int)((size_t)cfg().max_smem_sm / (b + 1024)); return o > cap ? cap : o; };
+    if (p.tma_in && p.mt == 1) {
+      const int occ_now = occ_of(smem);
+      while (sa < sa_cap) {
+        const size_t s2 = layout<NT, KS, KC>(p, sa + 1, p.nb_stages);
+        if (s2 <= (size_t)cfg().max_smem && occ_of(s2) >= occ_now) { ++sa; smem = s2; }
+        else { layout<NT, KS, KC>(p, sa, p.nb_stages); break; }
+      }
+      p.sa = sa;
     }
   }
   // persistent grid: as many CTAs as are co-resident (registers allow two per SM; 2*NT of 512 TMEM columns each)
@@ -1223,7 +1255,9 @@ static bool build_params(const ConvTcW& w, const ConvTcArgs& a, KParams& p) {
     p.xf = (a.pro_ab && p.tma_in) ? 1 : 0;
     if (p.xf == 1) p.coef_floats = 2 * a.C0;
   }
-  p.tma_out = (!a.ps && map_out(&p.map_out, a.dst, a.N, a.H, a.W, w.Cout, w.ntile, a.ds ? 3 : w.ks, mx)) ? 1 : 0;
+  static int no_tma_out = -1;   // env LD_CONV_NO_TMA_OUT=1: direct 16-byte stores from registers instead of smem staging + TMA store (A/B aid)
+  if (no_tma_out < 0) { const char* e = getenv("LD_CONV_NO_TMA_OUT"); no_tma_out = e ? atoi(e) : 0; }
+  p.tma_out = (!a.ps && !no_tma_out && map_out(&p.map_out, a.dst, a.N, a.H, a.W, w.Cout, w.ntile, a.ds ? 3 : w.ks, mx)) ? 1 : 0;
   if (mx) {
     p.tiles_x = (a.W + 13) / 14; p.tiles_y = (a.H + 7) / 8;
     p.ntiles = a.N * p.tiles_x * p.tiles_y;

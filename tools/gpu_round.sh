@@ -46,10 +46,15 @@ if has ncu; then
   cap conv32_xf conv_tc_kernel 2 src python tools/gpu_conv_pro_one.py
   cap conv32_dual conv_tc_kernel 2 src python tools/gpu_conv_dual_one.py
   cap conv256 conv_tc_kernel 3 src python tools/gpu_conv_one.py 256 0 32 256 3 0 32
+  cap conv32_stats conv_tc_kernel 5 nosrc python tools/gpu_conv_variant_one.py 1
+  cap conv_up2 conv_tc_kernel 3 nosrc python tools/gpu_conv_one.py 64 0 256 32 3 1 32 3
   cap la_ctx la_ctx_kernel 1 src python tools/gpu_la_dbg.py 32 32 65536 2
   cap la_out la_out_kernel 1 src python tools/gpu_la_dbg.py 32 32 65536 2
+  cap la_out8 la_out_kernel 1 nosrc python tools/gpu_la_dbg.py 32 32 16384 2 8
   cap attn attn_tc_kernel 2 src python tools/gpu_attn_one.py 32 1024 4
   cap step step_kernel 3 nosrc python tools/gpu_step_one.py 16 256 0
+  cap knn knn_tc_kernel 1 nosrc python tools/gpu_knn_one.py
+  cap attn4096 attn_tc_kernel 1 nosrc python tools/gpu_attn_one.py 8 4096 8
   cap gn_apply gn_apply_bf16_fast 20 nosrc python tools/gpu_profile_ops.py 32 256 mri 2
   cap conv7 conv7_tc_kernel 1 nosrc python tools/gpu_profile_ops.py 32 256 mri 2
   ls -la $O/${TAG}_ncu_* | head -40
