@@ -53,10 +53,14 @@ namespace {
 #define LD_CONV_MX 0                   // merged-x geometry for 3x3 / 32-cout layers (see Geo): parity-green, not faster yet (epilogue bound); -DLD_CONV_MX=1 for A/B builds
 #endif
 #ifndef LD_CONV_EG
+#ifndef LD_CONV_SPLITLD
+#define LD_CONV_SPLITLD 0             // narrow tiles: accumulator read-out in 16-column halves (see the epilogue)
+#endif
 #define LD_CONV_EG 2                   // epilogue warp-groups of the lean kernel (alternate tiles)
 #endif
 constexpr bool kUseMX = LD_CONV_MX != 0;
-// LD_EXP (bit mask, A/B builds for TIMING ONLY -- results are wrong when set): 1 no fence.proxy.async in the epilogue, 2 no named barriers,
+// LD_EXP (bit mask, A/B builds for TIMING ONLY -- results are wrong when set): 32 no transform work, 64 no proxy fence after the transform,
+// 128 no register statistics; 1 no fence.proxy.async in the epilogue, 2 no named barriers,
 // 4 no staging st.shared, 8 no TMEM read, 16 no cp.async.bulk.wait_group
 #ifndef LD_EXP
 #define LD_EXP 0
@@ -99,6 +103,8 @@ struct alignas(64) KParams {
                                      // place (pro_ab), 2 expand the low-resolution patch of a nearest x2 up-sampled source
   int off_raw, raw_stage;            // xf == 2: ring of raw low-resolution patches (bytes)
   int obuf;                          // output staging buffers (TMA store path): 2, or 4 = two per epilogue warp-group
+  int xhelp;                         // xf == 1 with resident weights: warps 2 and 3 (weights issued once / idle) join the four transform warps
+  int regstats;                      // 1: narrow tiles keep the GroupNorm partial sums in registers (stats_acc); bit 1 (env LD_CONV_REGSTATS) also for dual launches
   int mt, nacc;                      // mt = 2: every streamed weight stage serves TWO consecutive tiles of the CTA (two accumulators);
                                      // nacc = accumulator stages (2, or 1 when two NT-wide accumulators already fill TMEM)
   int ds, ds_cs;                     // 2x2 stride-2 (pixel-unshuffle) conv run as a 1x1 over four strided TMA gathers; ds_cs = source channels
@@ -202,6 +208,46 @@ __device__ __forceinline__ uint4 pro_apply_h(uint4 v, const float (&a)[8], const
   return make_uint4(out[0], out[1], out[2], out[3]);
 }
 
+// In-place "normalise on load" of one landed activation stage by a team of NXW warps.  The stage is cut into pairs of 32-pixel blocks
+// of one 8-channel group; warp xw takes PP consecutive pairs (same channel group as long as possible: its coefficients stay in
+// registers).  Both 16-byte loads of a pair are issued before the arithmetic and nothing branches around them (clamped address,
+// predicated store), so the two dependency chains (LDS -> FFMA -> MUFU.TANH -> FFMA -> pack -> STS) overlap: ncu r3i showed the old
+// block-per-iteration loop, whose `if (inside)` bodies could not be interleaved, stalled on the LDS latency for 30 % of its samples.
+// Padding pixels (hardware zero fill) are not rewritten: they stay exactly zero.
+template <int NXW, class G>
+__device__ __forceinline__ void xf_stage(uint8_t* stage, const float* ca, const float* cb, int xw, int lane, bool interior, int ty0,
+                                         int tx0, int H, int W, int act) {
+  constexpr int NBLK = (G::HPIX + 31) / 32, HB = NBLK / 2, P = G::CH * HB, PP = P / NXW;
+  static_assert(NBLK % 2 == 0 && P % NXW == 0 && (HB - 1) * 64 + 31 < G::HPIX, "pair split of the halo patch");
+  float pa[8], pb[8];
+  int cur = -1;
+#pragma unroll 1
+  for (int i = 0; i < PP; ++i) {
+    const int pi = xw * PP + i, c8 = pi / HB, hp0 = (pi - c8 * HB) * 64 + lane, hp1 = hp0 + 32;
+    if (c8 != cur) {
+      const float4 a0 = *reinterpret_cast<const float4*>(ca + c8 * 8), a1 = *reinterpret_cast<const float4*>(ca + c8 * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(cb + c8 * 8), b1 = *reinterpret_cast<const float4*>(cb + c8 * 8 + 4);
+      pa[0] = a0.x; pa[1] = a0.y; pa[2] = a0.z; pa[3] = a0.w; pa[4] = a1.x; pa[5] = a1.y; pa[6] = a1.z; pa[7] = a1.w;
+      pb[0] = b0.x; pb[1] = b0.y; pb[2] = b0.z; pb[3] = b0.w; pb[4] = b1.x; pb[5] = b1.y; pb[6] = b1.z; pb[7] = b1.w;
+      cur = c8;
+    }
+    bool ok0 = true, ok1 = hp1 < G::HPIX;
+    if (!interior) {
+      const int hy0 = hp0 / G::PITCH, hx0 = hp0 - hy0 * G::PITCH, hy1 = hp1 / G::PITCH, hx1 = hp1 - hy1 * G::PITCH;
+      ok0 = (unsigned)(ty0 + hy0 - 1) < (unsigned)H && (unsigned)(tx0 + hx0 - 1) < (unsigned)W;
+      ok1 = ok1 && (unsigned)(ty0 + hy1 - 1) < (unsigned)H && (unsigned)(tx0 + hx1 - 1) < (unsigned)W;
+    }
+    uint8_t* col = stage + (size_t)c8 * G::LBO_TMA;
+    uint4* q0 = reinterpret_cast<uint4*>(col + hp0 * 16);
+    uint4* q1 = reinterpret_cast<uint4*>(col + (hp1 < G::HPIX ? hp1 : hp0) * 16);
+    uint4 v0 = *q0, v1 = *q1;
+    v0 = pro_apply_h(v0, pa, pb, act);
+    v1 = pro_apply_h(v1, pa, pb, act);
+    if (ok0) *q0 = v0;
+    if (ok1) *q1 = v1;
+  }
+}
+
 // per-warp partial GroupNorm sums of 16 consecutive channels held by each lane (one pixel per lane).  The NV = 2 * groups
 // values of a lane are reduced together: every butterfly step halves the number of live values (a lane keeps the half its
 // lane bit selects and sends the other), so NV values cost NV - 1 + log2(32 / NV) shuffles instead of 5 * NV.
@@ -235,7 +281,41 @@ __device__ __forceinline__ void stats_chunk(const float (&f)[16], bool valid, fl
   if ((lane & ((32 >> LOG) - 1)) == 0) atomicAdd(sacc + 2 * grp0 + (lane >> (5 - LOG)), v[0]);
 }
 
-template <int NT, int KS, int KC, bool LEAN, int MT = 1>
+// Register variant for narrow tiles (NT <= 64, at most 8 groups in the tile): every thread keeps the running sums of ITS pixel row over
+// all the tiles of an image; the warp reduces them once, when the tile walk leaves the image (stats_flush_regs).  ncu r3i: the per-tile
+// butterfly + shared-memory CAS loops of stats_chunk were ~250 of the ~500 instructions per warp and tile, and the single epilogue
+// warp-group of the normalise-on-load launches was busy 83 % of the time.  `j0` is a constant after unrolling: the indices are static.
+template <int CPG>
+__device__ __forceinline__ void stats_acc(const float (&f)[16], float (&racc)[16], int j0) {
+  constexpr int NG = 16 / CPG;                   // CPG in {4, 8, 16}
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPG; ++j) { const float x = f[g * CPG + j]; s += x; q = fmaf(x, x, q); }
+    const int gi = j0 / CPG + g;
+    racc[2 * gi] += s; racc[2 * gi + 1] += q;
+  }
+}
+// 16 values per lane -> value (lane >> 1), summed over the warp, in the even lanes; added to sacc[0 .. nv)
+__device__ __forceinline__ void stats_flush_regs(float (&racc)[16], float* sacc, int nv, int lane) {
+#pragma unroll
+  for (int st = 0; st < 4; ++st) {
+    const int off = 16 >> st, half = 8 >> st;
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? racc[i] : racc[i + half], keep = up ? racc[i + half] : racc[i];
+      racc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  const float v = racc[0] + __shfl_xor_sync(0xffffffffu, racc[0], 1);
+  if (!(lane & 1) && (lane >> 1) < nv) atomicAdd(sacc + (lane >> 1), v);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) racc[i] = 0.f;
+}
+
+template <int NT, int KS, int KC, bool LEAN, int MT = 1, bool RS = false>
 __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) conv_tc_kernel(const __grid_constant__ KParams p) {
   constexpr bool MX = kUseMX && KS == 3 && NT == 32;
   using G = Geo<KS, KC, MX>;
@@ -268,7 +348,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
   const int SA = p.sa;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < SA; ++i) { mbar_init(a_full + 8 * i, (p.tma_in && !xf) ? 1 : 4); mbar_init(a_empty + 8 * i, 1); mbar_init(raw_full + 8 * i, 1); }
+    for (int i = 0; i < SA; ++i) { mbar_init(a_full + 8 * i, (p.tma_in && !xf) ? 1 : (xf && p.xhelp ? 6 : 4)); mbar_init(a_empty + 8 * i, 1); mbar_init(raw_full + 8 * i, 1); }
     for (int i = 0; i < SB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
     for (int i = 0; i < 4; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, (MT == 2 && R::kEpiGroups == 2 && !xf) ? 256 : 128); }
     fence_barrier_init();
@@ -417,13 +497,25 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
         }
       }
     }
-  } else if (xf && warp >= kEpiWarp0 + 4 && warp < kEpiWarp0 + 8) {
+  } else if (xf && ((warp >= kEpiWarp0 + 4 && warp < kEpiWarp0 + 8) || (p.xhelp && (warp == kWWarp || warp == kWWarp + 1)))) {
     // ================================================================== in-place transform ============
-    // "normalise on load" for TMA-fed launches: the raw patch landed in the operand layout; every warp owns the 8-channel
-    // groups c8 = xw, xw + 4, .. (coefficients in registers), lanes walk the patch pixels (conflict-free 16-byte accesses).
+    // "normalise on load" for TMA-fed launches: the raw patch landed in the operand layout.  The stage is cut into units of (8-channel
+    // group c8, block of 32 patch pixels); transform warp xw of nxw takes the units xw, xw + nxw, ..: coefficients of the unit's channel
+    // group in registers, lanes on consecutive pixels (conflict-free 16-byte accesses).  With resident weights the weight warp (after
+    // issuing its one bulk copy) and the spare warp join the four transform warps (ncu r3i: the transform warps were busy 80 % of the
+    // launch and, once the GroupNorm sums of the epilogue moved into registers, the stage that bounds it).
     // Padding pixels (hardware zero fill) stay exactly zero, like the reference's conv padding of the normalised tensor.
-    const int xw = warp - (kEpiWarp0 + 4);
-    const int xtid = threadIdx.x - (kEpiWarp0 + 4) * 32;   // 0..127 inside the transform warp-group
+    if (warp == kWWarp && lane == 0) {   // helper mode implies resident weights: the whole filter, once
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)n_tile * p.nchunks * TAPSW * B_STAGE;
+      const int total = p.nchunks * TAPSW;
+      mbar_arrive_expect_tx(b_full, (uint32_t)total * B_STAGE);
+      for (int i = 0; i < total; ++i) bulk_g2s(smem_u32(b_s + (size_t)i * B_STAGE), wsrc + (size_t)i * B_STAGE, B_STAGE, b_full);
+    }
+    if (warp == kWWarp) pdl_wait();      // (skipped above for the weight warp) the coefficient table comes from an earlier kernel
+    __syncwarp();
+    const int nxw = p.xhelp ? 6 : 4;
+    const int xw = warp >= kEpiWarp0 + 4 ? warp - (kEpiWarp0 + 4) : 4 + (warp - kWWarp);
+    const int xtid = xw * 32 + lane;                       // 0 .. 32 * nxw - 1 inside the transform team
     int coef_img = -1;                                     // image whose coefficient table sits in shared memory (xf == 1)
     Ring ra;
     TileWalk twA, twB;
@@ -440,10 +532,10 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
         if (p.xf == 1 && img != coef_img) {
           // y = a x + b table of this image -> shared memory (ncu: fetched from global memory per stage, the loads were exposed for an L2
           // round trip on every tile).  For SiLU the table holds a / 2, b / 2: silu(y) = h + h tanh(h) with h = y / 2.
-          named_bar(5, 128);                               // every transform warp is done with the previous image's table
+          named_bar(5, 32 * nxw);                          // every transform warp is done with the previous image's table
           const float sc = p.pro_act == 1 ? 0.5f : 1.0f;
-          for (int i = xtid; i < 2 * p.C0; i += 128) coef[i] = __ldg(p.pro_ab + (size_t)img * 2 * p.C0 + i) * sc;
-          named_bar(5, 128);
+          for (int i = xtid; i < 2 * p.C0; i += 32 * nxw) coef[i] = __ldg(p.pro_ab + (size_t)img * 2 * p.C0 + i) * sc;
+          named_bar(5, 32 * nxw);
           coef_img = img;
         }
         mbar_wait(raw_full + 8 * ra.s, ra.ph);
@@ -463,29 +555,33 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
                   *reinterpret_cast<const uint4*>(rc + (((hy + 1) >> 1) * G::RP + ((hx + 1) >> 1)) * 16);
             }
           }
-        } else
-        for (int c8 = xw; c8 < G::CH; c8 += 4) {
-          const float4* ab = reinterpret_cast<const float4*>(coef + c * KC + c8 * 8);
-          const float4 a0 = ab[0], a1 = ab[1];
-          const float4* bb = reinterpret_cast<const float4*>(coef + p.C0 + c * KC + c8 * 8);
-          const float4 b0 = bb[0], b1 = bb[1];
-          const float pa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-          const float pb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-          uint8_t* col = stage + (size_t)c8 * G::LBO_TMA;
-#pragma unroll 2
-          for (int hp = lane; hp < G::HPIX; hp += 32) {
-            bool ok = interior;
-            if (!ok) {
-              const int hy = hp / G::PITCH, hx = hp - hy * G::PITCH;
-              ok = (unsigned)(ty0 + hy - 1) < (unsigned)p.H && (unsigned)(tx0 + hx - 1) < (unsigned)p.W;
-            }
-            if (ok) {
-              uint4* q = reinterpret_cast<uint4*>(col + hp * 16);
-              *q = pro_apply_h(*q, pa, pb, p.pro_act);
+        } else if (LD_EXP & 32) {   // timing experiment: no transform work
+        } else if constexpr (KS == 3 && !MX) {
+          if (p.xhelp) xf_stage<6, G>(stage, coef + c * KC, coef + p.C0 + c * KC, xw, lane, interior, ty0, tx0, p.H, p.W, p.pro_act);
+          else xf_stage<4, G>(stage, coef + c * KC, coef + p.C0 + c * KC, xw, lane, interior, ty0, tx0, p.H, p.W, p.pro_act);
+        } else {
+          for (int c8 = xw; c8 < G::CH; c8 += 4) {
+            const float4* ab = reinterpret_cast<const float4*>(coef + c * KC + c8 * 8);
+            const float4 a0 = ab[0], a1 = ab[1];
+            const float4* bb = reinterpret_cast<const float4*>(coef + p.C0 + c * KC + c8 * 8);
+            const float4 b0 = bb[0], b1 = bb[1];
+            const float pa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float pb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint8_t* col = stage + (size_t)c8 * G::LBO_TMA;
+            for (int hp = lane; hp < G::HPIX; hp += 32) {
+              bool ok = interior;
+              if (!ok) {
+                const int hy = hp / G::PITCH, hx = hp - hy * G::PITCH;
+                ok = (unsigned)(ty0 + hy - 1) < (unsigned)p.H && (unsigned)(tx0 + hx - 1) < (unsigned)p.W;
+              }
+              if (ok) {
+                uint4* q = reinterpret_cast<uint4*>(col + hp * 16);
+                *q = pro_apply_h(*q, pa, pb, p.pro_act);
+              }
             }
           }
         }
-        fence_proxy_async();
+        if (!(LD_EXP & 64)) fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(a_full + 8 * ra.s);
         ra.advance(SA);
@@ -511,7 +607,14 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
     // GroupNorm partial sums of the image being walked live in shared memory (sacc) and go to global memory, one double
     // atomic per (group, statistic), when the walk leaves the image
     int stat_img = -1;
+    // RS instantiation (host: p.regstats): narrow tile, GroupNorm statistics with 4 / 8 / 16 channels per group, at most 8 groups
+    constexpr bool kRegStats = RS && NT <= 64 && !MX;
+    constexpr bool reg_stats = kRegStats;
+    float racc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) racc[i] = 0.f;
     auto flush_stats = [&](int im) {
+      if (kRegStats && reg_stats) stats_flush_regs(racc, sacc, 2 * (NT / cpg), lane);
       named_bar(ebar, 128);
       const int ng2 = 2 * (NT / cpg > 0 ? NT / cpg : 1);
       if (etid < ng2) {
@@ -565,11 +668,14 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
       // staged output row: MX tiles are 8 x 14 pixels dense (patch columns 14, 15 of every row produce nothing)
       const int orow_i = MX ? (m >> 4) * G::TW + (m & 15) : m;
       uint8_t* orow = o_s + (size_t)ob * (128 * O_ROW) + (size_t)orow_i * O_ROW;
-#pragma unroll 1
+#pragma unroll (NT <= 64 ? 2 : 1)
       for (int j1 = 0; j1 < NT; j1 += 32) {
-        uint32_t r32[32];
-        if (!MX) {
-          if (!(LD_EXP & 8)) { tmem_ld32(trow + j1, r32); tmem_ld_wait(); }
+        // narrow tiles read the accumulator 16 columns at a time: the GroupNorm sums kept in registers across tiles (stats_acc) plus 32
+        // accumulator columns do not fit the 80-register budget of two co-resident CTAs (spills landed in the MMA warp's loop)
+        constexpr bool kSplitLd = LD_CONV_SPLITLD && NT <= 64 && !MX;
+        uint32_t r32[kSplitLd ? 16 : 32];
+        if (!MX && !kSplitLd) {
+          if (!(LD_EXP & 8)) { tmem_ld32(trow + j1, reinterpret_cast<uint32_t(&)[32]>(r32)); tmem_ld_wait(); }
           else { for (int j = 0; j < 32; ++j) r32[j] = (uint32_t)(m + j); }
           if (j1 + 32 == NT && !p.dual && arrive_here) {   // every TMEM read of this thread is complete: hand the stage back
             tc_fence_before();
@@ -580,6 +686,11 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
         for (int h = 0; h < 2; ++h) {
           const int j0 = j1 + 16 * h;
           float f[16];
+          if (kSplitLd) {
+            tmem_ld16(trow + j0, reinterpret_cast<uint32_t(&)[16]>(r32)); tmem_ld_wait();
+            if (h == 1 && j1 + 32 == NT && !p.dual && arrive_here) { tc_fence_before(); mbar_arrive(acc_empty + 8 * as); }
+          }
+          constexpr int rb = kSplitLd ? 0 : 16;   // offset of half 1 inside r32
           if (MX) {
             // out[lane] = D[lane][kx=0] + D[lane+1][kx=1] + D[lane+2][kx=2]: neighbours along the patch row are the next lanes
             uint32_t a0[16], a1[16], a2[16];
@@ -596,13 +707,20 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
               const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j0 + j);
-              f[j] = __uint_as_float(r32[16 * h + j]) + b4.x; f[j + 1] = __uint_as_float(r32[16 * h + j + 1]) + b4.y;
-              f[j + 2] = __uint_as_float(r32[16 * h + j + 2]) + b4.z; f[j + 3] = __uint_as_float(r32[16 * h + j + 3]) + b4.w;
+              f[j] = __uint_as_float(r32[rb * h + j]) + b4.x; f[j + 1] = __uint_as_float(r32[rb * h + j + 1]) + b4.y;
+              f[j + 2] = __uint_as_float(r32[rb * h + j + 2]) + b4.z; f[j + 3] = __uint_as_float(r32[rb * h + j + 3]) + b4.w;
             }
           }
           if (p.stats) {
             const int grp0 = (nbase + j0) / cpg - nbase / cpg;
             const bool valid = opix >= 0;
+            if (kRegStats && reg_stats) {
+              if (valid && !(LD_EXP & 128)) {
+                if (cpg == 4) stats_acc<4>(f, racc, j0);
+                else if (cpg == 8) stats_acc<8>(f, racc, j0);
+                else stats_acc<16>(f, racc, j0);
+              }
+            } else
             switch (cpg) {
               case 2: stats_chunk<2>(f, valid, sacc, grp0, lane); break;
               case 4: stats_chunk<4>(f, valid, sacc, grp0, lane); break;
@@ -913,6 +1031,8 @@ int configure_one() {
   if (cudaFuncSetAttribute(conv_tc_kernel<NT, KS, KC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg().max_smem) != cudaSuccess) return -1;
   if constexpr (NT >= 128) {
     if (cudaFuncSetAttribute(conv_tc_kernel<NT, KS, KC, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg().max_smem) != cudaSuccess) return -1;
+  } else {
+    if (cudaFuncSetAttribute(conv_tc_kernel<NT, KS, KC, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg().max_smem) != cudaSuccess) return -1;
   }
   return cudaFuncSetAttribute(conv_tc_kernel<NT, KS, KC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg().max_smem) == cudaSuccess ? 0 : -1;
 }
@@ -962,6 +1082,11 @@ int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
   p.obuf = 2;
   p.resident = layout<NT, KS, KC>(p, sa, total) <= limit ? 1 : 0;
   p.nb_stages = p.resident ? total : SB;
+  {
+    static int xh_env = -1;   // env LD_CONV_XHELP=0: four transform warps only (A/B aid)
+    if (xh_env < 0) { const char* e = getenv("LD_CONV_XHELP"); xh_env = e ? atoi(e) : 1; }
+    p.xhelp = (p.tma_in && p.xf == 1 && p.resident && KS == 3 && !MX && xh_env) ? 1 : 0;
+  }
   // Streamed weights: a stage (NT x KC) feeds KC/16 MMAs of NT/2 clocks each, i.e. the ring must take in 64 B/clk per SM and its
   // four stages cover ~1 us of MMA work -- less than the L2 latency under load (tensor pipe 58 % busy, ncu).  With mt = 2 every
   // stage serves two consecutive tiles of the CTA (two accumulators): half the weight traffic per FLOP, twice the cover.
@@ -972,6 +1097,14 @@ int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
   size_t smem = layout<NT, KS, KC>(p, sa, p.nb_stages);
   if (smem > (size_t)cfg().max_smem) { sa = 3; p.mt = 1; smem = layout<NT, KS, KC>(p, sa, p.nb_stages); }   // pairs need four activation stages
   p.nacc = (p.mt == 2 && NT == 256) ? 1 : 2;
+  {
+    static int rs_env = -1;   // 0 = per-tile butterfly everywhere, 1 = registers except dual launches (default: the dual launch measured 4 % slower with the
+                              // 16 extra live registers), 3 = registers everywhere
+    if (rs_env < 0) { const char* e = getenv("LD_CONV_REGSTATS"); rs_env = e ? atoi(e) : 1; }
+    const int cpg = p.stats ? p.Cout / p.stats_G : 0;
+    const bool fits = p.stats && p.tma_in && NT <= 64 && !MX && p.mt == 1 && (cpg == 4 || cpg == 8 || cpg == 16) && NT / cpg <= 8;
+    p.regstats = (fits && (p.dual ? (rs_env & 2) : (rs_env & 1))) ? 1 : 0;
+  }
   {
     // narrow tiles (NT <= 64) leave TMEM to spare: four accumulator stages let the MMA warp run two tiles ahead of each epilogue
     // warp-group.  MEASURED: no effect on any variant of the 32-channel convolution (81 / 88 / 136 / 178 us with 2 or 4 stages,
@@ -1049,6 +1182,9 @@ int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
   }
   if constexpr (NT >= 128) {
     if (lean && p.mt == 2) { launch_k(conv_tc_kernel<NT, KS, KC, true, 2>, dim3((unsigned)gx, (unsigned)ntiles_y), Roles<true>::kThreads, smem, s, true, p); return 1; }
+  }
+  if constexpr (NT <= 64) {
+    if (lean && p.regstats) { launch_k(conv_tc_kernel<NT, KS, KC, true, 1, true>, dim3((unsigned)gx, (unsigned)ntiles_y), Roles<true>::kThreads, smem, s, true, p); return 1; }
   }
   if (lean) launch_k(conv_tc_kernel<NT, KS, KC, true>, dim3((unsigned)gx, (unsigned)ntiles_y), Roles<true>::kThreads, smem, s, true, p);
   else launch_k(conv_tc_kernel<NT, KS, KC, false>, dim3((unsigned)gx, (unsigned)ntiles_y), Roles<false>::kThreads, smem, s, true, p);
