@@ -103,6 +103,9 @@ struct alignas(64) KParams {
                                      // place (pro_ab), 2 expand the low-resolution patch of a nearest x2 up-sampled source
   int off_raw, raw_stage;            // xf == 2: ring of raw low-resolution patches (bytes)
   int obuf;                          // output staging buffers (TMA store path): 2, or 4 = two per epilogue warp-group
+  int bias_const;                    // 1: single n-tile of <= 64 channels, bias (and the fused 1x1's) read from bias_c (constant bank operands:
+                                     // ncu r3q: the broadcast LDS.128 of the bias cost ~6 shared-memory wavefronts each next to the operand reads)
+  float bias_c[128];
   int xhelp;                         // xf == 1 with resident weights: warps 2 and 3 (weights issued once / idle) join the four transform warps
   int regstats;                      // 1: narrow tiles keep the GroupNorm partial sums in registers (stats_acc); bit 1 (env LD_CONV_REGSTATS) also for dual launches
   int mt, nacc;                      // mt = 2: every streamed weight stage serves TWO consecutive tiles of the CTA (two accumulators);
@@ -110,6 +113,10 @@ struct alignas(64) KParams {
   int ds, ds_cs;                     // 2x2 stride-2 (pixel-unshuffle) conv run as a 1x1 over four strided TMA gathers; ds_cs = source channels
   int ps;                            // > 0: pixel-shuffle output of the folded nearest-x2 + 3x3 convolution (ConvTcArgs::ps = real Cout)
   int a_stage, lbo16;                // activation stage pitch (bytes) and chunk stride (16-byte units)
+  int swz;                           // 1: TMA-fed stage = dense pixel rows of KC * 2 bytes, hardware-swizzled (64B for KC = 32, 128B for KC = 64):
+                                     // the TMA unit moves 64 / 128-byte rows instead of the 16-byte rows of the no-swizzle K-major image (which
+                                     // cost one shared-memory write cycle EACH: 720 per tile, as many as the operand reads of the 18 MMAs) and
+                                     // tcgen05.mma reads the shifted tap views through the same swizzle (absolute address bits; tests/micro/swz_view.cu)
   int off_a, off_b, off_coef;        // shared memory carve-up (bytes)
   // normalise-on-load prologue (GroupNorm affine [+ FiLM] + activation of the source tensor)
   const float* pro_ab;   // [N][2][C0]: scale then shift (gn_coef_kernel), or null
@@ -214,7 +221,9 @@ __device__ __forceinline__ uint4 pro_apply_h(uint4 v, const float (&a)[8], const
 // predicated store), so the two dependency chains (LDS -> FFMA -> MUFU.TANH -> FFMA -> pack -> STS) overlap: ncu r3i showed the old
 // block-per-iteration loop, whose `if (inside)` bodies could not be interleaved, stalled on the LDS latency for 30 % of its samples.
 // Padding pixels (hardware zero fill) are not rewritten: they stay exactly zero.
-template <int NXW, class G>
+// SWZ: the stage holds dense pixel rows of CH * 16 bytes, hardware-swizzled (KParams::swz): the 16-byte chunk of channel group c8 of the
+// pixel at absolute shared-memory address A sits at chunk c8 ^ ((A >> 7) & (CH - 1)) of its row.
+template <int NXW, class G, bool SWZ>
 __device__ __forceinline__ void xf_stage(uint8_t* stage, const float* ca, const float* cb, int xw, int lane, bool interior, int ty0,
                                          int tx0, int H, int W, int act) {
   constexpr int NBLK = (G::HPIX + 31) / 32, HB = NBLK / 2, P = G::CH * HB, PP = P / NXW;
@@ -237,9 +246,18 @@ __device__ __forceinline__ void xf_stage(uint8_t* stage, const float* ca, const 
       ok0 = (unsigned)(ty0 + hy0 - 1) < (unsigned)H && (unsigned)(tx0 + hx0 - 1) < (unsigned)W;
       ok1 = ok1 && (unsigned)(ty0 + hy1 - 1) < (unsigned)H && (unsigned)(tx0 + hx1 - 1) < (unsigned)W;
     }
-    uint8_t* col = stage + (size_t)c8 * G::LBO_TMA;
-    uint4* q0 = reinterpret_cast<uint4*>(col + hp0 * 16);
-    uint4* q1 = reinterpret_cast<uint4*>(col + (hp1 < G::HPIX ? hp1 : hp0) * 16);
+    const int hp1c = hp1 < G::HPIX ? hp1 : hp0;
+    uint4 *q0, *q1;
+    if (SWZ) {
+      constexpr int ROW = G::CH * 16;
+      const uint32_t sa = smem_u32(stage);
+      q0 = reinterpret_cast<uint4*>(stage + hp0 * ROW + ((c8 ^ (int)(((sa + hp0 * ROW) >> 7) & (G::CH - 1))) << 4));
+      q1 = reinterpret_cast<uint4*>(stage + hp1c * ROW + ((c8 ^ (int)(((sa + hp1c * ROW) >> 7) & (G::CH - 1))) << 4));
+    } else {
+      uint8_t* col = stage + (size_t)c8 * G::LBO_TMA;
+      q0 = reinterpret_cast<uint4*>(col + hp0 * 16);
+      q1 = reinterpret_cast<uint4*>(col + hp1c * 16);
+    }
     uint4 v0 = *q0, v1 = *q1;
     v0 = pro_apply_h(v0, pa, pb, act);
     v1 = pro_apply_h(v1, pa, pb, act);
@@ -402,13 +420,17 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
               if (KS == 3 && p.xf == 2)   // nearest x2 source (ddpm.py:116): the (TH/2+2) x (TW/2+2) low-resolution pixels under the halo patch
                 tma_load_5d(smem_u32(smem + p.off_raw + (size_t)ra.s * p.raw_stage), map, 0, tw.tx * (G::TW / 2) - 1, tw.ty * (G::TH / 2) - 1, cb8,
                             tw.img, fbar);
-              else if (KS == 3) tma_load_5d(dst, map, 0, tw.tx * G::TW - 1, tw.ty * G::TH - 1, cb8, tw.img, fbar);
-              else if (p.ds) {
+              else if (KS == 3) {
+                if (p.swz) tma_load_4d(dst, map, cb8 << 3, tw.tx * G::TW - 1, tw.ty * G::TH - 1, tw.img, fbar);
+                else tma_load_5d(dst, map, 0, tw.tx * G::TW - 1, tw.ty * G::TH - 1, cb8, tw.img, fbar);
+              } else if (p.ds) {
                 // chunk c covers channels [cbase % Cs, +KC) of unshuffle tap q = cbase / Cs = (p1, p2): every other pixel
                 // of the source starting at (2 ty + p1, 2 tx + p2) -- one strided TMA gather of 16 x 8 pixels
                 const int q = cbase / p.ds_cs, cq = cbase - q * p.ds_cs;
-                tma_load_5d(dst, map, 0, 2 * (tw.tx * 8) + (q & 1), 2 * (tw.ty * 16) + (q >> 1), cq >> 3, tw.img, fbar);
-              } else tma_load_3d(dst, map, 0, tw.tile * 128, cb8, fbar);
+                if (p.swz) tma_load_4d(dst, map, cq, 2 * (tw.tx * 8) + (q & 1), 2 * (tw.ty * 16) + (q >> 1), tw.img, fbar);
+                else tma_load_5d(dst, map, 0, 2 * (tw.tx * 8) + (q & 1), 2 * (tw.ty * 16) + (q >> 1), cq >> 3, tw.img, fbar);
+              } else if (p.swz) tma_load_2d(dst, map, cb8 << 3, tw.tile * 128, fbar);
+              else tma_load_3d(dst, map, 0, tw.tile * 128, cb8, fbar);
             } else {
               // development aid: complete the transaction without data
               asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(fbar), "r"(stage_bytes) : "memory");
@@ -556,10 +578,12 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
             }
           }
         } else if (LD_EXP & 32) {   // timing experiment: no transform work
-        } else if constexpr (KS == 3 && !MX) {
-          if (p.xhelp) xf_stage<6, G>(stage, coef + c * KC, coef + p.C0 + c * KC, xw, lane, interior, ty0, tx0, p.H, p.W, p.pro_act);
-          else xf_stage<4, G>(stage, coef + c * KC, coef + p.C0 + c * KC, xw, lane, interior, ty0, tx0, p.H, p.W, p.pro_act);
-        } else {
+        } else if (KS == 3 && !MX && p.swz) {
+          if constexpr (KS == 3 && !MX) {
+            if (p.xhelp) xf_stage<6, G, true>(stage, coef + c * KC, coef + p.C0 + c * KC, xw, lane, interior, ty0, tx0, p.H, p.W, p.pro_act);
+            else xf_stage<4, G, true>(stage, coef + c * KC, coef + p.C0 + c * KC, xw, lane, interior, ty0, tx0, p.H, p.W, p.pro_act);
+          }
+        } else {   // no-swizzle image (LD_CONV_NO_SWZ, 1x1): channel group per warp, lanes on pixels
           for (int c8 = xw; c8 < G::CH; c8 += 4) {
             const float4* ab = reinterpret_cast<const float4*>(coef + c * KC + c8 * 8);
             const float4 a0 = ab[0], a1 = ab[1];
@@ -705,6 +729,11 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
                      __shfl_down_sync(0xffffffffu, __uint_as_float(a2[j]), 2) + bias_s[j0 + j];
           } else {
 #pragma unroll
+            if (NT <= 64 && p.bias_const) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(r32[rb * h + j]) + p.bias_c[j0 + j];
+            } else
+#pragma unroll
             for (int j = 0; j < 16; j += 4) {
               const float4 b4 = *reinterpret_cast<const float4*>(bias_s + j0 + j);
               f[j] = __uint_as_float(r32[rb * h + j]) + b4.x; f[j + 1] = __uint_as_float(r32[rb * h + j + 1]) + b4.y;
@@ -762,7 +791,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
       }
       if (p.dual) {
         // second accumulator: the 1x1 res_conv of the same input tile (ddpm.py:198,212), direct 16-byte stores
-#pragma unroll 1
+#pragma unroll (NT <= 64 ? 2 : 1)
         for (int j1 = 0; j1 < NT; j1 += 32) {
           uint32_t r32[32];
           tmem_ld32(trow + DUALC + j1, r32);
@@ -774,9 +803,12 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
             for (int c = 0; c < 4; ++c) {
               uint32_t pk[4];
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                pk[j] = pack_bf16x2(__uint_as_float(r32[8 * c + 2 * j]) + bias_s[NT + j1 + 8 * c + 2 * j],
-                                    __uint_as_float(r32[8 * c + 2 * j + 1]) + bias_s[NT + j1 + 8 * c + 2 * j + 1]);
+              for (int j = 0; j < 4; ++j) {
+                const int cj = j1 + 8 * c + 2 * j;
+                const float b0 = (NT <= 64 && p.bias_const) ? p.bias_c[64 + (NT <= 64 ? cj : 0)] : bias_s[NT + cj];
+                const float b1 = (NT <= 64 && p.bias_const) ? p.bias_c[64 + (NT <= 64 ? cj + 1 : 0)] : bias_s[NT + cj + 1];
+                pk[j] = pack_bf16x2(__uint_as_float(r32[8 * c + 2 * j]) + b0, __uint_as_float(r32[8 * c + 2 * j + 1]) + b1);
+              }
               *reinterpret_cast<uint4*>(o2 + 8 * c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
           }
@@ -810,9 +842,14 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
     // are (lo, hi) register pairs and every tap / k-step only adds a small constant to `lo`.
     {
       constexpr uint32_t idesc = make_idesc(128, NMMA), idesc_d = make_idesc(128, NT);
-      const uint32_t a_hi = desc_hi(G::SBO), b_hi = desc_hi(128);
-      const uint32_t lbo16 = (uint32_t)p.lbo16;
-      const uint32_t a_lo0 = desc_lo(smem_u32(a_s), lbo16 << 4), b_lo0 = desc_lo(smem_u32(b_s), NMMA * 16),
+      // swizzled stage: pixel rows of KC * 2 bytes; 8-pixel core groups PITCH rows apart (3x3) or dense (1x1); a tap view starts
+      // (ky * PITCH + kx) rows into the patch, a k-step advances 32 bytes inside the swizzled row
+      constexpr uint32_t ROW16 = KC * 2 / 16;
+      const uint32_t a_hi = p.swz ? (desc_hi((KS == 3 ? G::PITCH : 8) * KC * 2) | (KC == 32 ? (4u << 29) : (2u << 29))) : desc_hi(G::SBO);
+      const uint32_t b_hi = desc_hi(128);
+      const uint32_t lbo16 = p.swz ? 1u : (uint32_t)p.lbo16;     // distance of the two 8-channel halves of a k-step is 2 * lbo16 (16-byte units)
+      const uint32_t tap16 = p.swz ? ROW16 : 1u;                 // one patch pixel in 16-byte units
+      const uint32_t a_lo0 = desc_lo(smem_u32(a_s), p.swz ? 16u : (lbo16 << 4)), b_lo0 = desc_lo(smem_u32(b_s), NMMA * 16),
                      bd_lo0 = desc_lo(smem_u32(b_s), NT * 16);   // fused-1x1 stage: [kc/8][NT][8] at the head of its slot
       const uint32_t a_stage16 = (uint32_t)p.a_stage >> 4;
       Ring ra, rb;
@@ -844,7 +881,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
                   const int ky = MX ? tap : tap / KS, kx = MX ? 0 : tap - ky * KS;
 #pragma unroll
                   for (int k = 0; k < KC / 16; ++k) {
-                    umma_bf16_lh(dcol, a_lo + (uint32_t)(ky * G::PITCH + kx) + (uint32_t)(2 * k) * lbo16, a_hi,
+                    umma_bf16_lh(dcol, a_lo + (uint32_t)(ky * G::PITCH + kx) * tap16 + (uint32_t)(2 * k) * lbo16, a_hi,
                                  b_lo + (uint32_t)(tap * (B_STAGE >> 4) + 2 * k * NMMA), b_hi, idesc, acc);
                     acc = 1;
                   }
@@ -853,7 +890,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
                   const uint32_t bd_lo = bd_lo0 + (uint32_t)((c * TAPSW + TAPS) * (B_STAGE >> 4));
 #pragma unroll
                   for (int k = 0; k < KC / 16; ++k)
-                    umma_bf16_lh(dcol + DUALC, a_lo + (uint32_t)(G::PITCH + 1) + (uint32_t)(2 * k) * lbo16, a_hi,
+                    umma_bf16_lh(dcol + DUALC, a_lo + (uint32_t)(G::PITCH + 1) * tap16 + (uint32_t)(2 * k) * lbo16, a_hi,
                                  bd_lo + (uint32_t)(2 * k * NT), b_hi, idesc_d, (c > 0 || k > 0) ? 1u : 0u);
                 }
               }
@@ -870,7 +907,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
               const uint32_t b_lo = b_lo0 + (uint32_t)(rb.s * (B_STAGE >> 4));
               const bool extra = tap == TAPS;   // fused 1x1 on the centre-tap view, second accumulator
               const int ky = extra ? KS / 2 : (MX ? tap : tap / KS), kx = extra ? KS / 2 : (MX ? 0 : tap - ky * KS);
-              const uint32_t a_t = a_lo + (uint32_t)(ky * G::PITCH + kx);
+              const uint32_t a_t = a_lo + (uint32_t)(ky * G::PITCH + kx) * tap16;
               if (elect_one()) {
                 if (extra) {
                   const uint32_t bd_lo = bd_lo0 + (uint32_t)(rb.s * (B_STAGE >> 4));
@@ -883,7 +920,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
                   for (int k = 0; k < KC / 16; ++k)
                     umma_bf16_lh(dcol, a_t + (uint32_t)(2 * k) * lbo16, a_hi, b_lo + (uint32_t)(2 * k * NMMA), b_hi, idesc, (acc | (uint32_t)k) ? 1u : 0u);
                   if (nm == 2) {   // same weight stage, second tile of the pair, second accumulator
-                    const uint32_t a_t1 = a_lo1 + (uint32_t)(ky * G::PITCH + kx);
+                    const uint32_t a_t1 = a_lo1 + (uint32_t)(ky * G::PITCH + kx) * tap16;
 #pragma unroll
                     for (int k = 0; k < KC / 16; ++k)
                       umma_bf16_lh(dcol + acc_cols, a_t1 + (uint32_t)(2 * k) * lbo16, a_hi, b_lo + (uint32_t)(2 * k * NMMA), b_hi, idesc,
@@ -982,6 +1019,31 @@ bool map_in_3x3(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int
   const cuuint32_t es[5] = {1, 1, 1, 1, 1};
   return f(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// Swizzled variants (KParams::swz): the same boxes with the channels of a pixel as ONE inner row of kc * 2 = 64 / 128 bytes, written
+// to shared memory through the 64B / 128B hardware swizzle.  [N][H][W][C] as (C, W, H, N), box (kc, PITCH, ROWS, 1).
+bool map_in_3x3_sw(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int kc, int pitch, int rows, int estride = 1) {
+  EncodeTiledFn f = encode_fn();
+  if (!f || (kc != 32 && kc != 64)) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)pitch, (cuuint32_t)rows, 1};
+  const cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+  return f(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// flattened pixels [M][C] as (C, M): box (kc, 128)
+bool map_in_1x1_sw(CUtensorMap* m, const void* ptr, long long M, int C, int kc) {
+  EncodeTiledFn f = encode_fn();
+  if (!f || (kc != 32 && kc != 64)) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)M};
+  const cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kc, 128};
+  const cuuint32_t es[2] = {1, 1};
+  return f(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // pixel-unshuffle gather: every other pixel of [N][H][W][C] in both directions -> 16 x 8 pixels per box
 bool map_in_ds(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int kc) {
@@ -1085,7 +1147,7 @@ int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
   {
     static int xh_env = -1;   // env LD_CONV_XHELP=0: four transform warps only (A/B aid)
     if (xh_env < 0) { const char* e = getenv("LD_CONV_XHELP"); xh_env = e ? atoi(e) : 1; }
-    p.xhelp = (p.tma_in && p.xf == 1 && p.resident && KS == 3 && !MX && xh_env) ? 1 : 0;
+    p.xhelp = (p.tma_in && p.xf == 1 && p.swz && p.resident && KS == 3 && !MX && xh_env) ? 1 : 0;
   }
   // Streamed weights: a stage (NT x KC) feeds KC/16 MMAs of NT/2 clocks each, i.e. the ring must take in 64 B/clk per SM and its
   // four stages cover ~1 us of MMA work -- less than the L2 latency under load (tensor pipe 58 % busy, ncu).  With mt = 2 every
@@ -1288,6 +1350,7 @@ int conv_tc_pack(const float* w, const float* bias, int Cin, int Cout, int ks, i
     if (cudaMalloc(slot, pk.size() * 2) != cudaSuccess) return -1;
     if (cudaMemcpy(*slot, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) return -1;
   }
+  for (int i = 0; i < 64; ++i) { out->bias_h[i] = (bias && i < Cout) ? bias[i] : 0.f; out->bias2_h[i] = (bias1 && i < Cout) ? bias1[i] : 0.f; }
   out->bias = nullptr;
   if (bias) {
     if (cudaMalloc(&out->bias, Cout * sizeof(float)) != cudaSuccess) return -1;
@@ -1365,6 +1428,8 @@ static bool build_params(const ConvTcW& w, const ConvTcArgs& a, KParams& p) {
   p.w = (const __nv_bfloat16*)(k64 ? w.w : w.w32); p.bias = w.bias; p.Cout = w.Cout;
   p.dst = (__nv_bfloat16*)a.dst; p.res = (const __nv_bfloat16*)a.res;
   p.dst2 = (__nv_bfloat16*)a.dst2; p.bias2 = w.bias2; p.dual = w.dual ? 1 : 0;
+  p.bias_const = (w.Cout == w.ntile && w.ntile <= 64) ? 1 : 0;
+  if (p.bias_const) { memcpy(p.bias_c, w.bias_h, 64 * sizeof(float)); memcpy(p.bias_c + 64, w.bias2_h, 64 * sizeof(float)); }
   p.M = (long long)a.N * a.H * a.W;
   p.pro_ab = a.pro_ab; p.pro_act = a.pro_act;
   p.coef_floats = 0;   // set below for the in-place normalise mode (xf == 1): the y = a x + b table of one image
@@ -1372,8 +1437,13 @@ static bool build_params(const ConvTcW& w, const ConvTcArgs& a, KParams& p) {
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("LD_CONV_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   // TMA activation loads whenever the source is read as stored (no up-sampling, no normalise-on-load)
   p.tma_in = 0;
+  p.swz = 0;
+  static int noswz = -1;   // env LD_CONV_NO_SWZ=1: the no-swizzle K-major stage image (16-byte TMA rows) everywhere (A/B aid)
+  if (noswz < 0) { const char* e = getenv("LD_CONV_NO_SWZ"); noswz = e ? atoi(e) : 0; }
+  const bool want_swz = !noswz && !mx;
   if (a.ds) {
-    p.tma_in = map_in_ds(&p.map_a0, a.src0, a.N, a.Hin, a.Win, a.C0, kc) ? 1 : 0;
+    if (want_swz && map_in_3x3_sw(&p.map_a0, a.src0, a.N, a.Hin, a.Win, a.C0, kc, 16, 32, 2)) { p.tma_in = 1; p.swz = 1; }
+    else p.tma_in = map_in_ds(&p.map_a0, a.src0, a.N, a.Hin, a.Win, a.C0, kc) ? 1 : 0;
   } else if (a.up) {
     // nearest x2 source: TMA fetches the low-resolution pixels under the halo patch, transform warps replicate them
     static int noup = -1;   // env LD_CONV_NO_XF=1: register-staging kernel instead (A/B aid)
@@ -1381,13 +1451,22 @@ static bool build_params(const ConvTcW& w, const ConvTcArgs& a, KParams& p) {
     const int rp = (mx ? 14 : 8) / 2 + 2, rr = (mx ? 8 : 16) / 2 + 2;
     if (!noup && a.H == 2 * a.Hin && a.W == 2 * a.Win && map_in_3x3(&p.map_a0, a.src0, a.N, a.Hin, a.Win, a.C0, kc, rp, rr)) { p.tma_in = 1; p.xf = 2; }
   } else {
-    bool ok = w.ks == 3 ? map_in_3x3(&p.map_a0, a.src0, a.N, a.Hin, a.Win, a.C0, kc, mx ? 16 : 10, mx ? 10 : 18) : map_in_1x1(&p.map_a0, a.src0, p.M, a.C0, kc);
-    if (ok && a.src1)
-      ok = w.ks == 3 ? map_in_3x3(&p.map_a1, a.src1, a.N, a.Hin, a.Win, a.C1, kc, mx ? 16 : 10, mx ? 10 : 18) : map_in_1x1(&p.map_a1, a.src1, p.M, a.C1, kc);
+    bool ok = false;
+    if (want_swz && (w.ks == 3 || !a.pro_ab)) {   // (the in-place normalise rewrite knows the swizzled rows for 3x3 only)
+      ok = w.ks == 3 ? map_in_3x3_sw(&p.map_a0, a.src0, a.N, a.Hin, a.Win, a.C0, kc, 10, 18) : map_in_1x1_sw(&p.map_a0, a.src0, p.M, a.C0, kc);
+      if (ok && a.src1)
+        ok = w.ks == 3 ? map_in_3x3_sw(&p.map_a1, a.src1, a.N, a.Hin, a.Win, a.C1, kc, 10, 18) : map_in_1x1_sw(&p.map_a1, a.src1, p.M, a.C1, kc);
+      p.swz = ok ? 1 : 0;
+    }
+    if (!ok) {
+      ok = w.ks == 3 ? map_in_3x3(&p.map_a0, a.src0, a.N, a.Hin, a.Win, a.C0, kc, mx ? 16 : 10, mx ? 10 : 18) : map_in_1x1(&p.map_a0, a.src0, p.M, a.C0, kc);
+      if (ok && a.src1)
+        ok = w.ks == 3 ? map_in_3x3(&p.map_a1, a.src1, a.N, a.Hin, a.Win, a.C1, kc, mx ? 16 : 10, mx ? 10 : 18) : map_in_1x1(&p.map_a1, a.src1, p.M, a.C1, kc);
+    }
     p.tma_in = ok ? 1 : 0;
     static int noxf = -1;   // env LD_CONV_NO_XF=1: normalise-on-load through the register-staging kernel (A/B aid)
     if (noxf < 0) { const char* e = getenv("LD_CONV_NO_XF"); noxf = e ? atoi(e) : 0; }
-    if (a.pro_ab && noxf) p.tma_in = 0;
+    if (a.pro_ab && noxf) { p.tma_in = 0; p.swz = 0; }
     p.xf = (a.pro_ab && p.tma_in) ? 1 : 0;
     if (p.xf == 1) p.coef_floats = 2 * a.C0;
   }
@@ -1462,6 +1541,8 @@ int conv_tc_launch(const ConvTcW& w, const ConvTcArgs& a, cudaStream_t s) {
     p = it->second.p;
     k64 = it->second.k64;
   }
+  // the key holds pointers only: the bias VALUES carried in the parameters always come from the weights of this call
+  if (p.bias_const) { memcpy(p.bias_c, w.bias_h, 64 * sizeof(float)); memcpy(p.bias_c + 64, w.bias2_h, 64 * sizeof(float)); }
   if (a.ds && !p.tma_in) return -1;
   const int ny = w.Cout / w.ntile;
   if (w.ks == 3) return k64 ? launch_nt<3, 64>(w.ntile, p, ny, s) : launch_nt<3, 32>(w.ntile, p, ny, s);

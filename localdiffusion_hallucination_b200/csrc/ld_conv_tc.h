@@ -13,6 +13,7 @@ struct ConvTcW {
   void* w = nullptr;     // bf16, [n_tile][cchunk][tap][kc/8][ntile][8] with kc = 64 (null if Cin % 64)
   void* w32 = nullptr;   // same with kc = 32 (used when a concat source is not a multiple of 64 channels)
   float* bias = nullptr; // fp32 [Cout] or null
+  float bias_h[64] = {}, bias2_h[64] = {};   // host copies for Cout <= 64: they travel in the kernel parameters (constant bank)
   // dual packing: every channel chunk carries a tenth stage, the 1x1 res_conv (ddpm.py:198) of the same input, whose
   // product with the centre-tap view goes to a second accumulator and a second output tensor (ConvTcArgs::dst2)
   bool dual = false;

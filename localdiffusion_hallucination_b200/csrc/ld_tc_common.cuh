@@ -113,6 +113,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 __device__ __forceinline__ void tma_prefetch_desc(const void* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst_smem),
+               "l"(map), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const void* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst_smem),
+               "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const void* map, int c0, int c1, int c2, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst_smem),
                "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
