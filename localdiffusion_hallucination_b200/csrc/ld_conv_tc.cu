@@ -215,6 +215,18 @@ __device__ __forceinline__ uint4 pro_apply_h(uint4 v, const float (&a)[8], const
   return make_uint4(out[0], out[1], out[2], out[3]);
 }
 
+// SiLU variant with the coefficients pre-halved, bf16 pairs unpacked with one ALU op per element (low half: shift, high half: mask)
+__device__ __forceinline__ uint4 pro_apply_silu_h(uint4 v, const float (&a)[8], const float (&b)[8]) {
+  uint32_t in[4] = {v.x, v.y, v.z, v.w}, out[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float h0 = fmaf(__uint_as_float(in[j] << 16), a[2 * j], b[2 * j]);
+    const float h1 = fmaf(__uint_as_float(in[j] & 0xffff0000u), a[2 * j + 1], b[2 * j + 1]);
+    out[j] = pack_bf16x2(fmaf(h0, tanh_approx(h0), h0), fmaf(h1, tanh_approx(h1), h1));
+  }
+  return make_uint4(out[0], out[1], out[2], out[3]);
+}
+
 // In-place "normalise on load" of one landed activation stage by a team of NXW warps.  The stage is cut into pairs of 32-pixel blocks
 // of one 8-channel group; warp xw takes PP consecutive pairs (same channel group as long as possible: its coefficients stay in
 // registers).  Both 16-byte loads of a pair are issued before the arithmetic and nothing branches around them (clamped address,
@@ -225,7 +237,7 @@ __device__ __forceinline__ uint4 pro_apply_h(uint4 v, const float (&a)[8], const
 // pixel at absolute shared-memory address A sits at chunk c8 ^ ((A >> 7) & (CH - 1)) of its row.
 template <int NXW, class G, bool SWZ>
 __device__ __forceinline__ void xf_stage(uint8_t* stage, const float* ca, const float* cb, int xw, int lane, bool interior, int ty0,
-                                         int tx0, int H, int W, int act) {
+                                         int tx0, int H, int W) {
   constexpr int NBLK = (G::HPIX + 31) / 32, HB = NBLK / 2, P = G::CH * HB, PP = P / NXW;
   static_assert(NBLK % 2 == 0 && P % NXW == 0 && (HB - 1) * 64 + 31 < G::HPIX, "pair split of the halo patch");
   float pa[8], pb[8];
@@ -259,8 +271,8 @@ __device__ __forceinline__ void xf_stage(uint8_t* stage, const float* ca, const 
       q1 = reinterpret_cast<uint4*>(col + hp1c * 16);
     }
     uint4 v0 = *q0, v1 = *q1;
-    v0 = pro_apply_h(v0, pa, pb, act);
-    v1 = pro_apply_h(v1, pa, pb, act);
+    v0 = pro_apply_silu_h(v0, pa, pb);   // SiLU only (every ResnetBlock): other activations take the generic loop of the caller
+    v1 = pro_apply_silu_h(v1, pa, pb);
     if (ok0) *q0 = v0;
     if (ok1) *q1 = v1;
   }
@@ -578,13 +590,14 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
             }
           }
         } else if (LD_EXP & 32) {   // timing experiment: no transform work
-        } else if (KS == 3 && !MX && p.swz) {
+        } else if (KS == 3 && !MX && p.swz && p.pro_act == 1) {
           if constexpr (KS == 3 && !MX) {
-            if (p.xhelp) xf_stage<6, G, true>(stage, coef + c * KC, coef + p.C0 + c * KC, xw, lane, interior, ty0, tx0, p.H, p.W, p.pro_act);
-            else xf_stage<4, G, true>(stage, coef + c * KC, coef + p.C0 + c * KC, xw, lane, interior, ty0, tx0, p.H, p.W, p.pro_act);
+            if (p.xhelp) xf_stage<6, G, true>(stage, coef + c * KC, coef + p.C0 + c * KC, xw, lane, interior, ty0, tx0, p.H, p.W);
+            else xf_stage<4, G, true>(stage, coef + c * KC, coef + p.C0 + c * KC, xw, lane, interior, ty0, tx0, p.H, p.W);
           }
-        } else {   // no-swizzle image (LD_CONV_NO_SWZ, 1x1): channel group per warp, lanes on pixels
-          for (int c8 = xw; c8 < G::CH; c8 += 4) {
+        } else {   // other activations (the once-per-call conditional encoder), no-swizzle image, 1x1: channel group per warp, lanes on pixels
+          const uint32_t sa = smem_u32(stage);
+          for (int c8 = xw; c8 < G::CH; c8 += nxw) {
             const float4* ab = reinterpret_cast<const float4*>(coef + c * KC + c8 * 8);
             const float4 a0 = ab[0], a1 = ab[1];
             const float4* bb = reinterpret_cast<const float4*>(coef + p.C0 + c * KC + c8 * 8);
@@ -600,6 +613,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
               }
               if (ok) {
                 uint4* q = reinterpret_cast<uint4*>(col + hp * 16);
+                if (p.swz) q = reinterpret_cast<uint4*>(stage + hp * (G::CH * 16) + ((c8 ^ (int)(((sa + hp * (G::CH * 16)) >> 7) & (G::CH - 1))) << 4));
                 *q = pro_apply_h(*q, pa, pb, p.pro_act);
               }
             }
@@ -1472,7 +1486,14 @@ static bool build_params(const ConvTcW& w, const ConvTcArgs& a, KParams& p) {
   }
   static int no_tma_out = -1;   // env LD_CONV_NO_TMA_OUT=1: direct 16-byte stores from registers instead of smem staging + TMA store (A/B aid)
   if (no_tma_out < 0) { const char* e = getenv("LD_CONV_NO_TMA_OUT"); no_tma_out = e ? atoi(e) : 0; }
-  p.tma_out = (!a.ps && !no_tma_out && map_out(&p.map_out, a.dst, a.N, a.H, a.W, w.Cout, w.ntile, a.ds ? 3 : w.ks, mx)) ? 1 : 0;
+  // Output path of narrow tiles: staging in shared memory + one TMA store per tile, or 16-byte stores straight from the accumulator
+  // registers.  Shared-memory bandwidth is what bounds these launches (operand reads of the MMAs + every other access), so the direct
+  // path wins where the epilogue has registers to spare: launches without statistics and dual launches (65 vs 71 us, 132 vs 146 us at
+  // 32x256x256); with the register statistics it loses (74 vs 69 us, 121 vs 111 us).  env LD_CONV_DIRECT: 0 never, 1 (default) that rule, 2 always.
+  static int direct = -1;
+  if (direct < 0) { const char* e = getenv("LD_CONV_DIRECT"); direct = e ? atoi(e) : 1; }
+  const bool go_direct = direct == 2 || (direct == 1 && (!a.stats || w.dual));
+  p.tma_out = (!a.ps && !no_tma_out && !go_direct && map_out(&p.map_out, a.dst, a.N, a.H, a.W, w.Cout, w.ntile, a.ds ? 3 : w.ks, mx)) ? 1 : 0;
   if (mx) {
     p.tiles_x = (a.W + 13) / 14; p.tiles_y = (a.H + 7) / 8;
     p.ntiles = a.N * p.tiles_x * p.tiles_y;

@@ -41,8 +41,9 @@ cap() {  # cap NAME REGEX SKIP [source] -- cmd...
     tail -3 $rep.log
   fi
 }
-if has ncuxf; then   # only the normalise-on-load variant, with source
+if has ncuxf; then   # only the normalise-on-load and plain variants, with source
   cap conv32_xf conv_tc_kernel 2 src python tools/gpu_conv_pro_one.py
+  cap conv32_plain conv_tc_kernel 3 src python tools/gpu_conv_one.py 32 0 256 32 3 0 32
 fi
 if has ncu; then
   cap conv32_plain conv_tc_kernel 3 src python tools/gpu_conv_one.py 32 0 256 32 3 0 32
