@@ -10,6 +10,8 @@ struct Conv7TcW {
   int Cout = 0;
   void* w = nullptr;      // bf16 [16 chunks][Cout][8]: K = [49 taps + pad | 49 taps + pad]
   float* bias = nullptr;  // fp32 [Cout] or null
+  void* wt = nullptr;     // bf16 [7 ky][2][256 n][8]: the banded (Toeplitz) form of every filter row (see ld_conv7_tc.cu)
+  float bias_h[64] = {};  // host copy: travels in the kernel parameters
 };
 
 // host weights fp32 [49 taps][Cout]; leaves ready == false for unsupported widths

@@ -138,6 +138,11 @@ __device__ __forceinline__ void tma_store_2d(const void* map, int c0, int c1, ui
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(src_smem)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const void* map, int c0, int c1, int c2, uint32_t src_smem) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2),
+               "r"(src_smem)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const void* map, int c0, int c1, int c2, int c3, uint32_t src_smem) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2),
                "r"(c3), "r"(src_smem)

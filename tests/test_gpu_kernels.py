@@ -254,7 +254,8 @@ def test_flash_attention_matches_torch(N, n, heads):
     assert util.rel_err(out, ref) < 1e-2
 
 
-@pytest.mark.parametrize("N,H,W,Cout", [(2, 32, 32, 32), (1, 20, 28, 32), (3, 64, 64, 64), (1, 256, 256, 32)])
+@pytest.mark.parametrize("N,H,W,Cout", [(2, 32, 32, 32), (1, 20, 28, 32), (3, 64, 64, 64), (1, 256, 256, 32), (2, 300, 36, 64),
+                                        (1, 18, 30, 32)])   # W % 4 != 0: the im2col form
 def test_init_conv7_matches_torch(N, H, W, Cout):
     """7x7 single-channel init_conv (ddpm.py:319) on tcgen05: the fp32 state enters as bf16 hi + lo, weights as bf16."""
     lib = _lib.lib()
