@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the stand-alone probes of the dominant kernel (launch-list captures)")
     a = ap.parse_args()
     c = CONFIGS[a.config]
     a.model = c["model"]
@@ -298,7 +299,7 @@ def run_ours(a):
                                "definition": "sum over layers of max(flops/sustained bf16 peak, min bytes/measured HBM bandwidth), "
                                              "layer table in localdiffusion_hallucination_b200/workload.py (SURVEY.md 8d)"},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
-            "roofline": dominant_kernel_roofline(lib, dev, a, hbm, src),
+            "roofline": None if a.no_roofline else dominant_kernel_roofline(lib, dev, a, hbm, src),
             "peaks": {"hbm_gbs": hbm, "bf16_tflops_burst": tf_burst, "bf16_tflops_sustained": tf_sus, "source": src},
         }
         if world == 1 and not a.no_cpu_baseline:

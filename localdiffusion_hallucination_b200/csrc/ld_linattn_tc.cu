@@ -429,36 +429,42 @@ __global__ void __launch_bounds__(kThreads, CtxCfg<C>::CTAS) la_ctx_kernel(const
 __global__ void __launch_bounds__(256) la_fold_kernel(const float* __restrict__ Z, const float* __restrict__ ksum,
                                                       const float* __restrict__ Ut, __nv_bfloat16* __restrict__ Mn, int C,
                                                       unsigned int* __restrict__ flag) {
-  extern __shared__ float zs[];      // [32 d][C]: Z[(h,d)][c] * 32^-0.5 / ksum[(h,d)]
-  const int h = blockIdx.x, n = blockIdx.y, hid = (int)gridDim.x * 32;
+  extern __shared__ float zs[];      // [32 d][C]: Z[(h,d)][c] * 32^-0.5 / ksum[(h,d)]; then the 32-column slice of U_h this block needs, [C c][32 c']
+  const int h = blockIdx.x, n = blockIdx.y, cz = blockIdx.z, hid = (int)gridDim.x * 32;
   if (threadIdx.x == 0) pdl_trigger();
+  const float* u = Ut + (size_t)h * C * C + cz * 32;
+  float* us = zs + 32 * C;
+  const int lane = threadIdx.x & 31, dq = threadIdx.x >> 5;     // thread = (c' = 32 cz + lane, 4 consecutive d)
+  for (int c = dq; c < C; c += 8) us[c * 32 + lane] = u[(size_t)c * C + lane];   // constants: before the wait on pass A
   pdl_wait();
-  for (int i = threadIdx.x; i < 32 * C; i += 256) {
-    const int d = i / C;
-    const float ks = ksum[(size_t)n * hid + h * 32 + d];
-    if (i % C == 0 && !(ks > 1e-30f) && flag) atomicAdd(flag, 1u);
-    zs[i] = Z[((size_t)n * hid + h * 32) * C + i] * 0.17677669529663687f / ks;
+  __shared__ float inv[32];
+  if (threadIdx.x < 32) {
+    const float ks = ksum[(size_t)n * hid + h * 32 + threadIdx.x];
+    if (cz == 0 && !(ks > 1e-30f) && flag) atomicAdd(flag, 1u);
+    inv[threadIdx.x] = 0.17677669529663687f / ks;
   }
   __syncthreads();
-  const float* u = Ut + (size_t)h * C * C;
-  __nv_bfloat16* dst = Mn + (size_t)n * hid * C;
-  // thread -> (c', group of 8 d): consecutive threads take consecutive c' (coalesced rows of Ut)
-  for (int i = threadIdx.x; i < 4 * C; i += 256) {
-    const int cp = i % C, dg = i / C;
-    float acc[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const float uu = u[(size_t)c * C + cp];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = fmaf(uu, zs[(dg * 8 + k) * C + c], acc[k]);
-    }
-    // (h,d) = j: chunk j>>3 = h*4 + dg, position j&7 = k  -> 16 contiguous bytes
-    uint32_t o[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) o[k] = pack_bf16x2(acc[2 * k], acc[2 * k + 1]);
-    *reinterpret_cast<uint4*>(dst + (size_t)(h * 4 + dg) * (C * 8) + cp * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  {
+    const float* zsrc = Z + ((size_t)n * hid + h * 32) * C;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < 32 * C; i += 256) zs[i] = zsrc[i] * inv[i / C];   // independent loads: the scale no longer sits between them
   }
+  __syncthreads();
+  // One block per (head, image, 32 output channels c'): 256 threads = 32 c' x 8 groups of 4 d.  Rows of the U slice are read
+  // conflict-free, Z is a broadcast.  (The first version gave one block all C output channels with U read from global memory inside
+  // the c loop: 34 us per launch at C = 128, 15 us at C = 32.)
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* zr = zs + (dq * 4) * C;
+#pragma unroll 8
+  for (int c = 0; c < C; ++c) {
+    const float uu = us[c * 32 + lane];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = fmaf(uu, zr[k * C + c], acc[k]);
+  }
+  // (h,d) = j: chunk j>>3 = h*4 + (dq >> 1), positions (dq & 1) * 4 + k  -> 8 contiguous bytes
+  __nv_bfloat16* dst = Mn + (size_t)n * hid * C;
+  *reinterpret_cast<uint2*>(dst + (size_t)(h * 4 + (dq >> 1)) * (C * 8) + (cz * 32 + lane) * 8 + (dq & 1) * 4) =
+      make_uint2(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]));
 }
 
 // ================================================================================================
@@ -796,7 +802,7 @@ int launch_c(const LinAttnTcW& w, const LinAttnTcArgs& a, cudaStream_t s) {
   CtxParams cp{(const __nv_bfloat16*)a.x, (const __nv_bfloat16*)w.wk, w.kb2, a.Z, a.ksum, a.HW, slA, HG};
   static int only = -1; if (only < 0) { const char* e = getenv("LD_LA_ONLY"); only = e ? atoi(e) : 0; }   // debug: 1 = pass A only, 2 = pass B only
   if (only != 2) launch_k(la_ctx_kernel<C>, dim3(slA, a.N, HG), dim3(kThreads), CtxCfg<C>::SMEM, s, true, cp);
-  launch_k(la_fold_kernel, dim3(4 * HG, a.N), dim3(256), 32 * C * sizeof(float), s, true, (const float*)a.Z, (const float*)a.ksum, (const float*)w.Ut,
+  launch_k(la_fold_kernel, dim3(4 * HG, a.N, C / 32), dim3(256), 64 * C * sizeof(float), s, true, (const float*)a.Z, (const float*)a.ksum, (const float*)w.Ut,
            (__nv_bfloat16*)a.Mn, C, a.flag);
   OutParams op{(const __nv_bfloat16*)a.x, (const __nv_bfloat16*)w.wq, (const __nv_bfloat16*)a.Mn, w.bout, w.g2,
                (__nv_bfloat16*)a.out, a.HW, slB, w.q_use_max, flatB ? 1 : 0, a.N};

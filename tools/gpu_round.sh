@@ -45,6 +45,9 @@ if has ncuxf; then   # only the normalise-on-load and plain variants, with sourc
   cap conv32_xf conv_tc_kernel 2 src python tools/gpu_conv_pro_one.py
   cap conv32_plain conv_tc_kernel 3 src python tools/gpu_conv_one.py 32 0 256 32 3 0 32
 fi
+if has ncu7; then   # only the init conv
+  cap conv7 conv7_ 1 nosrc python tools/gpu_profile_ops.py 32 256 mri 2
+fi
 if has ncu; then
   cap conv32_plain conv_tc_kernel 3 src python tools/gpu_conv_one.py 32 0 256 32 3 0 32
   cap conv32_xf conv_tc_kernel 2 src python tools/gpu_conv_pro_one.py
@@ -60,12 +63,12 @@ if has ncu; then
   cap knn knn_tc_kernel 1 nosrc python tools/gpu_knn_one.py
   cap attn4096 attn_tc_kernel 1 nosrc python tools/gpu_attn_one.py 8 4096 8
   cap gn_apply gn_apply_bf16_fast 20 nosrc python tools/gpu_profile_ops.py 32 256 mri 2
-  cap conv7 conv7_tc_kernel 1 nosrc python tools/gpu_profile_ops.py 32 256 mri 2
+  cap conv7 conv7_ 1 nosrc python tools/gpu_profile_ops.py 32 256 mri 2
   ls -la $O/${TAG}_ncu_* | head -40
 fi
 if has launches; then
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${TAG}_launches.csv \
-    python bench.py --steps 1 --warmup 0 --timesteps 3 --no-cpu-baseline --no-e2e > $O/${TAG}_launches.log 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2400 --csv --log-file $O/${TAG}_launches.csv \
+    python bench.py --steps 1 --warmup 0 --timesteps 12 --no-cpu-baseline --no-e2e --no-roofline > $O/${TAG}_launches.log 2>&1
   python profiles/summarize_launches.py $O/${TAG}_launches.csv > $O/${TAG}_launch_shares.md 2>&1
 fi
 if has bench; then
