@@ -106,6 +106,8 @@ struct alignas(64) KParams {
   int bias_const;                    // 1: single n-tile of <= 64 channels, bias (and the fused 1x1's) read from bias_c (constant bank operands:
                                      // ncu r3q: the broadcast LDS.128 of the bias cost ~6 shared-memory wavefronts each next to the operand reads)
   float bias_c[128];
+  int rot;                           // streamed weights: CTA b walks the taps of a chunk starting at tap b % 9 -- the CTAs of a launch no longer
+                                     // ask the L2 for the same 32 KB weight stage at the same moment (the ring is latency x depth bound)
   int xhelp;                         // xf == 1 with resident weights: warps 2 and 3 (weights issued once / idle) join the four transform warps
   int regstats;                      // 1: narrow tiles keep the GroupNorm partial sums in registers (stats_acc); bit 1 (env LD_CONV_REGSTATS) also for dual launches
   int mt, nacc;                      // mt = 2: every streamed weight stage serves TWO consecutive tiles of the CTA (two accumulators);
@@ -213,6 +215,14 @@ __device__ __forceinline__ uint4 pro_apply_h(uint4 v, const float (&a)[8], const
     out[j] = pack_bf16x2(y0, y1);
   }
   return make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+// The whole packed filter of a CTA in as few bulk copies as possible: a cp.async.bulk costs its issuing thread ~367 clk whatever its size
+// (tests/micro/tma_rate.cu: 2 KB .. 32 KB pieces all take 367 clk each, 5.6 .. 89 B/clk) -- one copy per 2 KB tap stage kept the first
+// MMA of every 32-channel launch waiting for 18 .. 40 of them (3 .. 7 us)
+__device__ __forceinline__ void resident_weights(uint32_t dst, const uint8_t* src, uint32_t bytes, uint32_t bar) {
+  constexpr uint32_t kPiece = 128 * 1024;
+  for (uint32_t o = 0; o < bytes; o += kPiece) bulk_g2s(dst + o, src + o, bytes - o < kPiece ? bytes - o : kPiece, bar);
 }
 
 // SiLU variant with the coefficients pre-halved, bf16 pairs unpacked with one ALU op per element (low half: shift, high half: mask)
@@ -543,7 +553,7 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.w) + (size_t)n_tile * p.nchunks * TAPSW * B_STAGE;
       const int total = p.nchunks * TAPSW;
       mbar_arrive_expect_tx(b_full, (uint32_t)total * B_STAGE);
-      for (int i = 0; i < total; ++i) bulk_g2s(smem_u32(b_s + (size_t)i * B_STAGE), wsrc + (size_t)i * B_STAGE, B_STAGE, b_full);
+      resident_weights(smem_u32(b_s), wsrc, (uint32_t)total * B_STAGE, b_full);
     }
     if (warp == kWWarp) pdl_wait();      // (skipped above for the weight warp) the coefficient table comes from an earlier kernel
     __syncwarp();
@@ -920,7 +930,9 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
               tc_fence_after();
               const uint32_t b_lo = b_lo0 + (uint32_t)(rb.s * (B_STAGE >> 4));
               const bool extra = tap == TAPS;   // fused 1x1 on the centre-tap view, second accumulator
-              const int ky = extra ? KS / 2 : (MX ? tap : tap / KS), kx = extra ? KS / 2 : (MX ? 0 : tap - ky * KS);
+              int tapr = tap;
+              if (KS == 3 && !MX && p.rot && !extra) { tapr = tap + (int)(blockIdx.x % TAPS); if (tapr >= TAPS) tapr -= TAPS; }
+              const int ky = extra ? KS / 2 : (MX ? tapr : tapr / KS), kx = extra ? KS / 2 : (MX ? 0 : tapr - ky * KS);
               const uint32_t a_t = a_lo + (uint32_t)(ky * G::PITCH + kx) * tap16;
               if (elect_one()) {
                 if (extra) {
@@ -966,17 +978,20 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
       const int total = p.nchunks * TAPSW;
       if (p.resident) {
         mbar_arrive_expect_tx(b_full, (uint32_t)total * B_STAGE);
-        for (int i = 0; i < total; ++i) bulk_g2s(smem_u32(b_s + (size_t)i * B_STAGE), wsrc + (size_t)i * B_STAGE, B_STAGE, b_full);
+        resident_weights(smem_u32(b_s), wsrc, (uint32_t)total * B_STAGE, b_full);
       } else {
         Ring rb;
         const int my_tiles = my_tile_count(p);
         for (int it = 0; it < my_tiles; it += MT) {
-          for (int i = 0; i < total; ++i) {
-            mbar_wait(b_empty + 8 * rb.s, rb.ph ^ 1);
-            mbar_arrive_expect_tx(b_full + 8 * rb.s, B_STAGE);
-            bulk_g2s(smem_u32(b_s + rb.s * B_STAGE), wsrc + (size_t)i * B_STAGE, B_STAGE, b_full + 8 * rb.s);
-            rb.advance(SB);
-          }
+          for (int c = 0, i = 0; c < p.nchunks; ++c)
+            for (int tap = 0; tap < TAPSW; ++tap, ++i) {
+              int src = i;
+              if (KS == 3 && !MX && p.rot && tap < TAPS) { int tr = tap + (int)(blockIdx.x % TAPS); if (tr >= TAPS) tr -= TAPS; src = c * TAPSW + tr; }
+              mbar_wait(b_empty + 8 * rb.s, rb.ph ^ 1);
+              mbar_arrive_expect_tx(b_full + 8 * rb.s, B_STAGE);
+              bulk_g2s(smem_u32(b_s + rb.s * B_STAGE), wsrc + (size_t)src * B_STAGE, B_STAGE, b_full + 8 * rb.s);
+              rb.advance(SB);
+            }
         }
       }
     }
@@ -1159,6 +1174,12 @@ int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
   p.resident = layout<NT, KS, KC>(p, sa, total) <= limit ? 1 : 0;
   p.nb_stages = p.resident ? total : SB;
   {
+    static int rot_env = -1;   // env LD_CONV_ROT=1: rotated tap order per CTA.  MEASURED: no effect (38.9 vs 39.1 us, 256 -> 256 at 32 x 32 x 32): the
+                               // L2 is not hot-spotted by 148 CTAs reading the same stage; off by default (canonical accumulation order)
+    if (rot_env < 0) { const char* e = getenv("LD_CONV_ROT"); rot_env = e ? atoi(e) : 0; }
+    p.rot = (!p.resident && rot_env) ? 1 : 0;
+  }
+  {
     static int xh_env = -1;   // env LD_CONV_XHELP=0: four transform warps only (A/B aid)
     if (xh_env < 0) { const char* e = getenv("LD_CONV_XHELP"); xh_env = e ? atoi(e) : 1; }
     p.xhelp = (p.tma_in && p.xf == 1 && p.swz && p.resident && KS == 3 && !MX && xh_env) ? 1 : 0;
@@ -1169,7 +1190,10 @@ int launch_one(KParams& p, int ntiles_y, cudaStream_t s) {
   static int mt_env = -1;   // env LD_CONV_MT=1 disables (A/B aid)
   if (mt_env < 0) { const char* e = getenv("LD_CONV_MT"); mt_env = e ? atoi(e) : 2; }
   // (not with the in-place normalise mode: its single epilogue warp-group would drain both accumulators back to back -- measured slower)
-  p.mt = (p.tma_in && !p.resident && NT >= 128 && KS == 3 && !p.dual && p.xf != 1 && mt_env == 2) ? 2 : 1;
+  // (NT = 256: with the cheap swizzled activation loads a single tile per weight pass is faster again -- 35.3 vs 38.8 us for 256 -> 256 at
+  //  32 x 32 x 32: the epilogue of one tile overlaps the MMAs of the next, and the bulk copies of the filter (90 B/clk per SM in 32 KB pieces,
+  //  tests/micro/tma_rate.cu) hide behind the MMAs either way; NT = 128 keeps the pairs: 38.8 vs 45.4 us; env LD_CONV_MT=3 forces pairs)
+  p.mt = (p.tma_in && !p.resident && (NT == 128 || (NT >= 128 && mt_env == 3)) && KS == 3 && !p.dual && p.xf != 1 && mt_env >= 2) ? 2 : 1;
   size_t smem = layout<NT, KS, KC>(p, sa, p.nb_stages);
   if (smem > (size_t)cfg().max_smem) { sa = 3; p.mt = 1; smem = layout<NT, KS, KC>(p, sa, p.nb_stages); }   // pairs need four activation stages
   p.nacc = (p.mt == 2 && NT == 256) ? 1 : 2;

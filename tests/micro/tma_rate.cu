@@ -4,18 +4,13 @@
 //   0: (8 ch, W, H, C/8, N) box (8, 10, 18, 4, 1), no swizzle      -- the kernel's K-major operand image, 720 rows of 16 B
 //   1: (C, W, H, N) box (32, 10, 18, 1), no swizzle                -- 180 rows of 64 B
 //   2: same box, SWIZZLE_64B
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../../localdiffusion_hallucination_b200/csrc tma_rate.cu -o tma_rate -lcuda
+// A second part times cp.async.bulk (1-D) copies of 2 .. 32 KB out of an L2-resident buffer: ~367 clk per copy and issuing CTA whatever the size.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I../../localdiffusion_hallucination_b200/csrc tma_rate.cu -o tma_rate
 #include <cstdio>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include "ld_tc_common.cuh"
 using namespace ld::tc;
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const void* map, int c0, int c1, int c2, int c3, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst_smem),
-               "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
-               : "memory");
-}
 
 __global__ void __launch_bounds__(128) k(const __grid_constant__ CUtensorMap map, int variant, int ntiles, int tiles_x, int tiles_y, int stages,
                                          long long* out) {
@@ -40,6 +35,31 @@ __global__ void __launch_bounds__(128) k(const __grid_constant__ CUtensorMap map
     for (; done < mine; ++done) {
       mbar_wait(b0 + 8 * (done % stages), (done / stages) & 1);
       if (issued < mine) { issue(issued); ++issued; }
+    }
+    out[blockIdx.x] = clock64() - t0;
+  }
+}
+
+// cp.async.bulk (1-D) of `chunk`-byte pieces out of an L2-resident buffer of `total` bytes, ring of `stages` buffers
+__global__ void __launch_bounds__(128) kb(const uint8_t* src, int total, int chunk, int stages, int reps, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[8];
+  const uint32_t b0 = smem_u32(bars);
+  if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) mbar_init(b0 + 8 * i, 1); fence_barrier_init(); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int n = total / chunk * reps;
+    const long long t0 = clock64();
+    int issued = 0, done = 0;
+    auto issue = [&](int i) {
+      const int s = i % stages;
+      mbar_arrive_expect_tx(b0 + 8 * s, chunk);
+      bulk_g2s(smem_u32(smem) + s * chunk, src + (size_t)(i % (total / chunk)) * chunk, chunk, b0 + 8 * s);
+    };
+    for (; issued < n && issued < stages; ++issued) issue(issued);
+    for (; done < n; ++done) {
+      mbar_wait(b0 + 8 * (done % stages), (done / stages) & 1);
+      if (issued < n) { issue(issued); ++issued; }
     }
     out[blockIdx.x] = clock64() - t0;
   }
@@ -92,6 +112,26 @@ int main() {
         printf("variant %d  ctas/SM=%d stages=%d: %7.1f us  (%.0f clk per tile per SM, %.0f GB/s of tensor bytes)\n", variant, cps, stages, ms * 1e3,
                avg / ((double)ntiles / sms), (double)N * H * W * C * 2 / (ms * 1e-3) * 1e-9);
       }
+  }
+  // bulk copies: the weight stream of the 256 -> 256 convolution (1.18 MB per CTA in 32 KB stages, every CTA reads the same bytes)
+  {
+    const int total = 36 * 32768;
+    uint8_t* wsrc; cudaMalloc(&wsrc, total); cudaMemset(wsrc, 1, total);
+    cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int chunk : {65536, 32768, 16384, 8192, 4096, 2048})
+      for (int stages : {4})
+        for (int ctas : {148, 296}) {               // 296: two co-resident CTAs per SM (<= 100 KB each)
+          if (stages * chunk > (ctas == 296 ? 100 : 200) * 1024) { if (ctas == 296) continue; }
+          if (stages * chunk > 200 * 1024) continue;
+          kb<<<ctas, 128, stages * chunk>>>(wsrc, total, chunk, stages, 2, d);
+          cudaDeviceSynchronize();
+          kb<<<ctas, 128, stages * chunk>>>(wsrc, total, chunk, stages, 2, d);
+          if (cudaDeviceSynchronize() != cudaSuccess) { printf("bulk: %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
+          static long long h[1024]; cudaMemcpy(h, d, ctas * 8, cudaMemcpyDeviceToHost);
+          double avg = 0; for (int i = 0; i < ctas; ++i) avg += (double)h[i]; avg /= ctas;
+          printf("bulk copy chunk %5d B  stages=%d  CTAs=%3d: %6.1f B/clk per CTA, %6.1f clk per copy per CTA\n", chunk, stages, ctas,
+                 2.0 * total / avg, avg / (2.0 * total / chunk));
+        }
   }
   return 0;
 }
