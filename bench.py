@@ -345,7 +345,7 @@ def dominant_kernel_roofline(lib, dev, a, hbm, src):
     if N == 32 and S == 256 and os.path.isfile(tp):  # ncu captures taken on exactly these launch shapes
         t = json.load(open(tp))
         traffic, tsrc = t["traffic_bytes_per_launch_weighted"], t["source"]
-    return {"kernel": "conv_tc_kernel<32,3,32> (3x3 tcgen05 conv, 32 output channels, %dx%dx%d; TMA in, TMA out), launch-weighted over its "
+    return {"kernel": "conv_tc_kernel<32,3,32> (3x3 tcgen05 conv, 32 output channels, %dx%dx%d; swizzled TMA in, register or TMA stores out), launch-weighted over its "
                       "four in-situ variants" % (N, S, S), "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
             "traffic": traffic, "traffic_source": tsrc, "variants": rows, "peak_source": src,
             "algorithmic_bytes_per_launch": tot_b / sum(v[5] for v in variants)}
