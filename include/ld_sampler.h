@@ -215,7 +215,8 @@ LD_API int64_t ld_workspace_bytes(const ld_handle* h);
  *   "la_exact"  (default 0)  LinearAttention through the exact-max kernels (the engine switches to them by itself when the fused
  *                            kernels' analytic soft-max shift underflows, see ld_sample);
  *   "up2"       (default 1)  nearest x2 up-sampling folded into the conv filter; 0 = replicate-on-load kernel;
- *   "pdl"       (default 0)  programmatic dependent launch between the kernels of a timestep (measured slower);
+ *   "pdl"       (default 0)  programmatic dependent launch: 1 between all kernels of a timestep (measured slower), 2 only for the
+ *                            launches that follow a tiny kernel (measured equal within noise);
  *   "attn_simt", "debug_keep", "use_tc" (before ld_finalize_weights): test aids. */
 LD_API int ld_set_option(ld_handle* h, const char* name, int64_t value);
 /* Current value of a tunable ("la_exact" reads 1 once the engine has switched LinearAttention to the exact-max kernels). */

@@ -1332,6 +1332,7 @@ __global__ void gn_coef_kernel(const double* __restrict__ stats, const float* __
 int gn_coef_launch(const double* stats, const float* gamma, const float* beta, const float* film, int film_stride, int G, int C, int N,
                    long long HW, float eps, float* ab, cudaStream_t s) {
   launch_k(gn_coef_kernel, dim3(N), dim3(C < 256 ? C : 256), 0, s, true, stats, gamma, beta, film, film_stride, G, C, (double)HW * (C / G), eps, ab);
+  pdl_after_small() = 1;
   return 1;
 }
 

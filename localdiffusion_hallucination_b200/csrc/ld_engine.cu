@@ -27,8 +27,10 @@
 namespace ld {
 
 int& pdl_flag() {
-  // measured in-process on the bench workload (tools/gpu_ab.py pdl=0,1): 5.21 ms per timestep without, 5.55 ms with -- the early-scheduled
-  // CTAs of the next kernel start at different times on different SMs and skew the static tile split of the persistent kernels.  Off by default.
+  // measured in-process on the bench workload (tools/gpu_ab.py): every kernel (1): 5.21 ms per timestep without, 5.55 ms with -- the
+  // early-scheduled CTAs of the next kernel start at different times on different SMs and skew the static tile split of the persistent
+  // kernels; only the launches that follow a tiny kernel (2, ld_launch.cuh): 4.71 -> 4.61, 4.66 -> 4.67, 4.67 -> 4.68 ms in three
+  // alternating runs (minima 1 % lower each time): inside the noise, so the default stays off.
   static int v = [] { const char* e = getenv("LD_PDL"); return e ? atoi(e) : 0; }();
   return v;
 }
@@ -1939,7 +1941,7 @@ int ld_set_option(ld_handle* h, const char* name, int64_t value) {
   else if (!strcmp(name, "debug_keep")) E.opt_debug_keep = value;
   else if (!strcmp(name, "la_exact")) E.opt_la_exact = value;
   else if (!strcmp(name, "attn_simt")) E.opt_attn_simt = value;
-  else if (!strcmp(name, "pdl")) pdl_flag() = value != 0;      // process-wide: programmatic dependent launch (ld_launch.cuh)
+  else if (!strcmp(name, "pdl")) pdl_flag() = (int)value;      // process-wide: programmatic dependent launch, 1 all kernels, 2 only after tiny kernels (ld_launch.cuh)
   else if (!strcmp(name, "up2")) E.opt_up2 = value;
   else if (!strcmp(name, "use_tc")) { if (E.finalized) return fail(LD_ERR_STATE, "use_tc must be set before finalize"); E.use_tc = value != 0 && E.bf; }
   else return fail(LD_ERR_INVALID, "unknown option '%s'", name);

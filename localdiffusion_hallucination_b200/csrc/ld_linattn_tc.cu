@@ -431,11 +431,11 @@ __global__ void __launch_bounds__(256) la_fold_kernel(const float* __restrict__ 
                                                       unsigned int* __restrict__ flag) {
   extern __shared__ float zs[];      // [32 d][C]: Z[(h,d)][c] * 32^-0.5 / ksum[(h,d)]; then the 32-column slice of U_h this block needs, [C c][32 c']
   const int h = blockIdx.x, n = blockIdx.y, cz = blockIdx.z, hid = (int)gridDim.x * 32;
-  if (threadIdx.x == 0) pdl_trigger();
   const float* u = Ut + (size_t)h * C * C + cz * 32;
   float* us = zs + 32 * C;
   const int lane = threadIdx.x & 31, dq = threadIdx.x >> 5;     // thread = (c' = 32 cz + lane, 4 consecutive d)
   for (int c = dq; c < C; c += 8) us[c * 32 + lane] = u[(size_t)c * C + lane];   // constants: before the wait on pass A
+  if (threadIdx.x == 0) pdl_trigger();
   pdl_wait();
   __shared__ float inv[32];
   if (threadIdx.x < 32) {
@@ -804,6 +804,7 @@ int launch_c(const LinAttnTcW& w, const LinAttnTcArgs& a, cudaStream_t s) {
   if (only != 2) launch_k(la_ctx_kernel<C>, dim3(slA, a.N, HG), dim3(kThreads), CtxCfg<C>::SMEM, s, true, cp);
   launch_k(la_fold_kernel, dim3(4 * HG, a.N, C / 32), dim3(256), 64 * C * sizeof(float), s, true, (const float*)a.Z, (const float*)a.ksum, (const float*)w.Ut,
            (__nv_bfloat16*)a.Mn, C, a.flag);
+  pdl_after_small() = 1;
   OutParams op{(const __nv_bfloat16*)a.x, (const __nv_bfloat16*)w.wq, (const __nv_bfloat16*)a.Mn, w.bout, w.g2,
                (__nv_bfloat16*)a.out, a.HW, slB, w.q_use_max, flatB ? 1 : 0, a.N};
   if (only != 1) launch_k(la_out_kernel<C, HG>, flatB ? dim3(ctasB, 1) : dim3(slB, a.N), dim3(kThreads), OutCfg<C, HG>::SMEM, s, true, op);
