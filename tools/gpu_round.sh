@@ -45,6 +45,9 @@ if has ncuxf; then   # only the normalise-on-load and plain variants, with sourc
   cap conv32_xf conv_tc_kernel 2 src python tools/gpu_conv_pro_one.py
   cap conv32_plain conv_tc_kernel 3 src python tools/gpu_conv_one.py 32 0 256 32 3 0 32
 fi
+if has ncu64; then   # 64 -> 64 at 128 x 128
+  cap conv64_plain conv_tc_kernel 3 src python tools/gpu_variant_shape.py 0 64 0 32 128 64
+fi
 if has ncu7; then   # only the init conv
   cap conv7 conv7_ 1 nosrc python tools/gpu_profile_ops.py 32 256 mri 2
 fi
