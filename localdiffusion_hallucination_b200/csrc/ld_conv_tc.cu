@@ -808,13 +808,20 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
               const int cidx = nbase + j0, q = cidx / p.ps, c = cidx - q * p.ps;
               o = ((((size_t)img * (2 * p.H) + 2 * ogy + (q >> 1)) * (2 * p.W)) + 2 * ogx + (q & 1)) * p.ps + c;
             }
-            *reinterpret_cast<uint4*>(p.dst + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(p.dst + o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            // one 32-byte store per 16 channels: a lane fills a whole sector (two 16-byte stores left every sector half written per
+            // instruction -- 1024 sector operations per 64-channel tile, the epilogue-only knock-out ran at 2245 clk per tile)
+            // (the register-statistics instantiation keeps 16-byte stores: it takes this path only under LD_CONV_DIRECT=2, and its
+            //  register allocation -- 80-register budget -- measured 3 % slower on the TMA store path with the wide store in its code)
+            if constexpr (!RS) st_global_v8(p.dst + o, pk);
+            else {
+              *reinterpret_cast<uint4*>(p.dst + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(p.dst + o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
           }
         }
       }
-      if (p.dual) {
-        // second accumulator: the 1x1 res_conv of the same input tile (ddpm.py:198,212), direct 16-byte stores
+      if (!RS && p.dual) {   // (the register-statistics instantiation never runs dual launches)
+        // second accumulator: the 1x1 res_conv of the same input tile (ddpm.py:198,212), direct 32-byte stores
 #pragma unroll (NT <= 64 ? 2 : 1)
         for (int j1 = 0; j1 < NT; j1 += 32) {
           uint32_t r32[32];
@@ -824,16 +831,16 @@ __global__ void __launch_bounds__(Roles<LEAN>::kThreads, Roles<LEAN>::kMinCtas) 
           if (opix >= 0 && !(p.dbg & 4)) {
             __nv_bfloat16* o2 = p.dst2 + (size_t)opix * p.Cout + nbase + j1;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint32_t pk[4];
+            for (int c = 0; c < 4; c += 2) {
+              uint32_t pk[8];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
+              for (int j = 0; j < 8; ++j) {
                 const int cj = j1 + 8 * c + 2 * j;
                 const float b0 = (NT <= 64 && p.bias_const) ? p.bias_c[64 + (NT <= 64 ? cj : 0)] : bias_s[NT + cj];
                 const float b1 = (NT <= 64 && p.bias_const) ? p.bias_c[64 + (NT <= 64 ? cj + 1 : 0)] : bias_s[NT + cj + 1];
                 pk[j] = pack_bf16x2(__uint_as_float(r32[8 * c + 2 * j]) + b0, __uint_as_float(r32[8 * c + 2 * j + 1]) + b1);
               }
-              *reinterpret_cast<uint4*>(o2 + 8 * c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              st_global_v8(o2 + 8 * c, pk);
             }
           }
         }
