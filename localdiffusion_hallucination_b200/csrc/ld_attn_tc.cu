@@ -243,11 +243,11 @@ __global__ void __launch_bounds__(kThreads, 2) attn_tc_kernel(const AttnParams p
       const float inv = 1.0f / l;
       __nv_bfloat16* dst = p.out + ((size_t)img * p.n + tok) * (p.heads * 32) + h * 32;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t w[4];
+      for (int c = 0; c < 2; ++c) {   // 32-byte stores
+        uint32_t w[8];
 #pragma unroll
-        for (int jx = 0; jx < 4; ++jx) w[jx] = pack_bf16x2(o[8 * c + 2 * jx] * inv, o[8 * c + 2 * jx + 1] * inv);
-        *reinterpret_cast<uint4*>(dst + 8 * c) = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int jx = 0; jx < 8; ++jx) w[jx] = pack_bf16x2(o[16 * c + 2 * jx] * inv, o[16 * c + 2 * jx + 1] * inv);
+        st_global_v8(dst + 16 * c, w);
       }
     }
   }

@@ -701,15 +701,15 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
         if (px < hw_lim) {
           const float inv = rsqrtf(fmaxf(ss, 1e-24f));            // to_out RMSNorm (ddpm.py:231,251)
 #pragma unroll
-          for (int j0 = 0; j0 < C; j0 += 8) {
-            const uint32_t xi[4] = {xv[j0 / 8].x, xv[j0 / 8].y, xv[j0 / 8].z, xv[j0 / 8].w};
-            uint32_t o4[4];
+          for (int j0 = 0; j0 < C; j0 += 16) {   // 32-byte stores: a lane fills a whole sector of its pixel row
+            const uint32_t xi[8] = {xv[j0 / 8].x, xv[j0 / 8].y, xv[j0 / 8].z, xv[j0 / 8].w, xv[j0 / 8 + 1].x, xv[j0 / 8 + 1].y, xv[j0 / 8 + 1].z, xv[j0 / 8 + 1].w};
+            uint32_t o8[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 8; ++j) {
               const float2 xf = unpack_bf16x2(xi[j]);
-              o4[j] = pack_bf16x2(fmaf(o[j0 + 2 * j] * inv, bg_s[C + j0 + 2 * j], xf.x), fmaf(o[j0 + 2 * j + 1] * inv, bg_s[C + j0 + 2 * j + 1], xf.y));
+              o8[j] = pack_bf16x2(fmaf(o[j0 + 2 * j] * inv, bg_s[C + j0 + 2 * j], xf.x), fmaf(o[j0 + 2 * j + 1] * inv, bg_s[C + j0 + 2 * j + 1], xf.y));
             }
-            *reinterpret_cast<uint4*>(orow + j0) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+            st_global_v8(orow + j0, o8);
           }
         }
       } else {
