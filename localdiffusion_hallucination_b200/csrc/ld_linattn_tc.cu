@@ -679,10 +679,10 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
       __nv_bfloat16* orow = p.out + ((size_t)n * p.HW + px) * C;
       if constexpr (C <= 64) {
         // one sweep: the whole row stays in registers; the residual row of x is requested before the accumulator is read
-        uint4 xv[C / 8];
+        uint32_t xw[C / 2];                                   // the residual row, 32 bytes per load
         if (px < hw_lim) {
 #pragma unroll
-          for (int j = 0; j < C / 8; ++j) xv[j] = __ldg(reinterpret_cast<const uint4*>(xr) + j);
+          for (int j = 0; j < C / 16; ++j) ld_global_nc_v8(xr + 16 * j, xw + 8 * j);
         }
         mbar_wait(d2_full + 8 * g, u & 1);
         tc_fence_after();
@@ -702,11 +702,10 @@ __global__ void __launch_bounds__(kThreads, 1) la_out_kernel(const OutParams p) 
           const float inv = rsqrtf(fmaxf(ss, 1e-24f));            // to_out RMSNorm (ddpm.py:231,251)
 #pragma unroll
           for (int j0 = 0; j0 < C; j0 += 16) {   // 32-byte stores: a lane fills a whole sector of its pixel row
-            const uint32_t xi[8] = {xv[j0 / 8].x, xv[j0 / 8].y, xv[j0 / 8].z, xv[j0 / 8].w, xv[j0 / 8 + 1].x, xv[j0 / 8 + 1].y, xv[j0 / 8 + 1].z, xv[j0 / 8 + 1].w};
             uint32_t o8[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float2 xf = unpack_bf16x2(xi[j]);
+              const float2 xf = unpack_bf16x2(xw[j0 / 2 + j]);
               o8[j] = pack_bf16x2(fmaf(o[j0 + 2 * j] * inv, bg_s[C + j0 + 2 * j], xf.x), fmaf(o[j0 + 2 * j + 1] * inv, bg_s[C + j0 + 2 * j + 1], xf.y));
             }
             st_global_v8(orow + j0, o8);
